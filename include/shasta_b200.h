@@ -1,0 +1,128 @@
+/*
+ * shasta_b200 — C ABI of the B200-native implementation of Shasta's overlap-detection hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. Each entry point
+ * cites the reference interface it replaces (paths relative to the chanzuckerberg/shasta tree).
+ * The shared library is shasta_b200/lib/libshasta_b200.so (sm_100a only; there is no CPU fallback:
+ * every compute entry point returns SHB_ERR_CUDA when no device is usable).
+ *
+ * Record layouts:
+ *   markers   : toc uint64[2R+1], row index = (readId<<1)|strand (src/ReadId.hpp:35-155);
+ *               data = 7-byte CompressedMarker records {uint32 kmerId, uint24 position}
+ *               (src/Marker.hpp:56-69), i.e. the payload of Data/Markers.toc + Data/Markers.data
+ *   readFlags : 1 byte per read, bit0 = isPalindromic (src/ReadFlags.hpp:10-30)
+ *   candidates: 12-byte OrientedReadPair {uint32 readIds[2]; uint8 isSameStrand; 3 pad}
+ *               (src/OrientedReadPair.hpp:18-86); pad bytes are written as 0
+ *   stats     : uint64[R][3] = ReadLowHashStatistics (src/LowHash0.cpp:386-393)
+ */
+#ifndef SHASTA_B200_H
+#define SHASTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SHB_OK = 0,
+    SHB_ERR_INVALID = 1,        /* bad argument; the message mirrors the reference's runtime_error text */
+    SHB_ERR_CUDA = 2,           /* CUDA failure or no sm_100 device */
+    SHB_ERR_OOM = 3,
+    SHB_ERR_STATE = 4           /* call order violated (e.g. markers not uploaded) */
+} shb_status;
+
+typedef struct shb_context shb_context;
+
+/* Message of the last error on the calling thread (std::runtime_error::what() equivalent). */
+const char* shb_last_error(void);
+
+/* One context per GPU / per process rank. device = CUDA ordinal. */
+shb_status shb_context_create(int device, shb_context** ctx);
+void shb_context_destroy(shb_context* ctx);
+
+/* Free a host buffer returned by this library. */
+void shb_free(void* hostPtr);
+
+/* ------------------------------------------------------------------------------------------
+ * Marker upload.  Replaces Assembler::accessMarkers (src/AssemblerMarkers.cpp, Data/Markers.*) +
+ * LowHash0::createKmerIds (src/LowHash0.cpp:261-308): the 7-byte AoS records are streamed to the
+ * device and converted to a uint32 k-mer id SoA that stays resident in HBM.
+ *
+ * readCountTotal = R of the whole assembly; [readBegin, readEnd) = the reads whose marker rows are
+ * passed here (toc has 2*(readEnd-readBegin)+1 entries and is relative: toc[0] == 0). A single-GPU
+ * run passes readBegin = 0, readEnd = readCountTotal. readFlags has readCountTotal entries.
+ * totalMarkerCount = markers.totalSize() over ALL reads (enters the bucket-count rule,
+ * src/LowHash0.cpp:73-76).
+ */
+shb_status shb_set_markers(shb_context* ctx,
+                           uint64_t readCountTotal, uint64_t readBegin, uint64_t readEnd,
+                           const uint64_t* toc, const uint8_t* markerData7,
+                           const uint8_t* readFlags, uint64_t totalMarkerCount);
+
+/* Same, with the k-mer ids already on the device (uint32 SoA, device pointer) — used by the
+ * synthetic generator of bench.py. The library takes a copy-free reference; the caller keeps the
+ * allocation alive until the context is destroyed or markers are replaced. tocHost is host memory. */
+shb_status shb_set_markers_device(shb_context* ctx,
+                                  uint64_t readCountTotal, uint64_t readBegin, uint64_t readEnd,
+                                  const uint64_t* tocHost, const uint32_t* kmerIdsDevice,
+                                  const uint8_t* readFlagsHost, uint64_t totalMarkerCount);
+
+/* ------------------------------------------------------------------------------------------
+ * LowHash0.  Replaces Assembler::findAlignmentCandidatesLowHash0 (src/AssemblerLowHash.cpp:10-55,
+ * declaration src/Assembler.hpp:688-699; Python binding src/PythonModule.cpp:218-228).
+ * Field for field the reference's arguments; threadCount is accepted and ignored.
+ */
+typedef struct {
+    uint64_t m;
+    double   hashFraction;
+    uint64_t minHashIterationCount;
+    double   alignmentCandidatesPerRead;
+    uint64_t log2MinHashBucketCount;
+    uint64_t minBucketSize;
+    uint64_t maxBucketSize;
+    uint64_t minFrequency;
+    uint64_t threadCount;
+    /* 0: candidate counts are merged once after the last iteration (fast path; needs
+     *    minHashIterationCount != 0).  1: merged after every iteration, which also yields the
+     *    per-iteration "high frequency / total" summary of src/LowHash0.cpp:185-196.
+     *    minHashIterationCount == 0 forces mode 1. */
+    uint32_t perIterationMerge;
+    uint32_t reserved;
+} shb_lowhash_params;
+
+typedef struct {
+    uint64_t iterations;            /* iterations executed */
+    uint64_t log2BucketCount;       /* after the rule of src/LowHash0.cpp:79-98 */
+    uint64_t lowHashCount;          /* total low hashes over all iterations */
+    uint64_t pairCount;             /* candidate pair hits generated over all iterations */
+    uint64_t candidateCount;
+    double   sweepMs;               /* device time of the hash sweep kernels (CUDA events) */
+    double   totalMs;               /* device time of the whole call */
+    uint64_t sweepLaunches;         /* number of sweep kernel launches */
+    uint64_t kernelLaunches;        /* all kernels launched by the call */
+} shb_lowhash_result;
+
+/* One-shot single-GPU call on the markers held by ctx.
+ *   candidates   : *candidates receives a host buffer of 12-byte OrientedReadPair records in the
+ *                  reference order (readId0, then (readId1, strand)); free with shb_free.
+ *   stats        : caller-allocated uint64[readCountTotal*3], or NULL.
+ *   iterSummary  : optional uint64[2*maxIterSummary] (highFrequency,total) per iteration; only
+ *                  filled in perIterationMerge mode.
+ */
+shb_status shb_lowhash0(shb_context* ctx, const shb_lowhash_params* params,
+                        void** candidates, uint64_t* candidateCount,
+                        uint64_t* stats, uint64_t* iterSummary, uint64_t maxIterSummary,
+                        shb_lowhash_result* result);
+
+/* Convenience: host buffers in, host buffers out (upload + LowHash0). This is the call a
+ * reference maintainer binds. */
+shb_status shb_find_alignment_candidates_lowhash0(
+    shb_context* ctx, uint64_t readCount, const uint64_t* toc, const uint8_t* markerData7,
+    const uint8_t* readFlags, const shb_lowhash_params* params,
+    void** candidates, uint64_t* candidateCount, uint64_t* stats, shb_lowhash_result* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

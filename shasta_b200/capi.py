@@ -1,0 +1,172 @@
+"""ctypes binding of the C ABI (include/shasta_b200.h -> shasta_b200/lib/libshasta_b200.so).
+
+There is no CPU fallback: importing this module without the built library, or creating a Context
+without a B200, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libshasta_b200.so")
+
+
+class ShastaB200Error(RuntimeError):
+    """Mirrors the std::runtime_error the reference throws (src/SHASTA_ASSERT.hpp, src/LowHash0.cpp:86)."""
+
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+class LowHashParams(C.Structure):
+    _fields_ = [("m", C.c_uint64), ("hashFraction", C.c_double), ("minHashIterationCount", C.c_uint64),
+                ("alignmentCandidatesPerRead", C.c_double), ("log2MinHashBucketCount", C.c_uint64),
+                ("minBucketSize", C.c_uint64), ("maxBucketSize", C.c_uint64), ("minFrequency", C.c_uint64),
+                ("threadCount", C.c_uint64), ("perIterationMerge", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class LowHashResult(C.Structure):
+    _fields_ = [("iterations", C.c_uint64), ("log2BucketCount", C.c_uint64), ("lowHashCount", C.c_uint64),
+                ("pairCount", C.c_uint64), ("candidateCount", C.c_uint64), ("sweepMs", C.c_double),
+                ("totalMs", C.c_double), ("sweepLaunches", C.c_uint64), ("kernelLaunches", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ShastaB200Error(2, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                     "(the CUDA extension is required; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.shb_last_error.restype = C.c_char_p
+        L.shb_context_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.shb_context_destroy.argtypes = [C.c_void_p]
+        L.shb_free.argtypes = [C.c_void_p]
+        L.shb_set_markers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.shb_set_markers_device.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.shb_lowhash0.argtypes = [C.c_void_p, C.POINTER(LowHashParams), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                   C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(LowHashResult)]
+        L.shb_find_alignment_candidates_lowhash0.argtypes = [
+            C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(LowHashParams),
+            C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(LowHashResult)]
+        _lib = L
+    return _lib
+
+
+def _check(status):
+    if status != 0:
+        raise ShastaB200Error(status, lib().shb_last_error().decode())
+
+
+def make_lowhash_params(m=4, hashFraction=0.01, minHashIterationCount=10, alignmentCandidatesPerRead=20.0,
+                        log2MinHashBucketCount=0, minBucketSize=0, maxBucketSize=10, minFrequency=2,
+                        threadCount=0, perIterationMerge=0):
+    return LowHashParams(m, hashFraction, minHashIterationCount, alignmentCandidatesPerRead, log2MinHashBucketCount,
+                         minBucketSize, maxBucketSize, minFrequency, threadCount, perIterationMerge, 0)
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Context:
+    """One per GPU (shb_context)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().shb_context_create(device, C.byref(self._h)))
+        self.read_count = 0
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            lib().shb_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_markers(self, toc, data7, flags, read_begin=0, read_end=None, read_count_total=None, total_marker_count=None):
+        toc = np.ascontiguousarray(toc, dtype=np.uint64)
+        data7 = np.ascontiguousarray(data7, dtype=np.uint8)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        n_local = (len(toc) - 1) // 2
+        if read_count_total is None:
+            read_count_total = n_local
+        if read_end is None:
+            read_end = read_begin + n_local
+        if total_marker_count is None:
+            total_marker_count = int(toc[-1])
+        _check(lib().shb_set_markers(self._h, read_count_total, read_begin, read_end, _ptr(toc), _ptr(data7), _ptr(flags), total_marker_count))
+        self.read_count = read_count_total
+
+    def set_markers_device(self, toc, kmer_ids_device_ptr, flags, keepalive=None, read_begin=0, read_end=None,
+                           read_count_total=None, total_marker_count=None):
+        toc = np.ascontiguousarray(toc, dtype=np.uint64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        n_local = (len(toc) - 1) // 2
+        if read_count_total is None:
+            read_count_total = n_local
+        if read_end is None:
+            read_end = read_begin + n_local
+        if total_marker_count is None:
+            total_marker_count = int(toc[-1])
+        _check(lib().shb_set_markers_device(self._h, read_count_total, read_begin, read_end, _ptr(toc),
+                                            C.c_void_p(kmer_ids_device_ptr), _ptr(flags), total_marker_count))
+        self._keep = keepalive
+        self.read_count = read_count_total
+
+    def lowhash0(self, params: LowHashParams, want_stats=True, max_iter_summary=0):
+        """Returns (candidates uint32[n,3] = (readId0, readId1, isSameStrand), stats uint64[R,3] | None,
+        iterSummary uint64[iters,2] | None, LowHashResult)."""
+        cand = C.c_void_p()
+        n = C.c_uint64()
+        res = LowHashResult()
+        stats = np.zeros((self.read_count, 3), np.uint64) if want_stats else None
+        summ = np.zeros((max_iter_summary, 2), np.uint64) if max_iter_summary else None
+        _check(lib().shb_lowhash0(self._h, C.byref(params), C.byref(cand), C.byref(n), _ptr(stats), _ptr(summ),
+                                  max_iter_summary, C.byref(res)))
+        out = _records_to_array(cand, n.value)
+        lib().shb_free(cand)
+        if summ is not None:
+            summ = summ[:min(res.iterations, max_iter_summary)]
+        return out, stats, summ, res
+
+    def find_alignment_candidates_lowhash0(self, toc, data7, flags, params: LowHashParams, want_stats=True):
+        """Host buffers in, host buffers out: the call a reference maintainer binds."""
+        toc = np.ascontiguousarray(toc, dtype=np.uint64)
+        data7 = np.ascontiguousarray(data7, dtype=np.uint8)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        R = (len(toc) - 1) // 2
+        cand = C.c_void_p()
+        n = C.c_uint64()
+        res = LowHashResult()
+        stats = np.zeros((R, 3), np.uint64) if want_stats else None
+        _check(lib().shb_find_alignment_candidates_lowhash0(self._h, R, _ptr(toc), _ptr(data7), _ptr(flags), C.byref(params),
+                                                           C.byref(cand), C.byref(n), _ptr(stats), C.byref(res)))
+        self.read_count = R
+        out = _records_to_array(cand, n.value)
+        lib().shb_free(cand)
+        return out, stats, res
+
+
+def _records_to_array(ptr, n):
+    """12-byte OrientedReadPair records -> uint32[n,3] with column 2 = isSameStrand (byte 0 of the third word)."""
+    if n == 0:
+        return np.zeros((0, 3), np.uint32)
+    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), (n, 3)).copy()
+    a[:, 2] &= 0xFF
+    return a

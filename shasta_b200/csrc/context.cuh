@@ -1,0 +1,41 @@
+// The per-GPU context behind the C ABI: device-resident markers and reusable workspaces.
+#pragma once
+
+#include "common.cuh"
+#include "primitives.cuh"
+
+#include <vector>
+
+struct shb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copyStream[2] = {nullptr, nullptr};
+
+    // ---- markers (a1, a4) -------------------------------------------------------------------
+    bool haveMarkers = false;
+    uint64_t readCountTotal = 0;        // R of the whole assembly
+    uint64_t readBegin = 0, readEnd = 0; // reads whose rows live on this GPU
+    uint64_t totalMarkerCount = 0;      // over all reads (bucket-count rule)
+    uint64_t localMarkerCount = 0;
+    shb::DeviceBuffer<uint32_t> kmerIdsOwned;
+    const uint32_t* kmerIds = nullptr;  // device, localMarkerCount entries (+ padding when owned)
+    shb::DeviceBuffer<uint64_t> toc;    // device, relative, 2*(readEnd-readBegin)+1 entries
+    shb::DeviceBuffer<uint8_t> readFlags; // device, readCountTotal entries
+    std::vector<uint64_t> tocHost;      // host copy of the relative toc
+    std::vector<uint8_t> readFlagsHost;
+
+    // ---- shared workspaces --------------------------------------------------------------------
+    shb::SortWorkspace sortWs;
+    shb::DeviceBuffer<uint32_t> scanWs;
+    shb::DeviceBuffer<unsigned long long> scalars;   // small device scratch for totals/counters
+
+    // ---- LowHash buffers (see lowhash.cu) -----------------------------------------------------
+    shb::DeviceBuffer<uint64_t> sweepKeys;  shb::DeviceBuffer<uint32_t> sweepVals;
+    shb::DeviceBuffer<uint64_t> entryKeysTmp; shb::DeviceBuffer<uint32_t> entryValsTmp;
+    shb::DeviceBuffer<uint32_t> flagsBuf, indexBuf, segStartBuf, countsBuf;
+    shb::DeviceBuffer<uint64_t> pairsA, pairsB;
+    shb::DeviceBuffer<uint64_t> accKeysA, accKeysB;
+    shb::DeviceBuffer<uint32_t> accValsA, accValsB;
+    shb::DeviceBuffer<unsigned long long> stats;
+    shb::DeviceBuffer<uint32_t> candidatesDev;
+};

@@ -1,0 +1,316 @@
+// LowHash0 device kernels (sm_100a). Reference: src/LowHash0.cpp (chanzuckerberg/shasta).
+//   extractKmerIdsKernel    <- LowHash0::createKmerIds            src/LowHash0.cpp:261-308
+//   lowhashSweepKernel      <- LowHash0::pass1ThreadFunction       src/LowHash0.cpp:314-360
+//                              + MurmurHash64A                     src/MurmurHash2.cpp:96-137
+//   bucket*Kernel           <- pass2 / pass3                       src/LowHash0.cpp:365-484
+//   candidate kernels       <- merge + final emission              src/LowHash0.cpp:204-214, 493-562
+#pragma once
+
+#include "common.cuh"
+
+namespace shb {
+
+// ---------------------------------------------------------------------------------------------
+// a4. 7-byte CompressedMarker AoS -> uint32 kmerId SoA.
+// The byte stream is read as aligned 32-bit words (coalesced), staged in shared memory, and each
+// k-mer id is re-assembled with a funnel shift. One block converts 1024 markers (7168 bytes).
+constexpr int kExtractThreads = 256;
+constexpr int kExtractMarkersPerBlock = 1024;
+
+static __global__ void __launch_bounds__(kExtractThreads)
+extractKmerIdsKernel(const uint32_t* __restrict__ words, uint64_t wordCount, uint64_t markerCount,
+                     uint32_t* __restrict__ kmerIds)
+{
+    constexpr int kWords = kExtractMarkersPerBlock * 7 / 4;          // 1792
+    __shared__ uint32_t sm[kWords + 1];
+    const uint64_t wordBase = uint64_t(blockIdx.x) * kWords;
+    for(int w = threadIdx.x; w < kWords + 1; w += kExtractThreads) {
+        const uint64_t gw = wordBase + w;
+        sm[w] = (gw < wordCount) ? words[gw] : 0u;
+    }
+    __syncthreads();
+    const uint64_t markerBase = uint64_t(blockIdx.x) * kExtractMarkersPerBlock;
+#pragma unroll
+    for(int i = 0; i < kExtractMarkersPerBlock / kExtractThreads; i++) {
+        const int local = i * kExtractThreads + threadIdx.x;
+        const uint64_t g = markerBase + local;
+        if(g < markerCount) {
+            const int byteOffset = local * 7;
+            const int w = byteOffset >> 2;
+            const int shift = (byteOffset & 3) * 8;
+            kmerIds[g] = __funnelshift_r(sm[w], sm[w + 1], shift);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a5. Hash sweep. Every marker position p is treated as the start of a feature (m consecutive
+// k-mer ids = 4m bytes); MurmurHash64A of the feature is evaluated for up to kMaxFusedIterations
+// seeds (= LowHash iterations, seed = 37*iteration) per pass over the k-mer ids: the per-block
+// mixing of the 64-bit words does not depend on the seed, so K iterations cost one read of the
+// k-mer ids and (m/2)*2 + 3K 64-bit multiplies per feature instead of K*(m+3).
+// Only hashes below the threshold (about hashFraction of them) look up which oriented read they
+// belong to (binary search in the toc) and whether the feature lies inside one non-palindromic read.
+constexpr int kSweepThreads = 256;
+constexpr int kSweepPositionsPerThread = 8;
+constexpr int kSweepTile = kSweepThreads * kSweepPositionsPerThread;      // 2048 positions per block
+constexpr int kMaxFusedIterations = 16;
+constexpr int kSweepStage = 128;          // staged low hashes per iteration per block before spilling
+constexpr int kMaxTemplatedM = 8;
+
+struct SweepArgs {
+    const uint32_t* kmerIds;        // local k-mer ids
+    uint64_t markerCount;           // local marker count
+    const uint64_t* toc;            // local toc, relative, orientedReadCount+1 entries
+    uint32_t orientedReadCount;     // local oriented reads
+    uint32_t orientedReadBase;      // global id of local oriented read 0
+    const uint8_t* readFlags;       // global, indexed by global readId
+    uint32_t m;
+    uint64_t hashThreshold;
+    uint64_t bucketMask;
+    uint32_t iterationBegin;
+    uint32_t iterationCount;        // <= kMaxFusedIterations
+    uint64_t* keys;                 // iterationCount slabs of `capacity` entries
+    uint32_t* vals;
+    uint64_t capacity;
+    unsigned long long* counts;     // [iterationCount]
+};
+
+__device__ __forceinline__ uint64_t murmurMix(uint64_t k)
+{
+    const uint64_t M = 0xc6a4a7935bd1e995ull;
+    k *= M;
+    k ^= k >> 47;
+    k *= M;
+    return k;
+}
+
+template<int MM> __global__ void __launch_bounds__(kSweepThreads)
+lowhashSweepKernel(const SweepArgs a)
+{
+    constexpr int kHalo = 2 * kMaxFusedIterations;       // >= any supported m (generic path caps m at 32)
+    __shared__ uint32_t sk[kSweepTile + kHalo];
+    __shared__ uint64_t stageKeys[kMaxFusedIterations][kSweepStage];
+    __shared__ uint32_t stageVals[kMaxFusedIterations][kSweepStage];
+    __shared__ uint32_t stageCount[kMaxFusedIterations];
+    __shared__ unsigned long long stageBase[kMaxFusedIterations];
+
+    const uint64_t M = 0xc6a4a7935bd1e995ull;
+    const uint32_t m = (MM > 0) ? uint32_t(MM) : a.m;
+    const uint64_t tileBase = uint64_t(blockIdx.x) * kSweepTile;
+
+    if(threadIdx.x < kMaxFusedIterations) stageCount[threadIdx.x] = 0;
+    for(int i = threadIdx.x; i < kSweepTile + kHalo; i += kSweepThreads) {
+        const uint64_t g = tileBase + i;
+        sk[i] = (g < a.markerCount) ? a.kmerIds[g] : 0u;
+    }
+    __syncthreads();
+
+    const uint32_t K = a.iterationCount;
+    const uint64_t lenTimesM = uint64_t(4u * m) * M;
+
+#pragma unroll 1
+    for(int slot = 0; slot < kSweepPositionsPerThread; slot++) {
+        const int local = slot * kSweepThreads + threadIdx.x;
+        const uint64_t p = tileBase + local;
+        if(p + m > a.markerCount) continue;
+
+        // Seed-independent part: mixed 64-bit blocks (little-endian pairs of k-mer ids) and tail.
+        uint64_t mixed[(MM > 0) ? ((MM / 2) > 0 ? (MM / 2) : 1) : 16];
+        const uint32_t blocks = m >> 1;
+        if(MM > 0) {
+#pragma unroll
+            for(int b = 0; b < MM / 2; b++) {
+                const uint64_t w = uint64_t(sk[local + 2*b]) | (uint64_t(sk[local + 2*b + 1]) << 32);
+                mixed[b] = murmurMix(w);
+            }
+        } else {
+            for(uint32_t b = 0; b < blocks; b++) {
+                const uint64_t w = uint64_t(sk[local + 2*b]) | (uint64_t(sk[local + 2*b + 1]) << 32);
+                mixed[b] = murmurMix(w);
+            }
+        }
+        const bool hasTail = (m & 1u) != 0;
+        const uint64_t tail = hasTail ? uint64_t(sk[local + m - 1]) : 0ull;
+
+        int resolved = 0;           // 0 = not looked up yet, 1 = valid feature, 2 = invalid
+        uint32_t orientedRead = 0;
+
+#pragma unroll 1
+        for(uint32_t s = 0; s < K; s++) {
+            const uint64_t seed = uint64_t(a.iterationBegin + s) * 37ull;
+            uint64_t h = seed ^ lenTimesM;
+            if(MM > 0) {
+#pragma unroll
+                for(int b = 0; b < MM / 2; b++) { h ^= mixed[b]; h *= M; }
+            } else {
+                for(uint32_t b = 0; b < blocks; b++) { h ^= mixed[b]; h *= M; }
+            }
+            if(hasTail) { h ^= tail; h *= M; }
+            h ^= h >> 47;
+            h *= M;
+            h ^= h >> 47;
+            if(h < a.hashThreshold) {
+                if(resolved == 0) {
+                    // Largest o with toc[o] <= p.
+                    uint32_t lo = 0, hi = a.orientedReadCount;
+                    while(hi - lo > 1) {
+                        const uint32_t mid = lo + ((hi - lo) >> 1);
+                        if(a.toc[mid] <= p) lo = mid; else hi = mid;
+                    }
+                    orientedRead = lo;
+                    const bool inside = (p + m <= a.toc[lo + 1]);
+                    const bool palindromic = (a.readFlags[(a.orientedReadBase + lo) >> 1] & 1u) != 0;
+                    resolved = (inside && !palindromic) ? 1 : 2;
+                }
+                if(resolved == 1) {
+                    const uint64_t key = ((h & a.bucketMask) << 32) | (h >> 32);
+                    const uint32_t val = a.orientedReadBase + orientedRead;
+                    const uint32_t li = atomicAdd(&stageCount[s], 1u);
+                    if(li < (uint32_t)kSweepStage) {
+                        stageKeys[s][li] = key;
+                        stageVals[s][li] = val;
+                    } else {
+                        // Staging full (pathological hashFraction or repeats): spill straight to HBM.
+                        const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
+                        if(gi < a.capacity) {
+                            a.keys[uint64_t(s) * a.capacity + gi] = key;
+                            a.vals[uint64_t(s) * a.capacity + gi] = val;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if(threadIdx.x < K) {
+        const uint32_t c = min(stageCount[threadIdx.x], (uint32_t)kSweepStage);
+        stageBase[threadIdx.x] = c ? atomicAdd(&a.counts[threadIdx.x], (unsigned long long)c) : 0ull;
+    }
+    __syncthreads();
+    for(uint32_t s = 0; s < K; s++) {
+        const uint32_t c = min(stageCount[s], (uint32_t)kSweepStage);
+        for(uint32_t li = threadIdx.x; li < c; li += kSweepThreads) {
+            const unsigned long long gi = stageBase[s] + li;
+            if(gi < a.capacity) {
+                a.keys[uint64_t(s) * a.capacity + gi] = stageKeys[s][li];
+                a.vals[uint64_t(s) * a.capacity + gi] = stageVals[s][li];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7/a8. Bucket inspection. Entries (key = bucketId<<32 | hashHigh, val = orientedReadId) are sorted
+// by bucketId; segStart delimits the buckets. One thread per entry e0:
+//   * classifies its bucket size (sparse / good / crowded) into readLowHashStatistics (pass2,
+//     src/LowHash0.cpp:386-393);
+//   * for buckets whose size is in [max(2,minBucketSize), maxBucketSize], visits the bucket and
+//     counts / emits (readId0, readId1, strand) for equal hashHigh and readId1 > readId0 (pass3,
+//     src/LowHash0.cpp:430-458).
+__device__ __forceinline__ uint32_t segmentOf(const uint32_t* flags, const uint32_t* segIndexExclusive, uint32_t i)
+{
+    return segIndexExclusive[i] + flags[i] - 1u;
+}
+
+template<bool EMIT> __global__ void __launch_bounds__(256)
+bucketPairsKernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n,
+                  const uint32_t* __restrict__ flags, const uint32_t* __restrict__ segIndexExclusive,
+                  const uint32_t* __restrict__ segStart,
+                  uint64_t minBucketSize, uint64_t maxBucketSize,
+                  unsigned long long* __restrict__ stats,          // COUNT pass only (may be null)
+                  unsigned long long* __restrict__ pairTotal,      // COUNT pass only: 64-bit total of all counts
+                  uint32_t* __restrict__ pairCounts,               // COUNT pass: out; EMIT pass: exclusive offsets in
+                  uint64_t* __restrict__ pairsOut)                 // EMIT pass
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    uint32_t count = 0;
+    if(active) {
+        const uint32_t seg = segmentOf(flags, segIndexExclusive, i);
+        const uint32_t begin = segStart[seg];
+        const uint32_t end = segStart[seg + 1];
+        const uint64_t size = end - begin;
+        const uint32_t oread0 = vals[i];
+        const uint32_t readId0 = oread0 >> 1;
+        if(!EMIT && stats) {
+            const int cls = (size < minBucketSize) ? 0 : ((size > maxBucketSize) ? 2 : 1);
+            atomicAdd(&stats[3ull * readId0 + cls], 1ull);
+        }
+        const uint64_t lowest = minBucketSize > 2 ? minBucketSize : 2;
+        uint64_t out = EMIT ? pairCounts[i] : 0;
+        if(size >= lowest && size <= maxBucketSize) {
+            const uint32_t hashHigh0 = uint32_t(keys[i]);
+            for(uint32_t j = begin; j < end; j++) {
+                if(uint32_t(keys[j]) != hashHigh0) continue;
+                const uint32_t oread1 = vals[j];
+                const uint32_t readId1 = oread1 >> 1;
+                if(readId1 <= readId0) continue;
+                if(EMIT) {
+                    const uint32_t strand = (oread0 ^ oread1) & 1u;        // 0 = same strand
+                    pairsOut[out++] = (uint64_t(readId0) << 32) | (uint64_t(readId1) << 1) | strand;
+                } else {
+                    count++;
+                }
+            }
+        }
+        if(!EMIT) pairCounts[i] = count;
+    }
+    if(!EMIT) {
+        // Exact 64-bit total (the per-entry offsets are 32 bit; the host checks the total fits).
+        uint32_t warpSum = count;
+#pragma unroll
+        for(int d = 16; d > 0; d >>= 1) warpSum += __shfl_down_sync(0xffffffffu, warpSum, d);
+        if((threadIdx.x & 31u) == 0 && warpSum) atomicAdd(pairTotal, (unsigned long long)warpSum);
+    }
+}
+
+// Sorted pair keys -> unique keys with multiplicities.
+static __global__ void uniqueCountsKernel(const uint64_t* __restrict__ sortedKeys, const uint32_t* __restrict__ segStart,
+                                   uint32_t numSegments, uint64_t* __restrict__ outKeys, uint32_t* __restrict__ outCounts)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= numSegments) return;
+    const uint32_t b = segStart[s];
+    outKeys[s] = sortedKeys[b];
+    outCounts[s] = segStart[s + 1] - b;
+}
+
+// Sorted (key,count) items with duplicate keys -> unique keys with summed counts.
+static __global__ void segmentSumKernel(const uint64_t* __restrict__ sortedKeys, const uint32_t* __restrict__ sortedCounts,
+                                 const uint32_t* __restrict__ segStart, uint32_t numSegments,
+                                 uint64_t* __restrict__ outKeys, uint32_t* __restrict__ outCounts)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= numSegments) return;
+    const uint32_t b = segStart[s], e = segStart[s + 1];
+    uint32_t sum = 0;
+    for(uint32_t j = b; j < e; j++) sum += sortedCounts[j];
+    outKeys[s] = sortedKeys[b];
+    outCounts[s] = sum;
+}
+
+// flags[i] = (uint16(count[i]) >= minFrequency)   — the frequency is a wrapping uint16 in the
+// reference (src/LowHash0.hpp:116, src/LowHash0.cpp:207,521).
+static __global__ void frequencyFlagsKernel(const uint32_t* __restrict__ counts, uint32_t n, uint64_t minFrequency,
+                                     uint32_t* __restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    flags[i] = (uint64_t(counts[i] & 0xffffu) >= minFrequency) ? 1u : 0u;
+}
+
+// Compact the flagged keys into 12-byte OrientedReadPair records (src/OrientedReadPair.hpp:18-86).
+static __global__ void emitCandidatesKernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flags,
+                                     const uint32_t* __restrict__ offsets, uint32_t n, uint32_t* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n || !flags[i]) return;
+    const uint64_t key = keys[i];
+    const uint64_t o = offsets[i];
+    out[3*o + 0] = uint32_t(key >> 32);
+    out[3*o + 1] = uint32_t(key & 0xffffffffull) >> 1;
+    out[3*o + 2] = (key & 1ull) ? 0u : 1u;          // byte 0 = isSameStrand, bytes 1..3 = 0
+}
+
+} // namespace shb

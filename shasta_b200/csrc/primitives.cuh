@@ -1,0 +1,252 @@
+// Hand-written device-wide primitives used by the LowHash and alignment pipelines:
+// exclusive scan, LSD radix sort (64-bit keys, optional 32-bit payload), stream compaction helpers.
+// All are plain sm_100a CUDA (warp shuffles / match_any / shared-memory atomics); no CUB/Thrust.
+#pragma once
+
+#include "common.cuh"
+
+namespace shb {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItemsPerThread = 16;
+constexpr int kScanTile = kScanThreads * kScanItemsPerThread;     // 4096
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide exclusive scan of one value per thread (256 threads). Returns the exclusive prefix;
+// `total` receives the block total. `smem` must hold 8 T values. Ends with a __syncthreads so the
+// scratch can be reused immediately.
+template<class T> __device__ __forceinline__ T blockExclusiveScan256(T v, T& total, T* smem)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, d);
+        if(lane >= (unsigned)d) inc += t;
+    }
+    if(lane == 31) smem[warp] = inc;
+    __syncthreads();
+    T warpOffset = 0;
+    T tot = 0;
+#pragma unroll
+    for(int w = 0; w < kScanThreads / 32; w++) {
+        T s = smem[w];
+        if((unsigned)w < warp) warpOffset += s;
+        tot += s;
+    }
+    __syncthreads();
+    total = tot;
+    return warpOffset + inc - v;
+}
+
+template<class T> __global__ void __launch_bounds__(kScanThreads)
+scanReduceKernel(const T* __restrict__ in, T* __restrict__ blockSums, uint64_t n)
+{
+    __shared__ T smem[kScanThreads / 32];
+    const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
+    T sum = 0;
+#pragma unroll
+    for(int i = 0; i < kScanItemsPerThread; i++) {
+        const uint64_t idx = base + uint64_t(i) * kScanThreads + threadIdx.x;
+        if(idx < n) sum += in[idx];
+    }
+    T total;
+    blockExclusiveScan256<T>(sum, total, smem);
+    if(threadIdx.x == 0) blockSums[blockIdx.x] = total;
+}
+
+// out[i] = blockOffsets[block] + exclusive prefix within the block tile. in and out may alias.
+// If totalOut != nullptr (single-block top level) it receives the grand total.
+template<class T> __global__ void __launch_bounds__(kScanThreads)
+scanDownsweepKernel(const T* in, T* out, const T* __restrict__ blockOffsets, uint64_t n, T* totalOut)
+{
+    __shared__ T smem[kScanThreads / 32];
+    const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
+    T running = blockOffsets ? blockOffsets[blockIdx.x] : T(0);
+#pragma unroll 1
+    for(int i = 0; i < kScanItemsPerThread; i++) {
+        const uint64_t idx = base + uint64_t(i) * kScanThreads + threadIdx.x;
+        const T v = (idx < n) ? in[idx] : T(0);
+        T total;
+        const T ex = blockExclusiveScan256<T>(v, total, smem);
+        if(idx < n) out[idx] = running + ex;
+        running += total;
+    }
+    if(totalOut && threadIdx.x == 0) *totalOut = running;
+}
+
+// Workspace elements (of T) needed by exclusiveScan for n items.
+inline uint64_t scanWorkspaceElements(uint64_t n)
+{
+    uint64_t total = 0;
+    while(n > kScanTile) {
+        n = (n + kScanTile - 1) / kScanTile;
+        total += n;
+    }
+    return total + 1;
+}
+
+// Exclusive scan of n items. in/out may alias. totalOut (device pointer, may be null) receives the
+// sum of all items. workspace must hold scanWorkspaceElements(n) items.
+template<class T> void exclusiveScan(const T* in, T* out, uint64_t n, T* totalOut, T* workspace, cudaStream_t stream)
+{
+    if(n == 0) {
+        if(totalOut) SHB_CUDA(cudaMemsetAsync(totalOut, 0, sizeof(T), stream));
+        return;
+    }
+    if(n <= kScanTile) {
+        SHB_LAUNCH((scanDownsweepKernel<T>), 1, kScanThreads, 0, stream, in, out, (const T*)nullptr, n, totalOut);
+        return;
+    }
+    const uint64_t blocks = (n + kScanTile - 1) / kScanTile;
+    T* sums = workspace;
+    SHB_LAUNCH((scanReduceKernel<T>), (unsigned)blocks, kScanThreads, 0, stream, in, sums, n);
+    exclusiveScan<T>(sums, sums, blocks, totalOut, workspace + blocks, stream);
+    SHB_LAUNCH((scanDownsweepKernel<T>), (unsigned)blocks, kScanThreads, 0, stream, in, out, (const T*)sums, n, (T*)nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, stable. Keys uint64; optional uint32 payload.
+constexpr int kSortThreads = 256;
+constexpr int kSortItemsPerThread = 16;
+constexpr int kSortTile = kSortThreads * kSortItemsPerThread;     // 4096 keys per block
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+
+// hist[digit * numBlocks + block] = number of keys of the block's tile with that digit.
+static __global__ void __launch_bounds__(kSortThreads)
+radixHistogramKernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t digitMask,
+                     uint32_t* __restrict__ hist, uint32_t numBlocks)
+{
+    __shared__ uint32_t counts[kRadix];
+    counts[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+    for(int i = 0; i < kSortItemsPerThread; i++) {
+        const uint32_t idx = base + i * kSortThreads + threadIdx.x;
+        if(idx < n) {
+            const uint32_t d = uint32_t(keys[idx] >> shift) & digitMask;
+            atomicAdd(&counts[d], 1u);
+        }
+    }
+    __syncthreads();
+    hist[threadIdx.x * numBlocks + blockIdx.x] = counts[threadIdx.x];
+}
+
+// Stable scatter. offsets = exclusive scan of hist (same indexing).
+template<bool HAS_VALUES> __global__ void __launch_bounds__(kSortThreads)
+radixScatterKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ keysOut,
+                   const uint32_t* __restrict__ valsIn, uint32_t* __restrict__ valsOut,
+                   uint32_t n, int shift, uint32_t digitMask,
+                   const uint32_t* __restrict__ offsets, uint32_t numBlocks)
+{
+    constexpr int kWarps = kSortThreads / 32;
+    __shared__ uint32_t digitBase[kRadix];               // next output slot per digit
+    __shared__ uint32_t warpCounts[kWarps][kRadix];      // per chunk: count, then start slot, per warp
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    digitBase[threadIdx.x] = offsets[threadIdx.x * numBlocks + blockIdx.x];
+    const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll 1
+    for(int i = 0; i < kSortItemsPerThread; i++) {
+        const uint32_t idx = base + i * kSortThreads + threadIdx.x;
+        const bool active = idx < n;
+#pragma unroll
+        for(int w = 0; w < kWarps; w++) warpCounts[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint64_t key = 0;
+        uint32_t val = 0;
+        uint32_t d = kRadix;                             // sentinel digit for inactive lanes
+        if(active) {
+            key = keysIn[idx];
+            if(HAS_VALUES) val = valsIn[idx];
+            d = uint32_t(key >> shift) & digitMask;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned rankInWarp = __popc(peers & ((1u << lane) - 1u));
+        if(active && rankInWarp == 0) warpCounts[warp][d] = __popc(peers);
+        __syncthreads();
+        {
+            // Thread t owns digit t: turn the per-warp counts into start slots.
+            uint32_t run = digitBase[threadIdx.x];
+#pragma unroll
+            for(int w = 0; w < kWarps; w++) {
+                const uint32_t c = warpCounts[w][threadIdx.x];
+                warpCounts[w][threadIdx.x] = run;
+                run += c;
+            }
+            digitBase[threadIdx.x] = run;
+        }
+        __syncthreads();
+        if(active) {
+            const uint32_t dst = warpCounts[warp][d] + rankInWarp;
+            keysOut[dst] = key;
+            if(HAS_VALUES) valsOut[dst] = val;
+        }
+        __syncthreads();
+    }
+}
+
+struct SortWorkspace {
+    DeviceBuffer<uint32_t> hist;
+    DeviceBuffer<uint32_t> scanWs;
+};
+
+// Sorts n (key[,value]) items on the bit ranges given (each range [begin,end) is processed in
+// 8-bit passes, least significant range first). Buffers ping-pong between (keysA,valsA) and
+// (keysB,valsB); returns true if the result ends up in the B buffers.
+template<bool HAS_VALUES>
+bool radixSort(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t n,
+               const int (*bitRanges)[2], int rangeCount, SortWorkspace& ws, cudaStream_t stream)
+{
+    SHB_REQUIRE(n < (1ull << 32), SHB_ERR_INVALID, "radixSort: more than 2^32-1 items in one sort.");
+    if(n == 0) return false;
+    const uint32_t numBlocks = ceilDiv(n, kSortTile);
+    const uint64_t histSize = uint64_t(kRadix) * numBlocks;
+    ws.hist.reserve(histSize);
+    ws.scanWs.reserve(scanWorkspaceElements(histSize));
+    bool inB = false;
+    for(int r = 0; r < rangeCount; r++) {
+        for(int bit = bitRanges[r][0]; bit < bitRanges[r][1]; bit += kRadixBits) {
+            const int bits = (bitRanges[r][1] - bit < kRadixBits) ? (bitRanges[r][1] - bit) : kRadixBits;
+            const uint32_t digitMask = (1u << bits) - 1u;
+            uint64_t* kin = inB ? keysB : keysA;
+            uint64_t* kout = inB ? keysA : keysB;
+            uint32_t* vin = inB ? valsB : valsA;
+            uint32_t* vout = inB ? valsA : valsB;
+            SHB_LAUNCH(radixHistogramKernel, numBlocks, kSortThreads, 0, stream,
+                       (const uint64_t*)kin, (uint32_t)n, bit, digitMask, ws.hist.get(), numBlocks);
+            exclusiveScan<uint32_t>(ws.hist.get(), ws.hist.get(), histSize, nullptr, ws.scanWs.get(), stream);
+            SHB_LAUNCH((radixScatterKernel<HAS_VALUES>), numBlocks, kSortThreads, 0, stream,
+                       (const uint64_t*)kin, kout, (const uint32_t*)vin, vout, (uint32_t)n, bit, digitMask,
+                       (const uint32_t*)ws.hist.get(), numBlocks);
+            inB = !inB;
+        }
+    }
+    return inB;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Run detection on a sorted key array: flags[i] = 1 where (keys[i] >> shift) differs from its
+// predecessor (or i == 0).
+static __global__ void headFlagsKernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    flags[i] = (i == 0 || (keys[i] >> shift) != (keys[i-1] >> shift)) ? 1u : 0u;
+}
+
+// Given flags and their exclusive scan (segIndex), write segStart[segIndex[i]] = i for heads and
+// segStart[numSegments] = n (thread n-1 does the latter).
+static __global__ void segmentStartsKernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ segIndexExclusive,
+                                    uint32_t n, uint32_t* __restrict__ segStart)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    if(flags[i]) segStart[segIndexExclusive[i]] = i;
+    if(i == n - 1) segStart[segIndexExclusive[i] + flags[i]] = n;
+}
+
+} // namespace shb
