@@ -122,6 +122,18 @@ shb_status shb_find_alignment_candidates_lowhash0(
     const uint8_t* readFlags, const shb_lowhash_params* params,
     void** candidates, uint64_t* candidateCount, uint64_t* stats, shb_lowhash_result* result);
 
+/* ------------------------------------------------------------------------------------------
+ * Bench / test utilities (not part of the reference's interface): the marker-space synthetic read
+ * generator of shasta_b200/synth.py on the device, and helpers for the device buffers it returns.
+ */
+shb_status shb_synth_generate(shb_context* ctx, uint64_t seed, uint32_t k, double drop, double ins,
+                              uint64_t genomeMarkers, const uint32_t* genomeKmerHost, const uint64_t* genomePosHost,
+                              uint64_t readCount, const int64_t* startHost, const int64_t* spanHost,
+                              const uint8_t* revHost, uint64_t* tocOut /* 2*readCount+1 */,
+                              uint32_t** kmerIdsDevice, uint8_t** data7Device /* may be NULL */);
+shb_status shb_device_free(void* devicePtr);
+shb_status shb_copy_device_to_host(void* dstHost, const void* srcDevice, uint64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

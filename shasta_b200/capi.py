@@ -59,6 +59,11 @@ def lib():
         L.shb_find_alignment_candidates_lowhash0.argtypes = [
             C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(LowHashParams),
             C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(LowHashResult)]
+        L.shb_synth_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p,
+                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_device_free.argtypes = [C.c_void_p]
+        L.shb_copy_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -161,6 +166,52 @@ class Context:
         out = _records_to_array(cand, n.value)
         lib().shb_free(cand)
         return out, stats, res
+
+
+class DeviceMarkers:
+    """Synthetic markers generated on the device (bench/test utility)."""
+
+    def __init__(self, toc, flags, kmer_ptr, data7_ptr):
+        self.toc = toc
+        self.flags = flags
+        self.kmer_ptr = kmer_ptr
+        self.data7_ptr = data7_ptr
+        self.marker_count = int(toc[-1])
+
+    def kmer_ids_to_host(self):
+        out = np.empty(self.marker_count, np.uint32)
+        _check(lib().shb_copy_device_to_host(_ptr(out), C.c_void_p(self.kmer_ptr), out.nbytes))
+        return out
+
+    def data7_to_host(self, out=None):
+        if out is None:
+            out = np.empty(self.marker_count * 7, np.uint8)
+        _check(lib().shb_copy_device_to_host(_ptr(out), C.c_void_p(self.data7_ptr), self.marker_count * 7))
+        return out
+
+    def free(self):
+        for name in ("kmer_ptr", "data7_ptr"):
+            p = getattr(self, name)
+            if p:
+                lib().shb_device_free(C.c_void_p(p))
+                setattr(self, name, None)
+
+
+def synth_generate_device(ctx: Context, p, want_data7=True) -> DeviceMarkers:
+    """shasta_b200.synth.generate(p) on the GPU: bit-identical markers, device resident."""
+    from . import synth
+    gk, gpos = synth.genome(p)
+    start, span, rev = synth.read_windows(p)
+    gk = np.ascontiguousarray(gk, np.uint32)
+    gpos = np.ascontiguousarray(gpos, np.uint64)
+    toc = np.zeros(2 * p.reads + 1, np.uint64)
+    kptr = C.c_void_p()
+    dptr = C.c_void_p()
+    _check(lib().shb_synth_generate(ctx._h, p.seed, p.k, p.drop, p.ins, len(gk), _ptr(gk), _ptr(gpos), p.reads,
+                                    _ptr(np.ascontiguousarray(start, np.int64)), _ptr(np.ascontiguousarray(span, np.int64)),
+                                    _ptr(np.ascontiguousarray(rev, np.uint8)), _ptr(toc), C.byref(kptr),
+                                    C.byref(dptr) if want_data7 else None))
+    return DeviceMarkers(toc, synth.read_flags(p), kptr.value, dptr.value if want_data7 else None)
 
 
 def _records_to_array(ptr, n):

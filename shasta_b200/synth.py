@@ -98,9 +98,8 @@ def genome(p: SynthParams):
     return kmer, pos
 
 
-def generate(p: SynthParams):
-    """Returns dict(toc uint64[2R+1], data uint8[M*7], flags uint8[R], kmer uint32[M], pos uint32[M])."""
-    gk, gpos = genome(p)
+def read_windows(p: SynthParams):
+    """Per-read genome window: (start int64[R], span int64[R], rev uint8[R]) in genome-marker units."""
     G = p.genome_markers
     R = p.reads
     r = np.arange(R, dtype=U64)
@@ -112,7 +111,15 @@ def generate(p: SynthParams):
     length = np.clip(np.exp(mu + p.sigma * z), p.min_bases, p.max_bases)
     span = np.minimum(np.maximum((length / p.mean_gap).astype(np.int64), 8), G - 1)
     start = (mix64(p.seed, 4, r) % (U64(G) - span.astype(U64))).astype(np.int64)
-    rev = (mix64(p.seed, 8, r) & U64(1)).astype(bool)
+    rev = (mix64(p.seed, 8, r) & U64(1)).astype(np.uint8)
+    return start, span, rev
+
+
+def generate(p: SynthParams):
+    """Returns dict(toc uint64[2R+1], data uint8[M*7], flags uint8[R], kmer uint32[M], pos uint32[M])."""
+    gk, gpos = genome(p)
+    R = p.reads
+    start, span, rev = read_windows(p)
     k4 = U64(1 << (2 * p.k))
     dropT = p.drop
     insT = p.ins
@@ -153,10 +160,15 @@ def generate(p: SynthParams):
         pos[a:b] = ps
         kmer[b:c] = reverse_complement_kmer(km[::-1], p.k)
         pos[b:c] = total_len - p.k - ps[::-1]
-    flags = np.zeros(R, np.uint8)
+    flags = read_flags(p)
+    return dict(toc=toc, data=pack_markers(kmer, pos), flags=flags, kmer=kmer, pos=pos, k=p.k)
+
+
+def read_flags(p: SynthParams):
+    flags = np.zeros(p.reads, np.uint8)
     if p.palindromic_every:
         flags[p.palindromic_every - 1::p.palindromic_every] = 1
-    return dict(toc=toc, data=pack_markers(kmer, pos), flags=flags, kmer=kmer, pos=pos, k=p.k)
+    return flags
 
 
 def pack_markers(kmer, pos):

@@ -167,3 +167,23 @@ def test_larger_synthetic_properties_and_oracle(ctx):
     # Idempotence: a second run on the same context gives the same bytes.
     cand2, stats2, _, _ = ctx.lowhash0(capi.make_lowhash_params(**kw))
     assert np.array_equal(cand, cand2) and np.array_equal(stats, stats2)
+
+
+def test_device_generator_matches_numpy(ctx):
+    # The bench's on-device generator (csrc/synth.cu) must reproduce shasta_b200.synth.generate bit for bit.
+    from shasta_b200 import capi
+    p = synth.SynthParams(reads=400, k=14, genome_markers=40000, n50_bases=15000, min_bases=5000, seed=123, palindromic_every=50)
+    d = synth.generate(p)
+    dm = capi.synth_generate_device(ctx, p, want_data7=True)
+    assert np.array_equal(dm.toc, d["toc"])
+    assert np.array_equal(dm.kmer_ids_to_host(), d["kmer"])
+    assert np.array_equal(dm.data7_to_host(), d["data"])
+    assert np.array_equal(dm.flags, d["flags"])
+    # Device-resident path gives the same candidates as the host-upload path.
+    kw = dict(m=4, hashFraction=0.01, minHashIterationCount=10, minBucketSize=2, maxBucketSize=30, minFrequency=2)
+    ctx.set_markers_device(dm.toc, dm.kmer_ptr, dm.flags, keepalive=dm)
+    c1, s1, _, _ = ctx.lowhash0(capi.make_lowhash_params(**kw))
+    ctx.set_markers(d["toc"], d["data"], d["flags"])
+    c2, s2, _, _ = ctx.lowhash0(capi.make_lowhash_params(**kw))
+    assert np.array_equal(c1, c2) and np.array_equal(s1, s2) and len(c1) > 0
+    dm.free()
