@@ -123,6 +123,63 @@ shb_status shb_find_alignment_candidates_lowhash0(
     void** candidates, uint64_t* candidateCount, uint64_t* stats, shb_lowhash_result* result);
 
 /* ------------------------------------------------------------------------------------------
+ * Alignments.  Replaces Assembler::computeAlignments (src/AssemblerAlign.cpp:208-304, declaration
+ * src/Assembler.hpp:264-270; Python binding src/PythonModule.cpp:344-345).
+ * shb_align_options mirrors AlignOptions field for field (src/AssemblerOptions.hpp:177-199); k is the
+ * marker k-mer length (assemblerInfo->k): the method-3 downsampling hash kmerTable[kmerId].hash
+ * (src/AssemblerKmers.cpp:182-186) is recomputed from it instead of reading the 4^k-entry Data/Kmers table.
+ */
+typedef struct {
+    int32_t  alignMethod;            /* 3 (what every shipped conf selects) or 4 (Align4); 0/1 are not on the path */
+    int32_t  maxSkip;
+    int32_t  maxDrift;
+    int32_t  maxTrim;
+    int32_t  maxMarkerFrequency;     /* method 0 only; ignored */
+    int32_t  minAlignedMarkerCount;
+    double   minAlignedFraction;
+    int32_t  matchScore;
+    int32_t  mismatchScore;
+    int32_t  gapScore;
+    double   downsamplingFactor;
+    int32_t  bandExtend;
+    int32_t  maxBand;
+    int32_t  sameChannelReadAlignmentSuppressDeltaThreshold;    /* not used by computeAlignments */
+    int32_t  suppressContainments;
+    uint64_t align4DeltaX;
+    uint64_t align4DeltaY;
+    uint64_t align4MinEntryCountPerCell;
+    uint64_t align4MaxDistanceFromBoundary;
+    uint32_t k;
+    uint32_t reserved;
+} shb_align_options;
+
+typedef struct {
+    uint64_t candidateCount;
+    uint64_t alignmentCount;        /* stored ("good") alignments */
+    uint64_t skippedCount;          /* candidates the reference would skip with a logged exception */
+    uint64_t dpCells;               /* DP cell updates performed (both stages) */
+    double   dpMs;                  /* device time inside the DP kernels (CUDA events) */
+    double   totalMs;               /* device time of the whole call */
+    uint64_t kernelLaunches;
+} shb_align_result;
+
+/* Computes the marker alignment of every candidate on the markers held by ctx (all reads must be
+ * resident on this GPU).
+ *   candidates      : n 12-byte OrientedReadPair records (host), readIds[0] < readIds[1].
+ *   alignmentData   : receives a host buffer of 64-byte AlignmentData records (src/Alignment.hpp:419-447:
+ *                     OrientedReadPair + AlignmentInfo; padding bytes 0), in candidate order (the
+ *                     reference's order is thread-schedule dependent, any order is legal).
+ *   compressedToc   : receives uint64[count+1]; compressedData: the concatenated shasta::compress bytes
+ *                     (= Data/CompressedAlignments.toc/.data payload).
+ * All three are freed with shb_free.
+ */
+shb_status shb_compute_alignments(shb_context* ctx, const void* candidates, uint64_t candidateCount,
+                                  const shb_align_options* options,
+                                  void** alignmentData, uint64_t* alignmentCount,
+                                  uint64_t** compressedToc, uint8_t** compressedData,
+                                  shb_align_result* result);
+
+/* ------------------------------------------------------------------------------------------
  * Bench / test utilities (not part of the reference's interface): the marker-space synthetic read
  * generator of shasta_b200/synth.py on the device, and helpers for the device buffers it returns.
  */

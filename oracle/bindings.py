@@ -182,3 +182,196 @@ def candidate_digest(c):
         for v in (a, b, s):
             h = ((h ^ v) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     return h
+
+
+# ---------------------------------------------------------------------------------------------------
+# Alignment half
+class AlignOptions(C.Structure):
+    """orc_align_options: AlignOptions of src/AssemblerOptions.hpp:177-199 as used on the path."""
+    _fields_ = [("alignMethod", C.c_uint32), ("k", C.c_uint32),
+                ("maxSkip", C.c_uint64), ("maxDrift", C.c_uint64), ("maxTrim", C.c_uint64),
+                ("minAlignedMarkerCount", C.c_uint64), ("minAlignedFraction", C.c_double),
+                ("matchScore", C.c_int32), ("mismatchScore", C.c_int32), ("gapScore", C.c_int32),
+                ("downsamplingFactor", C.c_double), ("bandExtend", C.c_int32), ("maxBand", C.c_int32),
+                ("suppressContainments", C.c_uint32),
+                ("align4DeltaX", C.c_uint64), ("align4DeltaY", C.c_uint64),
+                ("align4MinEntryCountPerCell", C.c_uint64), ("align4MaxDistanceFromBoundary", C.c_uint64)]
+
+
+ALIGN_DEFAULTS = dict(alignMethod=3, k=10, maxSkip=30, maxDrift=30, maxTrim=30, minAlignedMarkerCount=100,
+                      minAlignedFraction=0.4, matchScore=6, mismatchScore=-1, gapScore=-1, downsamplingFactor=0.1,
+                      bandExtend=10, maxBand=1000, suppressContainments=0, align4DeltaX=200, align4DeltaY=10,
+                      align4MinEntryCountPerCell=10, align4MaxDistanceFromBoundary=100)
+
+
+def make_align_options(**kw):
+    d = dict(ALIGN_DEFAULTS)
+    d.update(kw)
+    return AlignOptions(**d)
+
+
+def _align_protos(lib):
+    lib.orc_overlap_align.restype = C.c_int
+    lib.orc_overlap_align.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.orc_compress_alignment.restype = C.c_uint64
+    lib.orc_compress_alignment.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.orc_decompress_alignment.restype = C.c_uint64
+    lib.orc_decompress_alignment.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.orc_alignment_info.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.orc_align_method3.restype = C.c_int
+    lib.orc_align_method3.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(AlignOptions), C.c_void_p]
+    lib.orc_align_method4.restype = C.c_int
+    lib.orc_align_method4.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(AlignOptions), C.c_void_p, C.POINTER(C.c_int)]
+    lib.orc_compute_alignments.restype = C.c_int
+    lib.orc_compute_alignments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(AlignOptions), C.c_uint32,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+
+
+class _Alignment(C.Structure):
+    _fields_ = [("ord", C.c_void_p), ("n", C.c_uint64), ("cap", C.c_uint64)]
+
+
+def _olib():
+    lib = oracle_lib()
+    if not getattr(lib, "_align_ready", False):
+        _align_protos(lib)
+        lib._align_ready = True
+    return lib
+
+
+def overlap_align(a, b, match=6, mismatch=-1, gap=-1, band=None):
+    """The oracle's DP. Returns (score, path uint32[n,2]) — diagonal steps in path order; score None on failure."""
+    lib = _olib()
+    a = np.ascontiguousarray(a, np.uint32)
+    b = np.ascontiguousarray(b, np.uint32)
+    p = C.c_void_p()
+    n = C.c_uint64()
+    lo, hi = band if band is not None else (0, 0)
+    s = lib.orc_overlap_align(a.ctypes.data, len(a), b.ctypes.data, len(b), match, mismatch, gap,
+                              1 if band is not None else 0, lo, hi, C.byref(p), C.byref(n))
+    if s == -2**31:
+        return None, np.zeros((0, 2), np.uint32)
+    path = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), (n.value, 2)).copy() if n.value else np.zeros((0, 2), np.uint32)
+    lib.orc_free(p)
+    return s, path
+
+
+def _take_alignment(lib, al):
+    out = np.ctypeslib.as_array(C.cast(al.ord, C.POINTER(C.c_uint32)), (al.n, 2)).copy() if al.n else np.zeros((0, 2), np.uint32)
+    if al.ord:
+        lib.orc_free(al.ord)
+    return out
+
+
+def oracle_align_pair(a, b, opts: AlignOptions):
+    """Single pair through method 3 or 4. Returns (status, ordinals uint32[n,2], tie flag)."""
+    lib = _olib()
+    a = np.ascontiguousarray(a, np.uint32)
+    b = np.ascontiguousarray(b, np.uint32)
+    al = _Alignment(None, 0, 0)
+    tie = C.c_int(0)
+    if opts.alignMethod == 4:
+        st = lib.orc_align_method4(a.ctypes.data, len(a), b.ctypes.data, len(b), C.byref(opts), C.byref(al), C.byref(tie))
+    else:
+        st = lib.orc_align_method3(a.ctypes.data, len(a), b.ctypes.data, len(b), C.byref(opts), C.byref(al))
+    return st, _take_alignment(lib, al), tie.value
+
+
+def oracle_alignment_info(ordinals, nx, ny):
+    lib = _olib()
+    o = np.ascontiguousarray(ordinals, np.uint32).reshape(-1)
+    out = np.zeros(12, np.uint32)
+    lib.orc_alignment_info(o.ctypes.data, len(o) // 2, nx, ny, out.ctypes.data)
+    return out
+
+
+def oracle_compress(ordinals):
+    lib = _olib()
+    o = np.ascontiguousarray(ordinals, np.uint32).reshape(-1)
+    buf = np.zeros(8 * len(o) + 16, np.uint8)
+    n = lib.orc_compress_alignment(o.ctypes.data, len(o) // 2, buf.ctypes.data)
+    return buf[:n].copy()
+
+
+def oracle_decompress(data, cap=1 << 20):
+    lib = _olib()
+    d = np.ascontiguousarray(data, np.uint8)
+    out = np.zeros((cap, 2), np.uint32)
+    n = lib.orc_decompress_alignment(d.ctypes.data, len(d), out.ctypes.data, cap)
+    return out[:n].copy()
+
+
+def oracle_compute_alignments(toc, kmer_ids, candidates, opts: AlignOptions, threads=1):
+    """Returns (records uint32[count,16], compressedToc uint64[count+1], compressedData uint8[], ties uint8[n])."""
+    lib = _olib()
+    toc = np.ascontiguousarray(toc, np.uint64)
+    kmer_ids = np.ascontiguousarray(kmer_ids, np.uint32)
+    cand = np.ascontiguousarray(candidates, np.uint32).reshape(-1, 3)
+    rec = C.c_void_p()
+    cnt = C.c_uint64()
+    ctoc = C.c_void_p()
+    cdata = C.c_void_p()
+    ties = C.c_void_p()
+    lib.orc_compute_alignments(toc.ctypes.data, kmer_ids.ctypes.data, cand.ctypes.data, len(cand), C.byref(opts), threads,
+                               C.byref(rec), C.byref(cnt), C.byref(ctoc), C.byref(cdata), C.byref(ties))
+    n = cnt.value
+    records = np.ctypeslib.as_array(C.cast(rec, C.POINTER(C.c_uint32)), (n, 16)).copy() if n else np.zeros((0, 16), np.uint32)
+    ctocn = np.ctypeslib.as_array(C.cast(ctoc, C.POINTER(C.c_uint64)), (n + 1,)).copy()
+    nb = int(ctocn[-1])
+    cdatan = np.ctypeslib.as_array(C.cast(cdata, C.POINTER(C.c_uint8)), (nb,)).copy() if nb else np.zeros(0, np.uint8)
+    tiesn = np.ctypeslib.as_array(C.cast(ties, C.POINTER(C.c_uint8)), (len(cand),)).copy() if len(cand) else np.zeros(0, np.uint8)
+    for p in (rec, ctoc, cdata, ties):
+        lib.orc_free(p)
+    return records, ctocn, cdatan, tiesn
+
+
+# ---- reference side (unmodified Align4.cpp / Alignment.cpp / compressAlignment.cpp) ----
+def _rlib():
+    lib = ref_lib()
+    if not getattr(lib, "_align_ready", False):
+        lib.ref_align4.restype = C.c_int
+        lib.ref_align4.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                   C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        lib.ref_alignment_info.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.ref_compress_alignment.restype = C.c_uint64
+        lib.ref_compress_alignment.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.ref_decompress_alignment.restype = C.c_uint64
+        lib.ref_decompress_alignment.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        lib.ref_test_alignment_compression.restype = C.c_int
+        lib._align_ready = True
+    return lib
+
+
+def ref_align4(a, b, opts: AlignOptions):
+    lib = _rlib()
+    a = np.ascontiguousarray(a, np.uint32)
+    b = np.ascontiguousarray(b, np.uint32)
+    p = C.c_void_p()
+    n = C.c_uint64()
+    rc = lib.ref_align4(a.ctypes.data, len(a), b.ctypes.data, len(b), opts.align4DeltaX, opts.align4DeltaY,
+                        opts.align4MinEntryCountPerCell, opts.align4MaxDistanceFromBoundary, opts.minAlignedMarkerCount,
+                        opts.minAlignedFraction, opts.maxSkip, opts.maxDrift, opts.maxTrim, opts.maxBand, C.byref(p), C.byref(n))
+    if rc:
+        raise RuntimeError("reference Align4 failed")
+    out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), (n.value, 2)).copy() if n.value else np.zeros((0, 2), np.uint32)
+    lib.ref_free(p)
+    return out
+
+
+def ref_alignment_info(ordinals, nx, ny):
+    lib = _rlib()
+    o = np.ascontiguousarray(ordinals, np.uint32).reshape(-1)
+    out = np.zeros(12, np.uint32)
+    lib.ref_alignment_info(o.ctypes.data, len(o) // 2, nx, ny, out.ctypes.data)
+    return out
+
+
+def ref_compress(ordinals):
+    lib = _rlib()
+    o = np.ascontiguousarray(ordinals, np.uint32).reshape(-1)
+    buf = np.zeros(8 * len(o) + 16, np.uint8)
+    n = lib.ref_compress_alignment(o.ctypes.data, len(o) // 2, buf.ctypes.data)
+    return buf[:n].copy()

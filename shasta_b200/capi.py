@@ -38,6 +38,36 @@ class LowHashResult(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class AlignOptions(C.Structure):
+    """shb_align_options: AlignOptions of src/AssemblerOptions.hpp:177-199 + k."""
+    _fields_ = [("alignMethod", C.c_int32), ("maxSkip", C.c_int32), ("maxDrift", C.c_int32), ("maxTrim", C.c_int32),
+                ("maxMarkerFrequency", C.c_int32), ("minAlignedMarkerCount", C.c_int32), ("minAlignedFraction", C.c_double),
+                ("matchScore", C.c_int32), ("mismatchScore", C.c_int32), ("gapScore", C.c_int32),
+                ("downsamplingFactor", C.c_double), ("bandExtend", C.c_int32), ("maxBand", C.c_int32),
+                ("sameChannelReadAlignmentSuppressDeltaThreshold", C.c_int32), ("suppressContainments", C.c_int32),
+                ("align4DeltaX", C.c_uint64), ("align4DeltaY", C.c_uint64), ("align4MinEntryCountPerCell", C.c_uint64),
+                ("align4MaxDistanceFromBoundary", C.c_uint64), ("k", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class AlignResult(C.Structure):
+    _fields_ = [("candidateCount", C.c_uint64), ("alignmentCount", C.c_uint64), ("skippedCount", C.c_uint64),
+                ("dpCells", C.c_uint64), ("dpMs", C.c_double), ("totalMs", C.c_double), ("kernelLaunches", C.c_uint64)]
+
+
+# Defaults of src/AssemblerOptions.cpp:380-489
+ALIGN_DEFAULTS = dict(alignMethod=3, maxSkip=30, maxDrift=30, maxTrim=30, maxMarkerFrequency=10, minAlignedMarkerCount=100,
+                      minAlignedFraction=0.4, matchScore=6, mismatchScore=-1, gapScore=-1, downsamplingFactor=0.1,
+                      bandExtend=10, maxBand=1000, sameChannelReadAlignmentSuppressDeltaThreshold=0, suppressContainments=0,
+                      align4DeltaX=200, align4DeltaY=10, align4MinEntryCountPerCell=10, align4MaxDistanceFromBoundary=100,
+                      k=10, reserved=0)
+
+
+def make_align_options(**kw):
+    d = dict(ALIGN_DEFAULTS)
+    d.update(kw)
+    return AlignOptions(**d)
+
+
 _lib = None
 
 
@@ -59,6 +89,9 @@ def lib():
         L.shb_find_alignment_candidates_lowhash0.argtypes = [
             C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(LowHashParams),
             C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(LowHashResult)]
+        L.shb_compute_alignments.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(AlignOptions), C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.POINTER(AlignResult)]
         L.shb_synth_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -212,6 +245,34 @@ def synth_generate_device(ctx: Context, p, want_data7=True) -> DeviceMarkers:
                                     _ptr(np.ascontiguousarray(rev, np.uint8)), _ptr(toc), C.byref(kptr),
                                     C.byref(dptr) if want_data7 else None))
     return DeviceMarkers(toc, synth.read_flags(p), kptr.value, dptr.value if want_data7 else None)
+
+
+def candidates_to_records(cand):
+    """uint32[n,3] (readId0, readId1, isSameStrand) -> n 12-byte OrientedReadPair records (as uint32[n,3])."""
+    c = np.ascontiguousarray(cand, dtype=np.uint32).reshape(-1, 3).copy()
+    c[:, 2] &= 1
+    return c
+
+
+def compute_alignments(ctx: Context, candidates, options: AlignOptions):
+    """Assembler::computeAlignments on the markers held by ctx.
+    Returns (records uint32[count,16], compressedToc uint64[count+1], compressedData uint8[], AlignResult)."""
+    cand = candidates_to_records(candidates)
+    rec = C.c_void_p()
+    cnt = C.c_uint64()
+    toc = C.c_void_p()
+    data = C.c_void_p()
+    res = AlignResult()
+    _check(lib().shb_compute_alignments(ctx._h, _ptr(cand), len(cand), C.byref(options), C.byref(rec), C.byref(cnt),
+                                        C.byref(toc), C.byref(data), C.byref(res)))
+    n = cnt.value
+    records = np.ctypeslib.as_array(C.cast(rec, C.POINTER(C.c_uint32)), (n, 16)).copy() if n else np.zeros((0, 16), np.uint32)
+    tocn = np.ctypeslib.as_array(C.cast(toc, C.POINTER(C.c_uint64)), (n + 1,)).copy()
+    nb = int(tocn[-1])
+    datan = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), (nb,)).copy() if nb else np.zeros(0, np.uint8)
+    for p in (rec, toc, data):
+        lib().shb_free(p)
+    return records, tocn, datan, res
 
 
 def _records_to_array(ptr, n):

@@ -1,0 +1,528 @@
+// Marker-space alignment kernels (sm_100a). Reference: chanzuckerberg/shasta
+//   downsampling hash            src/AssemblerKmers.cpp:182-186, src/MurmurHash2.cpp:37-88
+//   method 3 (two-stage banded)  src/AssemblerAlign3.cpp:23-313
+//   overlap DP + traceback       call sites src/AssemblerAlign3.cpp:117-122,254-260, src/Align4.cpp:1027-1033
+//                                 (SeqAn in the reference; rule set of SURVEY.md Appendix A)
+//   AlignmentInfo / filters      src/Alignment.cpp:67-113, src/AssemblerAlign.cpp:438-483
+//   compress                     src/compressAlignment.cpp:11-70
+#pragma once
+
+#include "common.cuh"
+
+namespace shb {
+
+// ---------------------------------------------------------------------------------------------
+// kmerTable[kmerId].hash without the 4^k table: MurmurHash2(&n, 8, 13477), n = kmerId + rc(kmerId).
+__device__ __forceinline__ uint32_t reverseComplementKmerId(uint32_t kmer, uint32_t k)
+{
+    const uint32_t mask = (k == 16) ? 0xffffu : ((1u << k) - 1u);
+    const uint32_t lsb = ~kmer & mask;
+    const uint32_t msb = ~(kmer >> k) & mask;
+    return ((__brev(msb) >> (32 - k)) << k) | (__brev(lsb) >> (32 - k));
+}
+
+__device__ __forceinline__ uint32_t kmerDownsamplingHash(uint32_t kmer, uint32_t k)
+{
+    const uint64_t n = uint64_t(kmer) + uint64_t(reverseComplementKmerId(kmer, k));
+    const uint32_t m = 0x5bd1e995u;
+    uint32_t h = 13477u ^ 8u;
+    uint32_t k1 = uint32_t(n);
+    k1 *= m; k1 ^= k1 >> 24; k1 *= m;
+    h *= m; h ^= k1;
+    uint32_t k2 = uint32_t(n >> 32);
+    k2 *= m; k2 ^= k2 >> 24; k2 *= m;
+    h *= m; h ^= k2;
+    h ^= h >> 13; h *= m; h ^= h >> 15;
+    return h;
+}
+
+static __global__ void downsampleFlagsKernel(const uint32_t* __restrict__ kmerIds, uint64_t begin, uint32_t n,
+                                             uint32_t k, uint32_t hashThreshold, uint32_t* __restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    flags[i] = (kmerDownsamplingHash(kmerIds[begin + i], k) < hashThreshold) ? 1u : 0u;
+}
+
+// Compact the downsampled markers of a chunk: dsKmer / dsOrdinal at (dsBase + exclusive index).
+static __global__ void downsampleCompactKernel(const uint32_t* __restrict__ kmerIds, uint64_t begin, uint32_t n,
+                                               const uint32_t* __restrict__ flags, const uint32_t* __restrict__ index,
+                                               const uint64_t* __restrict__ toc, uint32_t orientedReadCount, uint64_t dsBase,
+                                               uint32_t* __restrict__ dsKmer, uint32_t* __restrict__ dsOrdinal)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n || !flags[i]) return;
+    const uint64_t p = begin + i;
+    uint32_t lo = 0, hi = orientedReadCount;
+    while(hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if(toc[mid] <= p) lo = mid; else hi = mid;
+    }
+    const uint64_t d = dsBase + index[i];
+    dsKmer[d] = kmerIds[p];
+    dsOrdinal[d] = uint32_t(p - toc[lo]);
+}
+
+// dsToc[o] = number of downsampled markers before row o's first marker. Rows starting in this chunk.
+static __global__ void downsampleTocKernel(const uint64_t* __restrict__ toc, uint32_t orientedReadCount,
+                                           uint64_t begin, uint32_t n, const uint32_t* __restrict__ index,
+                                           uint64_t dsBase, uint64_t dsTotalAfterChunk, uint64_t* __restrict__ dsToc)
+{
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if(o > orientedReadCount) return;
+    const uint64_t p = toc[o];
+    if(p >= begin && p < begin + n) dsToc[o] = dsBase + index[p - begin];
+    else if(p == begin + n) dsToc[o] = dsTotalAfterChunk;       // rows starting exactly at the chunk end (or the final sentinel)
+}
+
+// ---------------------------------------------------------------------------------------------
+// One DP job = one overlap alignment of sequence a (horizontal, index i) against b (vertical, j)
+// restricted to the band lo <= i - j <= hi (already clipped to the matrix).
+struct DpJob {
+    uint64_t aOffset, bOffset;      // into the sequence array
+    uint32_t nx, ny;
+    int32_t lo, hi;
+    uint64_t traceOffset;           // in 32-bit words
+    uint64_t outOffset;             // stage 2: in ordinal pairs
+    uint32_t state;                 // 0 = run, others = skip (see kState*)
+    uint32_t pad;
+};
+constexpr uint32_t kStateRun = 0, kStateEmpty = 1, kStateSkipped = 2;
+
+struct DpScores { int32_t match, mismatch, gap; };
+
+constexpr int32_t kNegInf = -(1 << 29);
+constexpr int kDpMaxWarpsPerBlock = 4;
+
+__host__ __device__ inline uint32_t dpPaddedWidth(int32_t lo, int32_t hi) { return (uint32_t(hi - lo + 1) + 31u) & ~31u; }
+__host__ __device__ inline uint64_t dpTraceWords(uint32_t nx, int32_t lo, int32_t hi)
+{
+    return uint64_t(nx / 16 + 1) * dpPaddedWidth(lo, hi);
+}
+
+// Warp-cooperative banded overlap DP. Band offset e = j - i + hi in [0, W). Lanes own e % 32.
+//   hPrev/hCur : shared memory, Wpad + 1 ints each (sentinel at Wpad).   traceAcc: Wpad words.
+//   trace      : global scratch, dpTraceWords() words; word (i/16)*Wpad + e holds the 2-bit trace codes
+//                of columns 16*(i/16) .. +15 for band offset e (column i at bits 2*(i%16)).
+// Trace codes: 0 none, 1 diagonal, 2 vertical (j-1), 3 horizontal (i-1).
+// Tie-break and end-cell rules: SURVEY.md Appendix A (diag > vertical > horizontal; first strict maximum in
+// column-major order over last-row / last-column cells).
+__device__ inline void bandedOverlapDp(const uint32_t* __restrict__ a, uint32_t nx, const uint32_t* __restrict__ b, uint32_t ny,
+                                       int32_t lo, int32_t hi, DpScores sc,
+                                       int32_t* hPrev, int32_t* hCur, uint32_t* traceAcc, uint32_t* __restrict__ trace,
+                                       int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int32_t W = hi - lo + 1;
+    const int32_t Wpad = int32_t(dpPaddedWidth(lo, hi));
+    const int32_t chunks = Wpad >> 5;
+
+    bestScore = kNegInf * 2; bestI = -1; bestJ = -1;
+    for(int32_t e = lane; e <= Wpad; e += 32) { hPrev[e] = kNegInf; hCur[e] = kNegInf; }
+    for(int32_t e = lane; e < Wpad; e += 32) traceAcc[e] = 0;
+    __syncwarp();
+
+    for(int32_t i = 0; i <= int32_t(nx); i++) {
+        const uint32_t ai = (i > 0) ? a[i - 1] : 0u;
+        int32_t carry = kNegInf;                         // H of offset e-1 (previous chunk's last lane)
+        int32_t carryP = kNegInf * 2;                    // running prefix maximum of A(e) - e*gap
+        const bool lastColumn = (i == int32_t(nx));
+        const int32_t eLastRow = int32_t(ny) - i + hi;   // band offset of row j = ny in this column
+        for(int32_t c = 0; c < chunks; c++) {
+            const int32_t e = (c << 5) + int32_t(lane);
+            const int32_t j = e + i - hi;
+            const bool valid = (e < W) && (j >= 0) && (j <= int32_t(ny));
+            int32_t A = kNegInf, diag = kNegInf, horz = kNegInf;
+            const bool boundary = (i == 0) || (j == 0);
+            if(valid) {
+                if(boundary) A = 0;
+                else {
+                    diag = hPrev[e] + ((ai == b[j - 1]) ? sc.match : sc.mismatch);
+                    horz = hPrev[e + 1] + sc.gap;        // (i-1, j); sentinel / out-of-band entries hold kNegInf
+                    A = max(diag, horz);
+                }
+            }
+            // Vertical moves: H(e) = max(A(e), H(e-1) + gap)  ==  e*gap + prefixmax(A(e') - e'*gap).
+            int32_t P = A - e * sc.gap;
+#pragma unroll
+            for(int d = 1; d < 32; d <<= 1) {
+                const int32_t t = __shfl_up_sync(0xffffffffu, P, d);
+                if(lane >= (unsigned)d) P = max(P, t);
+            }
+            P = max(P, carryP);
+            int32_t H = P + e * sc.gap;
+            if(!valid) H = kNegInf;
+            if(valid && boundary) H = 0;
+            // Trace code.
+            int32_t below = __shfl_up_sync(0xffffffffu, H, 1);       // H(e-1) = cell (i, j-1)
+            if(lane == 0) below = carry;
+            uint32_t code = 0;
+            if(valid && !boundary) {
+                const int32_t vert = below + sc.gap;
+                code = (horz > max(diag, vert)) ? 3u : ((vert > diag) ? 2u : 1u);
+            }
+            hCur[e] = H;
+            uint32_t acc = (traceAcc[e] >> 2) | (code << 30);
+            traceAcc[e] = acc;
+            if((i & 15) == 15 || lastColumn) {
+                const uint32_t filled = uint32_t(i & 15) + 1u;       // columns accumulated in this word
+                trace[uint64_t(i >> 4) * uint32_t(Wpad) + uint32_t(e)] = acc >> (2u * (16u - filled));
+                traceAcc[e] = 0;
+            }
+            carry = __shfl_sync(0xffffffffu, H, 31);
+            carryP = __shfl_sync(0xffffffffu, P, 31);
+            // End-cell candidates: row ny in every column, all rows in the last column.
+            if(lastColumn) {
+                int32_t mx = valid ? H : kNegInf * 2;
+#pragma unroll
+                for(int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+                const unsigned who = __ballot_sync(0xffffffffu, valid && H == mx);
+                if(who && mx > bestScore) {
+                    const int first = __ffs(who) - 1;
+                    bestScore = mx; bestI = i; bestJ = ((c << 5) + first) + i - hi;
+                }
+            } else if(eLastRow >= (c << 5) && eLastRow < (c << 5) + 32 && eLastRow < W && eLastRow >= 0) {
+                const int32_t s = __shfl_sync(0xffffffffu, H, eLastRow & 31);
+                if(s > bestScore) { bestScore = s; bestI = i; bestJ = int32_t(ny); }
+            }
+        }
+        __syncwarp();
+        int32_t* t = hPrev; hPrev = hCur; hCur = t;
+    }
+}
+
+// Traceback (executed redundantly by all lanes; loads are warp-uniform). F(x, y) is called for every
+// diagonal step, last step first.
+template<class F> __device__ inline void tracebackPath(const uint32_t* __restrict__ trace, int32_t lo, int32_t hi,
+                                                       int32_t bestI, int32_t bestJ, F&& onDiagonal)
+{
+    const uint32_t Wpad = dpPaddedWidth(lo, hi);
+    int32_t i = bestI, j = bestJ;
+    int64_t cachedIndex = -1;
+    uint32_t word = 0;
+    while(i > 0 && j > 0) {
+        const int32_t e = j - i + hi;
+        const int64_t index = int64_t(i >> 4) * Wpad + e;
+        if(index != cachedIndex) { word = trace[index]; cachedIndex = index; }
+        const uint32_t code = (word >> (2 * (i & 15))) & 3u;
+        if(code == 1u) { onDiagonal(uint32_t(i - 1), uint32_t(j - 1)); i--; j--; }
+        else if(code == 2u) j--;
+        else if(code == 3u) i--;
+        else break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Method 3, stage 1 (src/AssemblerAlign3.cpp:62-239): unbanded DP on the downsampled markers,
+// then the band for stage 2. One warp per candidate.
+struct Method3Args {
+    const uint32_t* candidates;     // n x 3 (readId0, readId1, isSameStrand)
+    uint64_t candidateBegin; uint32_t n;
+    const uint64_t* toc;            // global rows (all reads)
+    const uint64_t* dsToc; const uint32_t* dsKmer; const uint32_t* dsOrdinal;
+    DpScores scores;
+    int32_t bandExtend, maxBand;
+    uint32_t wMin, wMax;            // only jobs with wMin < Wpad <= wMax are processed by this launch
+};
+
+static __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
+method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restrict__ trace, DpJob* __restrict__ jobs2)
+{
+    extern __shared__ int32_t smem[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + warp;
+    if(p >= g.n) return;
+    DpJob job = jobs1[p];
+    if(job.state != kStateRun) return;
+    const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
+    if(Wpad <= g.wMin || Wpad > g.wMax) return;
+    const uint32_t stride = g.wMax + 1;
+    int32_t* hPrev = smem + warp * 3 * stride;
+    int32_t* hCur = hPrev + stride;
+    uint32_t* traceAcc = reinterpret_cast<uint32_t*>(hCur + stride);
+    const uint32_t* a = g.dsKmer + job.aOffset;
+    const uint32_t* b = g.dsKmer + job.bOffset;
+    int32_t bestScore, bestI, bestJ;
+    bandedOverlapDp(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, hPrev, hCur, traceAcc, trace + job.traceOffset,
+                    bestScore, bestI, bestJ);
+    __syncwarp();
+    const uint32_t* oa = g.dsOrdinal + job.aOffset;
+    const uint32_t* ob = g.dsOrdinal + job.bOffset;
+    int32_t offsetMin = INT32_MAX, offsetMax = INT32_MIN;
+    uint32_t steps = 0;
+    tracebackPath(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, [&](uint32_t x, uint32_t y) {
+        steps++;
+        if(a[x] == b[y]) {
+            const int32_t off = int32_t(oa[x]) - int32_t(ob[y]);
+            offsetMin = min(offsetMin, off);
+            offsetMax = max(offsetMax, off);
+        }
+    });
+    if(lane == 0) {
+        DpJob j2 = jobs2[p];
+        if(steps == 0) j2.state = kStateEmpty;                                  // :185-191
+        else {
+            // 32-bit wrap-around like the compiled reference (:222-239)
+            const int32_t bandMin = int32_t(uint32_t(offsetMin) - uint32_t(g.bandExtend));
+            const int32_t bandMax = int32_t(uint32_t(offsetMax) + uint32_t(g.bandExtend));
+            if(int32_t(uint32_t(bandMax) - uint32_t(bandMin)) > g.maxBand) j2.state = kStateEmpty;
+            else if(bandMin > bandMax || bandMax < -int32_t(j2.ny) || bandMin > int32_t(j2.nx)) j2.state = kStateSkipped;  // SeqAn MinValue -> throw
+            else {
+                j2.lo = max(bandMin, -int32_t(j2.ny));
+                j2.hi = min(bandMax, int32_t(j2.nx));
+                j2.state = kStateRun;
+            }
+        }
+        jobs2[p] = j2;
+    }
+}
+
+// Stage 2 / generic banded alignment on full marker rows: DP, traceback, and the equal-kmer diagonal
+// steps written LAST STEP FIRST to ordinals[outOffset ...]; counts[p] receives how many.
+struct BandedArgs {
+    uint32_t n;
+    const uint32_t* kmerIds;
+    DpScores scores;
+    uint32_t wMin, wMax;
+};
+
+static __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
+bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __restrict__ trace,
+                  uint2* __restrict__ ordinals, uint32_t* __restrict__ counts)
+{
+    extern __shared__ int32_t smem[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + warp;
+    if(p >= g.n) return;
+    const DpJob job = jobs[p];
+    if(job.state != kStateRun) return;          // counts[] is zeroed by the host
+    const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
+    if(Wpad <= g.wMin || Wpad > g.wMax) return;
+    const uint32_t stride = g.wMax + 1;
+    int32_t* hPrev = smem + warp * 3 * stride;
+    int32_t* hCur = hPrev + stride;
+    uint32_t* traceAcc = reinterpret_cast<uint32_t*>(hCur + stride);
+    const uint32_t* a = g.kmerIds + job.aOffset;
+    const uint32_t* b = g.kmerIds + job.bOffset;
+    int32_t bestScore, bestI, bestJ;
+    bandedOverlapDp(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, hPrev, hCur, traceAcc, trace + job.traceOffset,
+                    bestScore, bestI, bestJ);
+    __syncwarp();
+    uint2* out = ordinals + job.outOffset;
+    uint32_t count = 0;
+    tracebackPath(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, [&](uint32_t x, uint32_t y) {
+        if(a[x] == b[y]) {
+            if(lane == 0) out[count] = make_uint2(x, y);
+            count++;
+        }
+    });
+    if(lane == 0) counts[p] = count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue, one thread per candidate: AlignmentInfo::create (src/Alignment.cpp:67-113), the filters of
+// computeAlignmentsThreadFunction (src/AssemblerAlign.cpp:438-483) and the compressed size
+// (src/compressAlignment.cpp:11-70). ordinals are stored last-first; entry k of the alignment is
+// ord[count-1-k].
+struct FilterOptions {
+    uint64_t minAlignedMarkerCount, maxSkip, maxDrift, maxTrim;
+    double minAlignedFraction;
+    uint32_t suppressContainments;
+};
+
+__device__ __forceinline__ uint32_t compressedStreakBytes(int32_t skip0, int32_t skip1, uint32_t len)
+{
+    if(skip0 >= 0 && skip0 <= 3 && skip1 >= 0 && skip1 <= 3 && len <= 8) return 1;
+    if(skip0 >= -8 && skip0 <= 7 && skip1 >= -8 && skip1 <= 7 && len <= 32) return 2;
+    if(skip0 >= -512 && skip0 <= 511 && skip1 >= -512 && skip1 <= 511 && len <= 512) return 4;
+    if(skip0 >= -524288 && skip0 <= 524287 && skip1 >= -524288 && skip1 <= 524287 && len <= 2097152) return 8;
+    return 16;
+}
+
+// info words = the 13 words [3..15] of the 64-byte AlignmentData record.
+static __global__ void alignmentInfoKernel(uint32_t n, const DpJob* __restrict__ jobs, const uint2* __restrict__ ordinals,
+                                           const uint32_t* __restrict__ counts, FilterOptions f,
+                                           uint32_t* __restrict__ infoWords, uint32_t* __restrict__ keep,
+                                           uint32_t* __restrict__ compressedBytes)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const DpJob job = jobs[p];
+    keep[p] = 0;
+    compressedBytes[p] = 0;
+    if(job.state != kStateRun) return;
+    const uint32_t count = counts[p];
+    if(count == 0) return;                               // empty alignments are never stored
+    const uint2* ord = ordinals + job.outOffset;
+    int32_t mn = INT32_MAX, mx = INT32_MIN;
+    uint32_t maxSkip = 0, maxDrift = 0;
+    long long sum = 0;
+    uint32_t bytes = 0;
+    uint2 prev = make_uint2(0, 0);
+    uint2 streakStart = make_uint2(0, 0);
+    uint2 lastOfPreviousStreak = make_uint2(0, 0);
+    uint32_t streakLen = 0;
+    for(uint32_t k = 0; k < count; k++) {
+        const uint2 o = ord[count - 1 - k];
+        const int32_t off = int32_t(o.x) - int32_t(o.y);
+        mn = min(mn, off); mx = max(mx, off); sum += off;
+        if(k) {
+            maxSkip = max(maxSkip, uint32_t(abs(int32_t(o.x) - int32_t(prev.x))));
+            maxSkip = max(maxSkip, uint32_t(abs(int32_t(o.y) - int32_t(prev.y))));
+            maxDrift = max(maxDrift, uint32_t(abs(off - (int32_t(prev.x) - int32_t(prev.y)))));
+        }
+        if(k && o.x == prev.x + 1 && o.y == prev.y + 1) streakLen++;
+        else {
+            if(k) {
+                bytes += compressedStreakBytes(int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
+                                               int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
+                lastOfPreviousStreak = prev;
+            }
+            streakStart = o; streakLen = 1;
+        }
+        prev = o;
+    }
+    bytes += compressedStreakBytes(int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
+                                   int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
+    const uint2 first = ord[count - 1], last = ord[0];
+    // Filters, in the reference's order.
+    if(uint64_t(count) < f.minAlignedMarkerCount) return;
+    const double frac0 = double(count) / double(last.x + 1 - first.x);
+    const double frac1 = double(count) / double(last.y + 1 - first.y);
+    if(min(frac0, frac1) < f.minAlignedFraction) return;
+    const uint32_t leftTrim = min(first.x, first.y);
+    const uint32_t rightTrim = min(job.nx - 1 - last.x, job.ny - 1 - last.y);
+    if(leftTrim > f.maxTrim || rightTrim > f.maxTrim) return;
+    if(uint64_t(maxSkip) > f.maxSkip) return;
+    if(uint64_t(maxDrift) > f.maxDrift) return;
+    if(f.suppressContainments) {
+        const uint32_t mt = uint32_t(f.maxTrim);
+        if((first.x <= mt && job.nx - 1 - last.x <= mt) || (first.y <= mt && job.ny - 1 - last.y <= mt)) return;
+    }
+    uint32_t* w = infoWords + 13ull * p;
+    w[0] = job.nx; w[1] = first.x; w[2] = last.x;
+    w[3] = job.ny; w[4] = first.y; w[5] = last.y;
+    w[6] = count; w[7] = uint32_t(mn); w[8] = uint32_t(mx);
+    w[9] = uint32_t(int32_t(round(double(sum) / double(count))));
+    w[10] = maxSkip; w[11] = maxDrift; w[12] = 0;
+    keep[p] = 1;
+    compressedBytes[p] = bytes;
+}
+
+__device__ __forceinline__ uint32_t writeCompressedStreak(uint8_t* out, int32_t skip0, int32_t skip1, uint32_t len)
+{
+    const uint64_t nm1 = len - 1;
+    if(skip0 >= 0 && skip0 <= 3 && skip1 >= 0 && skip1 <= 3 && len <= 8) {
+        out[0] = uint8_t(0u | (uint32_t(skip0) << 1) | (uint32_t(skip1) << 3) | (uint32_t(nm1) << 5));
+        return 1;
+    }
+    uint64_t v; uint32_t bytes;
+    if(skip0 >= -8 && skip0 <= 7 && skip1 >= -8 && skip1 <= 7 && len <= 32) {
+        v = 1u | ((uint32_t(skip0) & 0xFu) << 3) | ((uint32_t(skip1) & 0xFu) << 7) | (uint32_t(nm1) << 11); bytes = 2;
+    } else if(skip0 >= -512 && skip0 <= 511 && skip1 >= -512 && skip1 <= 511 && len <= 512) {
+        v = 3u | ((uint32_t(skip0) & 0x3FFu) << 3) | ((uint32_t(skip1) & 0x3FFu) << 13) | (uint32_t(nm1) << 23); bytes = 4;
+    } else if(skip0 >= -524288 && skip0 <= 524287 && skip1 >= -524288 && skip1 <= 524287 && len <= 2097152) {
+        v = 5ull | ((uint64_t(int64_t(skip0)) & 0xFFFFFull) << 3) | ((uint64_t(int64_t(skip1)) & 0xFFFFFull) << 23) | (nm1 << 43); bytes = 8;
+    } else {
+        const uint32_t w[4] = {7u, uint32_t(skip0), uint32_t(skip1), uint32_t(nm1)};
+        for(int i = 0; i < 16; i++) out[i] = uint8_t(w[i >> 2] >> (8 * (i & 3)));
+        return 16;
+    }
+    for(uint32_t i = 0; i < bytes; i++) out[i] = uint8_t(v >> (8 * i));
+    return bytes;
+}
+
+// One thread per kept candidate: 64-byte AlignmentData record + compressed alignment bytes.
+static __global__ void alignmentWriteKernel(uint32_t n, const uint32_t* __restrict__ candidates, const DpJob* __restrict__ jobs,
+                                            const uint2* __restrict__ ordinals, const uint32_t* __restrict__ counts,
+                                            const uint32_t* __restrict__ infoWords, const uint32_t* __restrict__ keep,
+                                            const uint32_t* __restrict__ keepIndex, const unsigned long long* __restrict__ byteOffsets,
+                                            uint64_t recordBase, uint64_t byteBase,
+                                            uint32_t* __restrict__ records, unsigned long long* __restrict__ compressedToc,
+                                            uint8_t* __restrict__ compressedData)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n || !keep[p]) return;
+    const uint64_t r = recordBase + keepIndex[p];
+    uint32_t* rec = records + 16ull * r;
+    rec[0] = candidates[3ull * p]; rec[1] = candidates[3ull * p + 1]; rec[2] = candidates[3ull * p + 2] & 0xffu;
+    for(int i = 0; i < 13; i++) rec[3 + i] = infoWords[13ull * p + i];
+    const uint64_t byteOffset = byteBase + byteOffsets[p];
+    compressedToc[r] = byteOffset;
+    uint8_t* out = compressedData + byteOffset;
+    const uint32_t count = counts[p];
+    const uint2* ord = ordinals + jobs[p].outOffset;
+    uint2 prev = make_uint2(0, 0), streakStart = make_uint2(0, 0), lastOfPreviousStreak = make_uint2(0, 0);
+    uint32_t streakLen = 0, w = 0;
+    for(uint32_t k = 0; k < count; k++) {
+        const uint2 o = ord[count - 1 - k];
+        if(k && o.x == prev.x + 1 && o.y == prev.y + 1) streakLen++;
+        else {
+            if(k) {
+                w += writeCompressedStreak(out + w, int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
+                                           int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
+                lastOfPreviousStreak = prev;
+            }
+            streakStart = o; streakLen = 1;
+        }
+        prev = o;
+    }
+    w += writeCompressedStreak(out + w, int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
+                               int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
+}
+
+} // namespace shb
+
+namespace shb {
+
+// Per-candidate job setup (src/AssemblerAlign.cpp:376-382): oriented reads (readId0, strand 0) and
+// (readId1, sameStrand ? 0 : 1); stage-1 job on the downsampled rows, stage-2 job skeleton on the full rows.
+static __global__ void method3SetupKernel(const uint32_t* __restrict__ candidates, uint32_t n,
+                                          const uint64_t* __restrict__ toc, const uint64_t* __restrict__ dsToc,
+                                          DpJob* __restrict__ jobs1, DpJob* __restrict__ jobs2,
+                                          unsigned long long* __restrict__ traceWords1, unsigned long long* __restrict__ outCount)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const uint32_t r0 = candidates[3ull * p], r1 = candidates[3ull * p + 1];
+    const bool same = (candidates[3ull * p + 2] & 0xffu) != 0;
+    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    DpJob j1, j2;
+    j1.aOffset = dsToc[o0]; j1.nx = uint32_t(dsToc[o0 + 1] - dsToc[o0]);
+    j1.bOffset = dsToc[o1]; j1.ny = uint32_t(dsToc[o1 + 1] - dsToc[o1]);
+    j1.lo = -int32_t(j1.ny); j1.hi = int32_t(j1.nx);
+    j1.traceOffset = 0; j1.outOffset = 0; j1.pad = 0;
+    j1.state = (j1.nx == 0 || j1.ny == 0) ? kStateEmpty : kStateRun;       // src/AssemblerAlign3.cpp:100-106
+    j2.aOffset = toc[o0]; j2.nx = uint32_t(toc[o0 + 1] - toc[o0]);
+    j2.bOffset = toc[o1]; j2.ny = uint32_t(toc[o1 + 1] - toc[o1]);
+    j2.lo = 0; j2.hi = 0; j2.traceOffset = 0; j2.outOffset = 0; j2.pad = 0;
+    j2.state = (j1.state == kStateRun) ? kStateSkipped : kStateEmpty;       // stage 1 overwrites it when it runs
+    jobs1[p] = j1; jobs2[p] = j2;
+    traceWords1[p] = (j1.state == kStateRun) ? dpTraceWords(j1.nx, j1.lo, j1.hi) : 0ull;
+    outCount[p] = min(j2.nx, j2.ny);
+}
+
+static __global__ void setTraceOffsetsKernel(DpJob* __restrict__ jobs, uint32_t n, const unsigned long long* __restrict__ traceOffsets,
+                                             const unsigned long long* __restrict__ outOffsets)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    jobs[p].traceOffset = traceOffsets[p];
+    if(outOffsets) jobs[p].outOffset = outOffsets[p];
+}
+
+static __global__ void stage2TraceWordsKernel(const DpJob* __restrict__ jobs, uint32_t n, unsigned long long* __restrict__ traceWords)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const DpJob j = jobs[p];
+    traceWords[p] = (j.state == kStateRun) ? dpTraceWords(j.nx, j.lo, j.hi) : 0ull;
+}
+
+static __global__ void widenBytesKernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* __restrict__ out)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p < n) out[p] = in[p];
+}
+
+} // namespace shb

@@ -13,6 +13,11 @@ void setLastError(const std::string& message) { g_lastError = message; }
 void lowhash0(shb_context* c, const shb_lowhash_params& p, void** candidatesOut, uint64_t* candidateCountOut,
               uint64_t* statsOut, uint64_t* iterSummary, uint64_t maxIterSummary, shb_lowhash_result* result);
 
+void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, const shb_align_options& o,
+                       void** alignmentDataOut, uint64_t* alignmentCountOut,
+                       uint64_t** compressedTocOut, uint8_t** compressedDataOut, shb_align_result* result);
+void destroyAlignCache(shb_context* c);
+
 template<class F> shb_status guarded(F&& f)
 {
     try {
@@ -86,6 +91,7 @@ void shb_context_destroy(shb_context* c)
     if(!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    destroyAlignCache(c);
     if(c->stream) cudaStreamDestroy(c->stream);
     for(int i = 0; i < 2; i++) if(c->copyStream[i]) cudaStreamDestroy(c->copyStream[i]);
     delete c;
@@ -163,6 +169,16 @@ shb_status shb_find_alignment_candidates_lowhash0(
     shb_status s = shb_set_markers(c, readCount, 0, readCount, toc, markerData7, readFlags, toc ? toc[2 * readCount] : 0);
     if(s != SHB_OK) return s;
     return shb_lowhash0(c, params, candidates, candidateCount, stats, nullptr, 0, result);
+}
+
+shb_status shb_compute_alignments(shb_context* c, const void* candidates, uint64_t candidateCount,
+                                  const shb_align_options* options, void** alignmentData, uint64_t* alignmentCount,
+                                  uint64_t** compressedToc, uint8_t** compressedData, shb_align_result* result)
+{
+    return guarded([&] {
+        SHB_REQUIRE(c && options && alignmentData && alignmentCount && compressedToc && compressedData, SHB_ERR_INVALID, "Null argument.");
+        computeAlignments(c, candidates, candidateCount, *options, alignmentData, alignmentCount, compressedToc, compressedData, result);
+    });
 }
 
 } // extern "C"

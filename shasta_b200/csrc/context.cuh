@@ -38,4 +38,7 @@ struct shb_context {
     shb::DeviceBuffer<uint32_t> accValsA, accValsB;
     shb::DeviceBuffer<unsigned long long> stats;
     shb::DeviceBuffer<uint32_t> candidatesDev;
+
+    // ---- alignment cache (downsampled markers; see align.cu) ------------------------------------
+    void* alignCache = nullptr;
 };

@@ -55,7 +55,7 @@ constexpr int kSweepThreads = 256;
 constexpr int kSweepPositionsPerThread = 8;
 constexpr int kSweepTile = kSweepThreads * kSweepPositionsPerThread;      // 2048 positions per block
 constexpr int kMaxFusedIterations = 16;
-constexpr int kSweepStage = 128;          // staged low hashes per iteration per block before spilling
+constexpr int kSweepQueue = 2048;         // low hashes queued per block before the (rare) inline path
 constexpr int kMaxTemplatedM = 8;
 
 struct SweepArgs {
@@ -85,21 +85,42 @@ __device__ __forceinline__ uint64_t murmurMix(uint64_t k)
     return k;
 }
 
+// Which oriented read does marker position p belong to, and is the feature starting at p valid
+// (inside one read, read not palindromic: src/LowHash0.cpp:325,337,344)? Returns the LOCAL
+// oriented read index or 0xffffffff.
+__device__ __forceinline__ uint32_t resolveFeature(const SweepArgs& a, uint64_t p, uint32_t m)
+{
+    uint32_t lo = 0, hi = a.orientedReadCount;          // largest lo with toc[lo] <= p
+    while(hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if(a.toc[mid] <= p) lo = mid; else hi = mid;
+    }
+    const bool inside = (p + m <= a.toc[lo + 1]);
+    const bool palindromic = (a.readFlags[(a.orientedReadBase + lo) >> 1] & 1u) != 0;
+    return (inside && !palindromic) ? lo : 0xffffffffu;
+}
+
+// The hot loop only hashes and queues the (about hashFraction) low hashes in shared memory; the
+// divergent work (toc binary search, validity, output slot) is done afterwards by all threads of the
+// block over the queue, so a warp never serialises behind one lane's rare path.
 template<int MM> __global__ void __launch_bounds__(kSweepThreads)
 lowhashSweepKernel(const SweepArgs a)
 {
     constexpr int kHalo = 2 * kMaxFusedIterations;       // >= any supported m (generic path caps m at 32)
     __shared__ uint32_t sk[kSweepTile + kHalo];
-    __shared__ uint64_t stageKeys[kMaxFusedIterations][kSweepStage];
-    __shared__ uint32_t stageVals[kMaxFusedIterations][kSweepStage];
-    __shared__ uint32_t stageCount[kMaxFusedIterations];
-    __shared__ unsigned long long stageBase[kMaxFusedIterations];
+    __shared__ uint64_t queueHash[kSweepQueue];
+    __shared__ uint32_t queueMeta[kSweepQueue];          // in: local | s<<16   out: orientedRead (global) or ~0
+    __shared__ uint32_t queueRank[kSweepQueue];
+    __shared__ uint32_t queueCount;
+    __shared__ uint32_t seedCount[kMaxFusedIterations];
+    __shared__ unsigned long long seedBase[kMaxFusedIterations];
 
     const uint64_t M = 0xc6a4a7935bd1e995ull;
     const uint32_t m = (MM > 0) ? uint32_t(MM) : a.m;
     const uint64_t tileBase = uint64_t(blockIdx.x) * kSweepTile;
 
-    if(threadIdx.x < kMaxFusedIterations) stageCount[threadIdx.x] = 0;
+    if(threadIdx.x < kMaxFusedIterations) seedCount[threadIdx.x] = 0;
+    if(threadIdx.x == 0) queueCount = 0;
     for(int i = threadIdx.x; i < kSweepTile + kHalo; i += kSweepThreads) {
         const uint64_t g = tileBase + i;
         sk[i] = (g < a.markerCount) ? a.kmerIds[g] : 0u;
@@ -108,6 +129,7 @@ lowhashSweepKernel(const SweepArgs a)
 
     const uint32_t K = a.iterationCount;
     const uint64_t lenTimesM = uint64_t(4u * m) * M;
+    const uint64_t threshold = a.hashThreshold;
 
 #pragma unroll 1
     for(int slot = 0; slot < kSweepPositionsPerThread; slot++) {
@@ -133,13 +155,10 @@ lowhashSweepKernel(const SweepArgs a)
         const bool hasTail = (m & 1u) != 0;
         const uint64_t tail = hasTail ? uint64_t(sk[local + m - 1]) : 0ull;
 
-        int resolved = 0;           // 0 = not looked up yet, 1 = valid feature, 2 = invalid
-        uint32_t orientedRead = 0;
-
-#pragma unroll 1
-        for(uint32_t s = 0; s < K; s++) {
-            const uint64_t seed = uint64_t(a.iterationBegin + s) * 37ull;
-            uint64_t h = seed ^ lenTimesM;
+        uint64_t seedTerm = (uint64_t(a.iterationBegin) * 37ull);
+#pragma unroll 2
+        for(uint32_t s = 0; s < K; s++, seedTerm += 37ull) {
+            uint64_t h = seedTerm ^ lenTimesM;
             if(MM > 0) {
 #pragma unroll
                 for(int b = 0; b < MM / 2; b++) { h ^= mixed[b]; h *= M; }
@@ -150,32 +169,19 @@ lowhashSweepKernel(const SweepArgs a)
             h ^= h >> 47;
             h *= M;
             h ^= h >> 47;
-            if(h < a.hashThreshold) {
-                if(resolved == 0) {
-                    // Largest o with toc[o] <= p.
-                    uint32_t lo = 0, hi = a.orientedReadCount;
-                    while(hi - lo > 1) {
-                        const uint32_t mid = lo + ((hi - lo) >> 1);
-                        if(a.toc[mid] <= p) lo = mid; else hi = mid;
-                    }
-                    orientedRead = lo;
-                    const bool inside = (p + m <= a.toc[lo + 1]);
-                    const bool palindromic = (a.readFlags[(a.orientedReadBase + lo) >> 1] & 1u) != 0;
-                    resolved = (inside && !palindromic) ? 1 : 2;
-                }
-                if(resolved == 1) {
-                    const uint64_t key = ((h & a.bucketMask) << 32) | (h >> 32);
-                    const uint32_t val = a.orientedReadBase + orientedRead;
-                    const uint32_t li = atomicAdd(&stageCount[s], 1u);
-                    if(li < (uint32_t)kSweepStage) {
-                        stageKeys[s][li] = key;
-                        stageVals[s][li] = val;
-                    } else {
-                        // Staging full (pathological hashFraction or repeats): spill straight to HBM.
+            if(h < threshold) {
+                const uint32_t q = atomicAdd(&queueCount, 1u);
+                if(q < (uint32_t)kSweepQueue) {
+                    queueHash[q] = h;
+                    queueMeta[q] = uint32_t(local) | (s << 16);
+                } else {
+                    // Queue full (pathological hashFraction): do the rare path inline.
+                    const uint32_t o = resolveFeature(a, p, m);
+                    if(o != 0xffffffffu) {
                         const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
                         if(gi < a.capacity) {
-                            a.keys[uint64_t(s) * a.capacity + gi] = key;
-                            a.vals[uint64_t(s) * a.capacity + gi] = val;
+                            a.keys[uint64_t(s) * a.capacity + gi] = ((h & a.bucketMask) << 32) | (h >> 32);
+                            a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
                         }
                     }
                 }
@@ -183,19 +189,36 @@ lowhashSweepKernel(const SweepArgs a)
         }
     }
     __syncthreads();
-    if(threadIdx.x < K) {
-        const uint32_t c = min(stageCount[threadIdx.x], (uint32_t)kSweepStage);
-        stageBase[threadIdx.x] = c ? atomicAdd(&a.counts[threadIdx.x], (unsigned long long)c) : 0ull;
+
+    // Queue pass A: resolve each queued low hash to its oriented read, rank it within (block, seed).
+    const uint32_t nq = min(queueCount, (uint32_t)kSweepQueue);
+    for(uint32_t q = threadIdx.x; q < nq; q += kSweepThreads) {
+        const uint32_t meta = queueMeta[q];
+        const uint32_t local = meta & 0xffffu, s = meta >> 16;
+        const uint32_t o = resolveFeature(a, tileBase + local, m);
+        if(o != 0xffffffffu) {
+            queueRank[q] = atomicAdd(&seedCount[s], 1u) | (s << 24);
+            queueMeta[q] = a.orientedReadBase + o;
+        } else {
+            queueMeta[q] = 0xffffffffu;
+        }
     }
     __syncthreads();
-    for(uint32_t s = 0; s < K; s++) {
-        const uint32_t c = min(stageCount[s], (uint32_t)kSweepStage);
-        for(uint32_t li = threadIdx.x; li < c; li += kSweepThreads) {
-            const unsigned long long gi = stageBase[s] + li;
-            if(gi < a.capacity) {
-                a.keys[uint64_t(s) * a.capacity + gi] = stageKeys[s][li];
-                a.vals[uint64_t(s) * a.capacity + gi] = stageVals[s][li];
-            }
+    if(threadIdx.x < K) {
+        const uint32_t c = seedCount[threadIdx.x];
+        seedBase[threadIdx.x] = c ? atomicAdd(&a.counts[threadIdx.x], (unsigned long long)c) : 0ull;
+    }
+    __syncthreads();
+    // Queue pass B: write (bucketId<<32 | hashHigh, orientedReadId) to the iteration's slab.
+    for(uint32_t q = threadIdx.x; q < nq; q += kSweepThreads) {
+        const uint32_t oread = queueMeta[q];
+        if(oread == 0xffffffffu) continue;
+        const uint32_t s = queueRank[q] >> 24;
+        const unsigned long long gi = seedBase[s] + (queueRank[q] & 0xffffffu);
+        if(gi < a.capacity) {
+            const uint64_t h = queueHash[q];
+            a.keys[uint64_t(s) * a.capacity + gi] = ((h & a.bucketMask) << 32) | (h >> 32);
+            a.vals[uint64_t(s) * a.capacity + gi] = oread;
         }
     }
 }

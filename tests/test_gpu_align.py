@@ -1,0 +1,96 @@
+"""GPU parity tests for Assembler::computeAlignments (method 3) through the C ABI, against the CPU oracle
+(oracle/align_oracle.c) on the same seeded inputs. Bar: bit-exact AlignmentData records and compressed bytes.
+The DP tie-break rule itself is 'parity unpinned' with respect to SeqAn (see oracle/align_oracle.c)."""
+import numpy as np
+import pytest
+
+from oracle import bindings as B
+from shasta_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from shasta_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _dataset(reads, k, seed, **kw):
+    p = synth.SynthParams(reads=reads, k=k, genome_markers=kw.pop("genome_markers", 20000), n50_bases=kw.pop("n50", 15000),
+                          min_bases=kw.pop("min_bases", 8000), seed=seed, **kw)
+    d = synth.generate(p)
+    lp = B.LowHashParams(m=4, hashFraction=0.01, minHashIterationCount=10, minBucketSize=2, maxBucketSize=30, minFrequency=2)
+    cand, _, _ = B.oracle_lowhash0(d["toc"], d["data"], d["flags"], lp)
+    return d, cand
+
+
+def _compare(ctx, d, cand, **opts):
+    from shasta_b200 import capi
+    ctx.set_markers(d["toc"], d["data"], d["flags"])
+    go = capi.make_align_options(**opts)
+    rec, ctoc, cdata, res = capi.compute_alignments(ctx, cand, go)
+    oo = B.make_align_options(**{k: v for k, v in opts.items() if k in B.ALIGN_DEFAULTS})
+    orec, otoc, odata, _ = B.oracle_compute_alignments(d["toc"], d["kmer"], cand, oo, threads=8)
+    assert res.candidateCount == len(cand)
+    assert rec.shape == orec.shape, (rec.shape, orec.shape)
+    assert np.array_equal(rec, orec)
+    assert np.array_equal(ctoc, otoc)
+    assert np.array_equal(cdata, odata)
+    return rec, res
+
+
+def test_method3_nanopore_like(ctx):
+    d, cand = _dataset(300, 10, 5)
+    rec, res = _compare(ctx, d, cand[:1500], alignMethod=3, k=10, maxSkip=30, maxDrift=30, maxTrim=30,
+                        minAlignedMarkerCount=100, minAlignedFraction=0.4, downsamplingFactor=0.1, bandExtend=10, maxBand=1000)
+    assert len(rec) > 100 and res.dpCells > 0
+
+
+def test_method3_may2022_options(ctx):
+    d, cand = _dataset(250, 14, 9)
+    rec, _ = _compare(ctx, d, cand[:1200], alignMethod=3, k=14, maxSkip=100, maxDrift=100, maxTrim=100,
+                      minAlignedMarkerCount=10, minAlignedFraction=0.1, downsamplingFactor=0.05, bandExtend=10, maxBand=1000)
+    assert len(rec) > 100
+
+
+def test_method3_strict_filters_and_containments(ctx):
+    d, cand = _dataset(250, 14, 13, drop=0.02, ins=0.01)
+    _compare(ctx, d, cand[:1000], alignMethod=3, k=14, maxSkip=6, maxDrift=4, maxTrim=2, minAlignedMarkerCount=200,
+             minAlignedFraction=0.97, downsamplingFactor=0.05, bandExtend=10, maxBand=1000)
+    _compare(ctx, d, cand[:1000], alignMethod=3, k=14, maxSkip=30, maxDrift=30, maxTrim=30, minAlignedMarkerCount=50,
+             minAlignedFraction=0.3, downsamplingFactor=0.1, bandExtend=5, maxBand=40, suppressContainments=1)
+
+
+def test_method3_random_pairs_and_scores(ctx):
+    # Unrelated read pairs (mostly empty / rejected alignments) and non-default scores.
+    d, _ = _dataset(120, 10, 21)
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 119, 600)
+    b = rng.integers(0, 119, 600)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    ok = lo < hi
+    cand = np.stack([lo[ok], hi[ok], rng.integers(0, 2, ok.sum())], 1).astype(np.uint32)
+    _compare(ctx, d, cand, alignMethod=3, k=10, maxSkip=30, maxDrift=30, maxTrim=30, minAlignedMarkerCount=5,
+             minAlignedFraction=0.05, downsamplingFactor=0.2, bandExtend=10, maxBand=1000)
+    _compare(ctx, d, cand, alignMethod=3, k=10, maxSkip=50, maxDrift=50, maxTrim=1000, minAlignedMarkerCount=3,
+             minAlignedFraction=0.0, matchScore=3, mismatchScore=-2, gapScore=-1, downsamplingFactor=0.3,
+             bandExtend=3, maxBand=200)
+
+
+def test_alignment_properties(ctx):
+    # Size-independent properties of the stored alignments: ordinals strictly increasing, codec round trip.
+    from shasta_b200 import capi
+    d, cand = _dataset(200, 10, 33)
+    ctx.set_markers(d["toc"], d["data"], d["flags"])
+    rec, ctoc, cdata, _ = capi.compute_alignments(ctx, cand[:800], capi.make_align_options(k=10, minAlignedMarkerCount=50))
+    assert len(rec)
+    for i in range(len(rec)):
+        ords = B.oracle_decompress(cdata[int(ctoc[i]):int(ctoc[i + 1])])
+        assert len(ords) == rec[i, 9]
+        assert (np.diff(ords[:, 0].astype(np.int64)) > 0).all() and (np.diff(ords[:, 1].astype(np.int64)) > 0).all()
+        assert ords[0, 0] == rec[i, 4] and ords[-1, 0] == rec[i, 5] and ords[0, 1] == rec[i, 7] and ords[-1, 1] == rec[i, 8]
+        off = ords[:, 0].astype(np.int64) - ords[:, 1].astype(np.int64)
+        assert off.min() == np.int32(rec[i, 10]) and off.max() == np.int32(rec[i, 11])
