@@ -1,4 +1,6 @@
 // computeAlignments on the GPU: host orchestration (src/AssemblerAlign.cpp:208-495 of chanzuckerberg/shasta).
+// Method 3: stage 1 (downsampled, unbanded) -> band -> stage 2 (banded, all markers) -> epilogue.
+// Method 4: Align4 front end (cells/components) -> one banded DP per component -> best -> epilogue.
 #include "context.cuh"
 #include "align_kernels.cuh"
 
@@ -30,42 +32,39 @@ struct Events {
 // Band-width classes: one launch per class so that shared memory is sized for the class.
 const uint32_t kClassLimits[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384};
 constexpr int kClassCount = 9;
+constexpr uint32_t kMaxBandWidth = 16384;
 
 uint32_t warpsForClass(uint32_t wMax)
 {
     // 3 * (wMax + 1) ints per warp; keep a block under ~200 KB of shared memory.
     const uint64_t perWarp = 3ull * (wMax + 1) * 4;
-    uint32_t w = uint32_t(std::min<uint64_t>(kDpMaxWarpsPerBlock, (200ull * 1024) / perWarp));
+    const uint32_t w = uint32_t(std::min<uint64_t>(kDpMaxWarpsPerBlock, (200ull * 1024) / perWarp));
     return w ? w : 1;
 }
 
-} // namespace
-
-// Downsampled marker CSR for method 3 (cached in the context per (k, downsamplingFactor)).
-struct DownsampledMarkers {
+// Derived per-marker data cached in the context (per marker generation).
+struct AlignCache {
+    // method 3: downsampled marker CSR
     DeviceBuffer<uint64_t> dsToc;
     DeviceBuffer<uint32_t> dsKmer, dsOrdinal;
-    uint64_t total = 0;
-    uint32_t maxRow = 0;
-    uint32_t k = 0;
-    double factor = -1.;
-    const uint32_t* forKmerIds = nullptr;
+    uint32_t dsMaxRow = 0, dsK = 0;
+    double dsFactor = -1.;
+    uint64_t dsGeneration = ~0ull;
+    // method 4: markers sorted by k-mer id within each oriented read
+    DeviceBuffer<uint32_t> sortedKmer, sortedOrdinal;
+    uint64_t sortedGeneration = ~0ull;
 };
 
-static DownsampledMarkers& downsampled(shb_context* c)
+AlignCache& cache(shb_context* c)
 {
-    if(!c->alignCache) c->alignCache = new DownsampledMarkers();
-    return *static_cast<DownsampledMarkers*>(c->alignCache);
-}
-void destroyAlignCache(shb_context* c)
-{
-    if(c->alignCache) { delete static_cast<DownsampledMarkers*>(c->alignCache); c->alignCache = nullptr; }
+    if(!c->alignCache) c->alignCache = new AlignCache();
+    return *static_cast<AlignCache*>(c->alignCache);
 }
 
-static void buildDownsampled(shb_context* c, uint32_t k, double factor)
+void buildDownsampled(shb_context* c, uint32_t k, double factor)
 {
-    DownsampledMarkers& ds = downsampled(c);
-    if(ds.k == k && ds.factor == factor && ds.forKmerIds == c->kmerIds && ds.dsToc.get()) return;
+    AlignCache& ds = cache(c);
+    if(ds.dsK == k && ds.dsFactor == factor && ds.dsGeneration == c->markerGeneration && ds.dsToc.get()) return;
     cudaStream_t st = c->stream;
     const uint64_t M = c->localMarkerCount;
     const uint32_t rows = uint32_t(2 * c->readCountTotal);
@@ -78,16 +77,13 @@ static void buildDownsampled(shb_context* c, uint32_t k, double factor)
     c->scanWs.reserve(scanWorkspaceElements(chunk));
     c->scalars.reserve(64);
     uint32_t* totalDev = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
-    // Pass 1 sizes the output exactly; pass 2 compacts.
-    std::vector<uint64_t> chunkBase;
+    // Pass 0 sizes the output exactly; pass 1 compacts.
     uint64_t total = 0;
     for(int pass = 0; pass < 2; pass++) {
         if(pass == 1) { ds.dsKmer.reserve(total + 1); ds.dsOrdinal.reserve(total + 1); }
         uint64_t running = 0;
-        size_t ci = 0;
-        for(uint64_t begin = 0; begin < M || (M == 0 && begin == 0); begin += chunk, ci++) {
+        for(uint64_t begin = 0; begin < M; begin += chunk) {
             const uint32_t n = uint32_t(std::min<uint64_t>(chunk, M - begin));
-            if(n == 0) break;
             SHB_LAUNCH(downsampleFlagsKernel, ceilDiv(n, 256), 256, 0, st, c->kmerIds, begin, n, k, hashThreshold, c->flagsBuf.get());
             exclusiveScan<uint32_t>(c->flagsBuf.get(), c->indexBuf.get(), n, totalDev, c->scanWs.get(), st);
             const uint32_t t = readBack<uint32_t>(totalDev, st);
@@ -109,7 +105,108 @@ static void buildDownsampled(shb_context* c, uint32_t k, double factor)
     SHB_CUDA(cudaStreamSynchronize(st));
     uint32_t maxRow = 0;
     for(uint32_t r = 0; r < rows; r++) maxRow = std::max<uint32_t>(maxRow, uint32_t(hostToc[r+1] - hostToc[r]));
-    ds.total = total; ds.maxRow = maxRow; ds.k = k; ds.factor = factor; ds.forKmerIds = c->kmerIds;
+    ds.dsMaxRow = maxRow; ds.dsK = k; ds.dsFactor = factor; ds.dsGeneration = c->markerGeneration;
+}
+
+// computeSortedMarkers (src/AssemblerAlign4.cpp:190-261): per oriented read, (kmerId, ordinal) sorted by kmerId.
+void buildSortedMarkers(shb_context* c, uint32_t k)
+{
+    AlignCache& sc = cache(c);
+    if(sc.sortedGeneration == c->markerGeneration && sc.sortedKmer.get()) return;
+    cudaStream_t st = c->stream;
+    const uint64_t M = c->localMarkerCount;
+    const uint32_t rows = uint32_t(2 * c->readCountTotal);
+    sc.sortedKmer.reserve(M + 1);
+    sc.sortedOrdinal.reserve(M + 1);
+    const std::vector<uint64_t>& toc = c->tocHost;
+    DeviceBuffer<uint64_t> keysA, keysB;
+    DeviceBuffer<uint32_t> valsA, valsB;
+    const uint64_t chunkLimit = 1ull << 28;
+    uint32_t rowBegin = 0;
+    while(rowBegin < rows) {
+        uint32_t rowEnd = rowBegin + 1;
+        while(rowEnd < rows && toc[rowEnd + 1] - toc[rowBegin] <= chunkLimit) rowEnd++;
+        const uint64_t markerBegin = toc[rowBegin];
+        const uint64_t n64 = toc[rowEnd] - markerBegin;
+        SHB_REQUIRE(n64 < (1ull << 32), SHB_ERR_INVALID, "An oriented read has more than 2^32-1 markers.");
+        const uint32_t n = uint32_t(n64);
+        if(n) {
+            keysA.reserve(n); keysB.reserve(n); valsA.reserve(n); valsB.reserve(n);
+            SHB_LAUNCH(sortedMarkerKeysKernel, ceilDiv(n, 256), 256, 0, st, c->kmerIds, (const uint64_t*)c->toc.get(),
+                       rowBegin, rowEnd, markerBegin, n, keysA.get(), valsA.get());
+            uint32_t rowBits = 1;
+            while((1ull << rowBits) < uint64_t(rowEnd - rowBegin)) rowBits++;
+            const int ranges[2][2] = {{0, int(2 * k)}, {32, 32 + int(rowBits)}};
+            const bool inB = radixSort<true>(keysA.get(), keysB.get(), valsA.get(), valsB.get(), n, ranges, 2, c->sortWs, st);
+            SHB_LAUNCH(sortedMarkerUnpackKernel, ceilDiv(n, 256), 256, 0, st, (const uint64_t*)(inB ? keysB.get() : keysA.get()), n,
+                       sc.sortedKmer.get() + markerBegin);
+            SHB_CUDA(cudaMemcpyAsync(sc.sortedOrdinal.get() + markerBegin, inB ? valsB.get() : valsA.get(), 4ull * n,
+                                     cudaMemcpyDeviceToDevice, st));
+        }
+        rowBegin = rowEnd;
+    }
+    SHB_CUDA(cudaStreamSynchronize(st));
+    sc.sortedGeneration = c->markerGeneration;
+}
+
+// Buffers shared by both methods for one batch of candidates.
+struct Batch {
+    DeviceBuffer<uint32_t> cand, counts, infoWords, jobKeep, jobBytes, keep, keepIndex, bytes32, selected, records;
+    DeviceBuffer<DpJob> jobs1, jobs;
+    DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, bytes64, bytesOff, scanWs64, ctoc;
+    DeviceBuffer<uint32_t> trace;
+    DeviceBuffer<uint2> ordinals;
+    DeviceBuffer<uint8_t> cdata;
+    // method 4
+    DeviceBuffer<unsigned long long> cellCnt, cellOff;
+    DeviceBuffer<uint32_t> gridCounts, gridAux, gridList, componentCount, jobOffsets;
+    DeviceBuffer<uint8_t> gridFlags;
+    DeviceBuffer<int32_t> gridBands;
+};
+
+struct DpTotals { unsigned long long traceWords = 0; double ms = 0.; };
+
+// Scratch offsets + the banded DP + traceback for nJobs jobs whose lo/hi/state are set.
+void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* sequences, DpScores scores, uint32_t maxWidth,
+                   Events& ev, DpTotals& totals)
+{
+    cudaStream_t st = c->stream;
+    unsigned long long* total64 = c->scalars.get() + 48;
+    b.scanWs64.reserve(scanWorkspaceElements(nJobs));
+    b.twOff.reserve(nJobs); b.outOff.reserve(nJobs); b.counts.reserve(nJobs);
+    exclusiveScan<unsigned long long>(b.tw.get(), b.twOff.get(), nJobs, total64, b.scanWs64.get(), st);
+    const unsigned long long traceWords = readBack<unsigned long long>(total64, st);
+    exclusiveScan<unsigned long long>(b.outCnt.get(), b.outOff.get(), nJobs, total64, b.scanWs64.get(), st);
+    const unsigned long long ordinalSlots = readBack<unsigned long long>(total64, st);
+    b.trace.reserve(traceWords + 1);
+    b.ordinals.reserve(ordinalSlots + 1);
+    totals.traceWords += traceWords;
+    SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nJobs, 256), 256, 0, st, b.jobs.get(), nJobs, (const unsigned long long*)b.twOff.get(),
+               (const unsigned long long*)b.outOff.get());
+    SHB_CUDA(cudaMemsetAsync(b.counts.get(), 0, 4ull * nJobs, st));
+    BandedArgs g;
+    g.n = nJobs; g.kmerIds = sequences; g.scores = scores;
+    SHB_CUDA(cudaEventRecord(ev.a, st));
+    uint32_t wMin = 0;
+    for(int k = 0; k < kClassCount; k++) {
+        const uint32_t wMax = kClassLimits[k];
+        const uint32_t warps = warpsForClass(wMax);
+        const size_t smem = size_t(warps) * 3 * (wMax + 1) * 4;
+        g.wMin = wMin; g.wMax = wMax;
+        SHB_CUDA(cudaFuncSetAttribute(bandedAlignKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        SHB_LAUNCH(bandedAlignKernel, ceilDiv(nJobs, warps), warps * 32, smem, st, g, (const DpJob*)b.jobs.get(), b.trace.get(),
+                   b.ordinals.get(), b.counts.get());
+        wMin = wMax;
+        if(wMax >= maxWidth) break;
+    }
+    SHB_CUDA(cudaEventRecord(ev.b, st));
+}
+
+} // namespace
+
+void destroyAlignCache(shb_context* c)
+{
+    if(c->alignCache) { delete static_cast<AlignCache*>(c->alignCache); c->alignCache = nullptr; }
 }
 
 
@@ -120,46 +217,52 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     SHB_REQUIRE(c->haveMarkers, SHB_ERR_STATE, "Markers are not accessible.");
     SHB_REQUIRE(c->readBegin == 0 && c->readEnd == c->readCountTotal, SHB_ERR_STATE,
                 "computeAlignments needs the markers of all reads on this GPU.");
-    SHB_REQUIRE(o.alignMethod == 3, SHB_ERR_INVALID, "Only Align.alignMethod 3 is implemented in this build.");
+    SHB_REQUIRE(o.alignMethod == 3 || o.alignMethod == 4, SHB_ERR_INVALID,
+                "Only Align.alignMethod 3 and 4 are implemented (0 and 1 are not on the hot path).");
     SHB_REQUIRE(o.gapScore <= 0, SHB_ERR_INVALID, "Align.gapScore must not be positive.");
     SHB_REQUIRE(o.k >= 1 && o.k <= 16, SHB_ERR_INVALID, "Invalid k.");
     SHB_REQUIRE(n == 0 || candidatesHost != nullptr, SHB_ERR_INVALID, "Null candidates.");
     SHB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     g_launchCount = 0;
-    Events totalEv, dpEv;
+    Events totalEv, dpEv1, dpEv2;
     SHB_CUDA(cudaEventRecord(totalEv.a, st));
     double dpMs = 0.;
+    const bool method4 = (o.alignMethod == 4);
 
-    // Validate candidates on the host (src/AssemblerAlign.cpp:378 asserts readIds[0] < readIds[1]).
+    // src/AssemblerAlign.cpp:378 asserts readIds[0] < readIds[1].
     const uint32_t* cand = static_cast<const uint32_t*>(candidatesHost);
     for(uint64_t i = 0; i < n; i++) {
         SHB_REQUIRE(cand[3*i] < cand[3*i+1] && cand[3*i+1] < c->readCountTotal, SHB_ERR_INVALID, "Invalid alignment candidate.");
     }
 
-    buildDownsampled(c, o.k, o.downsamplingFactor);
-    DownsampledMarkers& ds = downsampled(c);
+    AlignCache& ac = cache(c);
+    uint32_t maxStage1Width = 0;
+    if(method4) {
+        SHB_REQUIRE(o.align4DeltaX >= 1 && o.align4DeltaY >= 1 && o.align4DeltaX < (1ull << 31) && o.align4DeltaY < (1ull << 31),
+                    SHB_ERR_INVALID, "Invalid Align.align4.deltaX / deltaY.");
+        buildSortedMarkers(c, o.k);
+    } else {
+        buildDownsampled(c, o.k, o.downsamplingFactor);
+        maxStage1Width = 2 * ac.dsMaxRow + 2;
+        SHB_REQUIRE(maxStage1Width <= kMaxBandWidth, SHB_ERR_INVALID,
+                    "Downsampled reads are too long for the stage-1 kernel (limit 8191 downsampled markers).");
+    }
+    const uint32_t maxStage2Width = uint32_t(std::max(0, o.maxBand)) + 2;
+    SHB_REQUIRE(maxStage2Width <= kMaxBandWidth, SHB_ERR_INVALID, "Align.maxBand too large for this implementation (limit 16382).");
 
-    const DpScores scores{o.matchScore, o.mismatchScore, o.gapScore};
+    // Method 3 uses the configured scores; Align4 hard-codes 6/-1/-1 (src/Align4.hpp:159-161: never overwritten).
+    const DpScores scores = method4 ? DpScores{6, -1, -1} : DpScores{o.matchScore, o.mismatchScore, o.gapScore};
     FilterOptions fo;
     fo.minAlignedMarkerCount = uint64_t(o.minAlignedMarkerCount); fo.maxSkip = uint64_t(o.maxSkip);
     fo.maxDrift = uint64_t(o.maxDrift); fo.maxTrim = uint64_t(o.maxTrim);
-    fo.minAlignedFraction = o.minAlignedFraction; fo.suppressContainments = o.suppressContainments ? 1u : 0u;
+    fo.minAlignedFraction = o.minAlignedFraction;
+    fo.suppressContainments = (!method4 && o.suppressContainments) ? 1u : 0u;     // method 4 applies it after the selection
 
     const uint32_t batchMax = 32768;
-    DeviceBuffer<uint32_t> dCand, counts, infoWords, keep, keepIndex, cbytes32, records;
-    DeviceBuffer<DpJob> jobs1, jobs2;
-    DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, cbytes, cbytesOff, scanWs64, ctoc;
-    DeviceBuffer<uint32_t> trace;
-    DeviceBuffer<uint2> ordinals;
-    DeviceBuffer<uint8_t> cdata;
-    dCand.reserve(3ull * batchMax); counts.reserve(batchMax); infoWords.reserve(13ull * batchMax);
-    keep.reserve(batchMax); keepIndex.reserve(batchMax); cbytes32.reserve(batchMax);
-    jobs1.reserve(batchMax); jobs2.reserve(batchMax);
-    tw.reserve(batchMax); twOff.reserve(batchMax); outCnt.reserve(batchMax); outOff.reserve(batchMax);
-    cbytes.reserve(batchMax); cbytesOff.reserve(batchMax);
-    scanWs64.reserve(scanWorkspaceElements(batchMax));
-    c->scanWs.reserve(scanWorkspaceElements(batchMax));
+    const uint64_t cellBudget = 192ull << 20;      // method 4: cells of scratch per batch
+    Batch b;
+    c->scanWs.reserve(scanWorkspaceElements(4ull * batchMax * 64));
     c->scalars.reserve(64);
     unsigned long long* total64 = c->scalars.get() + 48;
     uint32_t* total32 = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
@@ -169,28 +272,49 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     std::vector<uint8_t> hostData;
     hostToc.push_back(0);
     uint64_t skipped = 0, dpCells = 0;
-    const uint32_t maxStage1Width = 2 * ds.maxRow + 2;
-    SHB_REQUIRE(maxStage1Width <= 16384, SHB_ERR_INVALID, "Downsampled reads are too long for the stage-1 kernel (limit 8191 markers).");
-    const uint32_t maxStage2Width = uint32_t(std::max(0, o.maxBand)) + 2;
-    SHB_REQUIRE(maxStage2Width <= 16384, SHB_ERR_INVALID, "Align.maxBand too large for this implementation (limit 16382).");
+    const std::vector<uint64_t>& toc = c->tocHost;
 
-    for(uint64_t begin = 0; begin < n; begin += batchMax) {
-        const uint32_t nb = uint32_t(std::min<uint64_t>(batchMax, n - begin));
-        SHB_CUDA(cudaMemcpyAsync(dCand.get(), cand + 3 * begin, 12ull * nb, cudaMemcpyHostToDevice, st));
-        SHB_LAUNCH(method3SetupKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)dCand.get(), nb,
-                   (const uint64_t*)c->toc.get(), (const uint64_t*)ds.dsToc.get(), jobs1.get(), jobs2.get(), tw.get(), outCnt.get());
-        // Stage 1 trace scratch.
-        exclusiveScan<unsigned long long>(tw.get(), twOff.get(), nb, total64, scanWs64.get(), st);
-        const unsigned long long traceWords1 = readBack<unsigned long long>(total64, st);
-        trace.reserve(traceWords1 + 1);
-        SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nb, 256), 256, 0, st, jobs1.get(), nb, (const unsigned long long*)twOff.get(),
-                   (const unsigned long long*)nullptr);
-        Method3Args g1;
-        g1.candidates = dCand.get(); g1.candidateBegin = begin; g1.n = nb;
-        g1.toc = c->toc.get(); g1.dsToc = ds.dsToc.get(); g1.dsKmer = ds.dsKmer.get(); g1.dsOrdinal = ds.dsOrdinal.get();
-        g1.scores = scores; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
-        SHB_CUDA(cudaEventRecord(dpEv.a, st));
-        {
+    for(uint64_t begin = 0; begin < n; ) {
+        // Batch size: bounded number of candidates and (method 4) of grid cells.
+        uint32_t nb = 0;
+        if(method4) {
+            uint64_t cells = 0;
+            while(begin + nb < n && nb < batchMax) {
+                const uint64_t i = begin + nb;
+                const uint64_t o0 = 2ull * cand[3*i], o1 = 2ull * cand[3*i+1] + ((cand[3*i+2] & 0xff) ? 0 : 1);
+                const uint64_t nx = toc[o0+1] - toc[o0], ny = toc[o1+1] - toc[o1];
+                uint64_t cc = 2;
+                if(nx && ny) cc += ((nx + ny - 2) / o.align4DeltaX + 1) * ((nx + ny - 2) / o.align4DeltaY + 1);
+                if(nb && cells + cc > cellBudget) break;
+                cells += cc; nb++;
+            }
+        } else nb = uint32_t(std::min<uint64_t>(batchMax, n - begin));
+
+        b.cand.reserve(3ull * nb);
+        SHB_CUDA(cudaMemcpyAsync(b.cand.get(), cand + 3 * begin, 12ull * nb, cudaMemcpyHostToDevice, st));
+        b.keep.reserve(nb); b.keepIndex.reserve(nb); b.bytes32.reserve(nb); b.bytes64.reserve(nb); b.bytesOff.reserve(nb);
+        b.scanWs64.reserve(scanWorkspaceElements(nb));
+        uint32_t nJobs = 0;
+        const uint32_t* jobIndex = nullptr;
+        DpTotals totals;
+
+        if(!method4) {
+            // ---- method 3 ---------------------------------------------------------------------------
+            nJobs = nb;
+            b.jobs1.reserve(nb); b.jobs.reserve(nb); b.tw.reserve(nb); b.twOff.reserve(nb); b.outCnt.reserve(nb);
+            SHB_LAUNCH(method3SetupKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb,
+                       (const uint64_t*)c->toc.get(), (const uint64_t*)ac.dsToc.get(), b.jobs1.get(), b.jobs.get(), b.tw.get(), b.outCnt.get());
+            exclusiveScan<unsigned long long>(b.tw.get(), b.twOff.get(), nb, total64, b.scanWs64.get(), st);
+            const unsigned long long traceWords1 = readBack<unsigned long long>(total64, st);
+            b.trace.reserve(traceWords1 + 1);
+            dpCells += 16ull * traceWords1;
+            SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nb, 256), 256, 0, st, b.jobs1.get(), nb, (const unsigned long long*)b.twOff.get(),
+                       (const unsigned long long*)nullptr);
+            Method3Args g1;
+            g1.candidates = b.cand.get(); g1.candidateBegin = begin; g1.n = nb;
+            g1.toc = c->toc.get(); g1.dsToc = ac.dsToc.get(); g1.dsKmer = ac.dsKmer.get(); g1.dsOrdinal = ac.dsOrdinal.get();
+            g1.scores = scores; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
+            SHB_CUDA(cudaEventRecord(dpEv1.a, st));
             uint32_t wMin = 0;
             for(int k = 0; k < kClassCount; k++) {
                 const uint32_t wMax = kClassLimits[k];
@@ -198,80 +322,99 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 const size_t smem = size_t(warps) * 3 * (wMax + 1) * 4;
                 g1.wMin = wMin; g1.wMax = wMax;
                 SHB_CUDA(cudaFuncSetAttribute(method3Stage1Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                SHB_LAUNCH(method3Stage1Kernel, ceilDiv(nb, warps), warps * 32, smem, st, g1, jobs1.get(), trace.get(), jobs2.get());
+                SHB_LAUNCH(method3Stage1Kernel, ceilDiv(nb, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get());
                 wMin = wMax;
                 if(wMax >= maxStage1Width) break;
             }
-        }
-        // Stage 2 scratch: trace words and ordinal slots.
-        SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)jobs2.get(), nb, tw.get());
-        exclusiveScan<unsigned long long>(tw.get(), twOff.get(), nb, total64, scanWs64.get(), st);
-        const unsigned long long traceWords2 = readBack<unsigned long long>(total64, st);
-        exclusiveScan<unsigned long long>(outCnt.get(), outOff.get(), nb, total64, scanWs64.get(), st);
-        const unsigned long long ordinalSlots = readBack<unsigned long long>(total64, st);
-        trace.reserve(traceWords2 + 1);
-        ordinals.reserve(ordinalSlots + 1);
-        dpCells += 16ull * (traceWords1 + traceWords2);
-        SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nb, 256), 256, 0, st, jobs2.get(), nb, (const unsigned long long*)twOff.get(),
-                   (const unsigned long long*)outOff.get());
-        SHB_CUDA(cudaMemsetAsync(counts.get(), 0, 4ull * nb, st));
-        BandedArgs g2;
-        g2.n = nb; g2.kmerIds = c->kmerIds; g2.scores = scores;
-        {
-            uint32_t wMin = 0;
-            for(int k = 0; k < kClassCount; k++) {
-                const uint32_t wMax = kClassLimits[k];
-                const uint32_t warps = warpsForClass(wMax);
-                const size_t smem = size_t(warps) * 3 * (wMax + 1) * 4;
-                g2.wMin = wMin; g2.wMax = wMax;
-                SHB_CUDA(cudaFuncSetAttribute(bandedAlignKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                SHB_LAUNCH(bandedAlignKernel, ceilDiv(nb, warps), warps * 32, smem, st, g2, (const DpJob*)jobs2.get(), trace.get(),
-                           ordinals.get(), counts.get());
-                wMin = wMax;
-                if(wMax >= maxStage2Width) break;
+            SHB_CUDA(cudaEventRecord(dpEv1.b, st));
+            SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());
+            runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
+            // Epilogue per job == per candidate.
+            b.infoWords.reserve(13ull * nJobs);
+            SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 128), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
+                       (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.keep.get(), b.bytes32.get());
+            // Candidates the reference would skip with a logged exception.
+            {
+                std::vector<DpJob> hj(nb);
+                SHB_CUDA(cudaMemcpyAsync(hj.data(), b.jobs.get(), sizeof(DpJob) * nb, cudaMemcpyDeviceToHost, st));
+                SHB_CUDA(cudaStreamSynchronize(st));
+                for(const DpJob& j : hj) if(j.state == kStateSkipped) skipped++;
+                float ms = 0.f;
+                SHB_CUDA(cudaEventElapsedTime(&ms, dpEv1.a, dpEv1.b));
+                dpMs += ms;
             }
+        } else {
+            // ---- method 4 ---------------------------------------------------------------------------
+            b.cellCnt.reserve(nb); b.cellOff.reserve(nb); b.componentCount.reserve(nb); b.jobOffsets.reserve(nb); b.selected.reserve(nb);
+            SHB_LAUNCH(align4CellCountKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb, (const uint64_t*)c->toc.get(),
+                       uint32_t(o.align4DeltaX), uint32_t(o.align4DeltaY), b.cellCnt.get());
+            exclusiveScan<unsigned long long>(b.cellCnt.get(), b.cellOff.get(), nb, total64, b.scanWs64.get(), st);
+            const unsigned long long cells = readBack<unsigned long long>(total64, st);
+            b.gridCounts.reserve(cells + 1); b.gridAux.reserve(cells + 1); b.gridList.reserve(cells + 1);
+            b.gridFlags.reserve(cells + 1); b.gridBands.reserve(cells + 1);
+            Align4Args g;
+            g.candidates = b.cand.get(); g.n = nb; g.toc = c->toc.get();
+            g.sortedKmer = ac.sortedKmer.get(); g.sortedOrdinal = ac.sortedOrdinal.get();
+            g.deltaX = uint32_t(o.align4DeltaX); g.deltaY = uint32_t(o.align4DeltaY);
+            g.minEntryCountPerCell = o.align4MinEntryCountPerCell; g.maxDistanceFromBoundary = o.align4MaxDistanceFromBoundary;
+            g.maxBand = int64_t(uint64_t(o.maxBand));
+            g.cellOffsets = b.cellOff.get(); g.counts = b.gridCounts.get(); g.aux = b.gridAux.get(); g.list = b.gridList.get();
+            g.flags = b.gridFlags.get(); g.bands = b.gridBands.get(); g.componentCount = b.componentCount.get();
+            SHB_LAUNCH(align4FrontEndKernel, ceilDiv(nb, 4), 128, 0, st, g);
+            exclusiveScan<uint32_t>(b.componentCount.get(), b.jobOffsets.get(), nb, total32, c->scanWs.get(), st);
+            nJobs = readBack<uint32_t>(total32, st);
+            if(nJobs) {
+                b.jobs.reserve(nJobs); b.tw.reserve(nJobs); b.outCnt.reserve(nJobs);
+                SHB_LAUNCH(align4MakeJobsKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb, (const uint64_t*)c->toc.get(),
+                           (const unsigned long long*)b.cellOff.get(), (const int32_t*)b.gridBands.get(),
+                           (const uint32_t*)b.componentCount.get(), (const uint32_t*)b.jobOffsets.get(), b.jobs.get(), b.tw.get(), b.outCnt.get());
+                runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
+                b.infoWords.reserve(13ull * nJobs); b.jobKeep.reserve(nJobs); b.jobBytes.reserve(nJobs);
+                // Align4's own filters (src/Align4.cpp:944-985), identical thresholds, no containment test.
+                SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 128), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
+                           (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.jobKeep.get(), b.jobBytes.get());
+            } else {
+                b.infoWords.reserve(13); b.jobKeep.reserve(1); b.jobBytes.reserve(1); b.jobs.reserve(1); b.counts.reserve(1); b.ordinals.reserve(1);
+            }
+            SHB_LAUNCH(align4SelectKernel, ceilDiv(nb, 256), 256, 0, st, nb, (const uint32_t*)b.jobOffsets.get(),
+                       (const uint32_t*)b.componentCount.get(), (const uint32_t*)b.jobKeep.get(), (const uint32_t*)b.infoWords.get(),
+                       (const uint32_t*)b.jobBytes.get(), o.suppressContainments ? 1u : 0u, uint32_t(o.maxTrim),
+                       b.selected.get(), b.keep.get(), b.bytes32.get());
+            jobIndex = b.selected.get();
         }
-        SHB_CUDA(cudaEventRecord(dpEv.b, st));
-        // Epilogue: info, filters, compressed sizes; then compaction.
-        SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nb, 128), 128, 0, st, nb, (const DpJob*)jobs2.get(), (const uint2*)ordinals.get(),
-                   (const uint32_t*)counts.get(), fo, infoWords.get(), keep.get(), cbytes32.get());
-        exclusiveScan<uint32_t>(keep.get(), keepIndex.get(), nb, total32, c->scanWs.get(), st);
+        dpCells += 16ull * totals.traceWords;
+
+        // ---- compaction + output of the kept alignments ---------------------------------------------------
+        exclusiveScan<uint32_t>(b.keep.get(), b.keepIndex.get(), nb, total32, c->scanWs.get(), st);
         const uint32_t kept = readBack<uint32_t>(total32, st);
-        SHB_LAUNCH(widenBytesKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)cbytes32.get(), nb, cbytes.get());
-        exclusiveScan<unsigned long long>(cbytes.get(), cbytesOff.get(), nb, total64, scanWs64.get(), st);
+        SHB_LAUNCH(widenBytesKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.bytes32.get(), nb, b.bytes64.get());
+        exclusiveScan<unsigned long long>(b.bytes64.get(), b.bytesOff.get(), nb, total64, b.scanWs64.get(), st);
         const unsigned long long bytes = readBack<unsigned long long>(total64, st);
-        {
+        if(nJobs) {
             float ms = 0.f;
-            SHB_CUDA(cudaEventElapsedTime(&ms, dpEv.a, dpEv.b));
+            SHB_CUDA(cudaEventElapsedTime(&ms, dpEv2.a, dpEv2.b));
             dpMs += ms;
         }
-        // Count the candidates the reference would skip with a logged exception.
-        {
-            std::vector<DpJob> hj(nb);
-            SHB_CUDA(cudaMemcpyAsync(hj.data(), jobs2.get(), sizeof(DpJob) * nb, cudaMemcpyDeviceToHost, st));
-            SHB_CUDA(cudaStreamSynchronize(st));
-            for(const DpJob& j : hj) if(j.state == kStateSkipped) skipped++;
-        }
         if(kept) {
-            records.reserve(16ull * kept); ctoc.reserve(kept); cdata.reserve(bytes + 16);
-            SHB_LAUNCH(alignmentWriteKernel, ceilDiv(nb, 128), 128, 0, st, nb, (const uint32_t*)dCand.get(), (const DpJob*)jobs2.get(),
-                       (const uint2*)ordinals.get(), (const uint32_t*)counts.get(), (const uint32_t*)infoWords.get(),
-                       (const uint32_t*)keep.get(), (const uint32_t*)keepIndex.get(), (const unsigned long long*)cbytesOff.get(),
-                       0ull, 0ull, records.get(), ctoc.get(), cdata.get());
+            b.records.reserve(16ull * kept); b.ctoc.reserve(kept); b.cdata.reserve(bytes + 16);
+            SHB_LAUNCH(alignmentWriteKernel, ceilDiv(nb, 128), 128, 0, st, nb, (const uint32_t*)b.cand.get(), (const DpJob*)b.jobs.get(),
+                       (const uint2*)b.ordinals.get(), (const uint32_t*)b.counts.get(), (const uint32_t*)b.infoWords.get(), jobIndex,
+                       (const uint32_t*)b.keep.get(), (const uint32_t*)b.keepIndex.get(), (const unsigned long long*)b.bytesOff.get(),
+                       b.records.get(), b.ctoc.get(), b.cdata.get());
             const size_t r0 = hostRecords.size(), b0 = hostData.size();
             hostRecords.resize(r0 + 16ull * kept);
             hostData.resize(b0 + bytes);
             std::vector<unsigned long long> tocBatch(kept);
-            SHB_CUDA(cudaMemcpyAsync(hostRecords.data() + r0, records.get(), 64ull * kept, cudaMemcpyDeviceToHost, st));
-            SHB_CUDA(cudaMemcpyAsync(tocBatch.data(), ctoc.get(), 8ull * kept, cudaMemcpyDeviceToHost, st));
-            if(bytes) SHB_CUDA(cudaMemcpyAsync(hostData.data() + b0, cdata.get(), bytes, cudaMemcpyDeviceToHost, st));
+            SHB_CUDA(cudaMemcpyAsync(hostRecords.data() + r0, b.records.get(), 64ull * kept, cudaMemcpyDeviceToHost, st));
+            SHB_CUDA(cudaMemcpyAsync(tocBatch.data(), b.ctoc.get(), 8ull * kept, cudaMemcpyDeviceToHost, st));
+            if(bytes) SHB_CUDA(cudaMemcpyAsync(hostData.data() + b0, b.cdata.get(), bytes, cudaMemcpyDeviceToHost, st));
             SHB_CUDA(cudaStreamSynchronize(st));
             for(uint32_t i = 0; i < kept; i++) {
-                // toc entry = start of alignment i; the end is the next start (or the batch end).
                 const uint64_t end = (i + 1 < kept) ? tocBatch[i + 1] : bytes;
                 hostToc.push_back(b0 + end);
             }
         }
+        begin += nb;
     }
 
     SHB_CUDA(cudaEventRecord(totalEv.b, st));

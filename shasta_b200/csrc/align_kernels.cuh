@@ -433,25 +433,27 @@ __device__ __forceinline__ uint32_t writeCompressedStreak(uint8_t* out, int32_t 
 }
 
 // One thread per kept candidate: 64-byte AlignmentData record + compressed alignment bytes.
+// jobIndex maps a candidate to the DP job that produced its alignment (NULL = identity, method 3).
 static __global__ void alignmentWriteKernel(uint32_t n, const uint32_t* __restrict__ candidates, const DpJob* __restrict__ jobs,
                                             const uint2* __restrict__ ordinals, const uint32_t* __restrict__ counts,
-                                            const uint32_t* __restrict__ infoWords, const uint32_t* __restrict__ keep,
+                                            const uint32_t* __restrict__ infoWords, const uint32_t* __restrict__ jobIndex,
+                                            const uint32_t* __restrict__ keep,
                                             const uint32_t* __restrict__ keepIndex, const unsigned long long* __restrict__ byteOffsets,
-                                            uint64_t recordBase, uint64_t byteBase,
                                             uint32_t* __restrict__ records, unsigned long long* __restrict__ compressedToc,
                                             uint8_t* __restrict__ compressedData)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n || !keep[p]) return;
-    const uint64_t r = recordBase + keepIndex[p];
+    const uint32_t j = jobIndex ? jobIndex[p] : p;
+    const uint64_t r = keepIndex[p];
     uint32_t* rec = records + 16ull * r;
     rec[0] = candidates[3ull * p]; rec[1] = candidates[3ull * p + 1]; rec[2] = candidates[3ull * p + 2] & 0xffu;
-    for(int i = 0; i < 13; i++) rec[3 + i] = infoWords[13ull * p + i];
-    const uint64_t byteOffset = byteBase + byteOffsets[p];
+    for(int i = 0; i < 13; i++) rec[3 + i] = infoWords[13ull * j + i];
+    const uint64_t byteOffset = byteOffsets[p];
     compressedToc[r] = byteOffset;
     uint8_t* out = compressedData + byteOffset;
-    const uint32_t count = counts[p];
-    const uint2* ord = ordinals + jobs[p].outOffset;
+    const uint32_t count = counts[j];
+    const uint2* ord = ordinals + jobs[j].outOffset;
     uint2 prev = make_uint2(0, 0), streakStart = make_uint2(0, 0), lastOfPreviousStreak = make_uint2(0, 0);
     uint32_t streakLen = 0, w = 0;
     for(uint32_t k = 0; k < count; k++) {
@@ -523,6 +525,338 @@ static __global__ void widenBytesKernel(const uint32_t* __restrict__ in, uint32_
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p < n) out[p] = in[p];
+}
+
+} // namespace shb
+
+// =============================================================================================
+// Method 4 (Align4) front end — src/Align4.cpp:195-868, one warp per candidate.
+// Only the NUMBER of alignment-matrix entries per (iX,iY) cell matters to the reference (createCells,
+// :380-436), so the sparse matrix is a dense count grid in global scratch. Then: cell flags, forward /
+// backward reachability (children (iX+{0,1}, iY+{-1,0,1}), :682-787), 8-neighbourhood components of the
+// active cells (:792-868) and one band per component (:890-934), in raster order of each component's
+// first cell (the reference's order depends on std::unordered_map iteration; it only matters when two kept
+// components tie on markerCount).
+namespace shb {
+
+struct Align4Args {
+    const uint32_t* candidates; uint32_t n;
+    const uint64_t* toc;
+    const uint32_t* sortedKmer; const uint32_t* sortedOrdinal;     // per oriented read, sorted by kmerId
+    uint32_t deltaX, deltaY;
+    uint64_t minEntryCountPerCell, maxDistanceFromBoundary;
+    int64_t maxBand;
+    const unsigned long long* cellOffsets;      // per candidate: first cell of its scratch (exclusive scan of cell counts)
+    uint32_t* counts;       // per cell: match count, later component label / YMin
+    uint32_t* aux;          // per cell: YMax per component root
+    uint32_t* list;         // per cell: compact list of existing cells (raster indices)
+    uint8_t* flags;         // per cell: 1 exists, 2 nearLeftOrTop, 4 nearRightOrBottom, 8 forward, 16 backward
+    int32_t* bands;         // per cell: (bandMin, bandMax) per component, compact, 2 ints each
+    uint32_t* componentCount;   // per candidate
+};
+
+__device__ __forceinline__ void align4GridSize(uint32_t nx, uint32_t ny, uint32_t deltaX, uint32_t deltaY, uint32_t& nIX, uint32_t& nIY)
+{
+    if(nx == 0 || ny == 0) { nIX = 0; nIY = 0; return; }
+    const uint32_t sizeXY = nx + ny - 1;
+    nIX = (sizeXY - 1) / deltaX + 1;
+    nIY = (sizeXY - 1) / deltaY + 1;
+}
+
+static __global__ void align4CellCountKernel(const uint32_t* __restrict__ candidates, uint32_t n, const uint64_t* __restrict__ toc,
+                                             uint32_t deltaX, uint32_t deltaY, unsigned long long* __restrict__ cellCounts)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const uint32_t r0 = candidates[3ull * p], r1 = candidates[3ull * p + 1];
+    const bool same = (candidates[3ull * p + 2] & 0xffu) != 0;
+    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    uint32_t nIX, nIY;
+    align4GridSize(uint32_t(toc[o0 + 1] - toc[o0]), uint32_t(toc[o1 + 1] - toc[o1]), deltaX, deltaY, nIX, nIY);
+    cellCounts[p] = (unsigned long long)nIX * nIY + 2;      // +2: room for one degenerate band
+}
+
+__device__ __forceinline__ void align4Getxy(int32_t X, int32_t Y, int32_t nx, int32_t& x, int32_t& y)
+{
+    x = (X - Y + nx - 1) / 2;       // C division truncates toward zero, as in src/Align4.cpp:183-191
+    y = (X + Y - nx + 1) / 2;
+}
+
+static __global__ void __launch_bounds__(128) align4FrontEndKernel(Align4Args g)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if(p >= g.n) return;
+    const uint32_t r0 = g.candidates[3ull * p], r1 = g.candidates[3ull * p + 1];
+    const bool same = (g.candidates[3ull * p + 2] & 0xffu) != 0;
+    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    const uint64_t aBegin = g.toc[o0], bBegin = g.toc[o1];
+    const uint32_t nx = uint32_t(g.toc[o0 + 1] - aBegin), ny = uint32_t(g.toc[o1 + 1] - bBegin);
+    uint32_t nIX, nIY;
+    align4GridSize(nx, ny, g.deltaX, g.deltaY, nIX, nIY);
+    const uint32_t nCells = nIX * nIY;
+    const uint64_t base = g.cellOffsets[p];
+    uint32_t* counts = g.counts + base;
+    uint32_t* aux = g.aux + base;
+    uint32_t* list = g.list + base;
+    uint8_t* flags = g.flags + base;
+    int32_t* bands = g.bands + base;
+    if(nCells == 0) { if(lane == 0) g.componentCount[p] = 0; return; }
+
+    for(uint32_t i = lane; i < nCells; i += 32) { counts[i] = 0; flags[i] = 0; }
+    __syncwarp();
+
+    // createAlignmentMatrix (:195-267): every pair of equal k-mers (x in read 0, y in read 1) adds one entry
+    // to cell (X/deltaX, Y/deltaY), X = x + y, Y = y + nx - 1 - x.
+    const uint32_t* sa = g.sortedKmer + aBegin; const uint32_t* oa = g.sortedOrdinal + aBegin;
+    const uint32_t* sb = g.sortedKmer + bBegin; const uint32_t* ob = g.sortedOrdinal + bBegin;
+    for(uint32_t t = lane; t < nx; t += 32) {
+        const uint32_t kmer = sa[t];
+        uint32_t lo = 0, hi = ny;               // lower bound of kmer in sb
+        while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(sb[mid] < kmer) lo = mid + 1; else hi = mid; }
+        const uint32_t x = oa[t];
+        for(uint32_t q = lo; q < ny && sb[q] == kmer; q++) {
+            const uint32_t y = ob[q];
+            const uint32_t X = x + y, Y = nx + y - x - 1;
+            atomicAdd(&counts[(Y / g.deltaY) * nIX + X / g.deltaX], 1u);
+        }
+    }
+    __syncwarp();
+
+    // createCells (:380-436) + compact list of existing cells in raster order.
+    uint32_t listSize = 0;
+    for(uint32_t i0 = 0; i0 < nCells; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool exists = false;
+        if(i < nCells) {
+            const uint32_t cnt = counts[i];
+            exists = cnt > 0 && !(int64_t(cnt) < int64_t(g.minEntryCountPerCell));
+            if(exists) {
+                const uint32_t iX = i % nIX, iY = i / nIX;
+                int32_t x, y;
+                align4Getxy(int32_t(iX * g.deltaX), int32_t((iY + 1) * g.deltaY), int32_t(nx), x, y);
+                const uint32_t dLeft = x < 0 ? 0u : uint32_t(x);
+                align4Getxy(int32_t((iX + 1) * g.deltaX), int32_t(iY * g.deltaY), int32_t(nx), x, y);
+                const uint32_t dRight = (x >= int32_t(nx) - 1) ? 0u : (nx - 1 - uint32_t(x));
+                align4Getxy(int32_t(iX * g.deltaX), int32_t(iY * g.deltaY), int32_t(nx), x, y);
+                const uint32_t dTop = y < 0 ? 0u : uint32_t(y);
+                align4Getxy(int32_t((iX + 1) * g.deltaX), int32_t((iY + 1) * g.deltaY), int32_t(nx), x, y);
+                const uint32_t dBottom = (y >= int32_t(ny) - 1) ? 0u : (ny - 1 - uint32_t(y));
+                uint8_t f = 1;
+                if(uint64_t(dLeft) < g.maxDistanceFromBoundary || uint64_t(dTop) < g.maxDistanceFromBoundary) f |= 2 | 8;   // seeds are forward accessible
+                if(uint64_t(dRight) < g.maxDistanceFromBoundary || uint64_t(dBottom) < g.maxDistanceFromBoundary) f |= 4;
+                flags[i] = f;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, exists);
+        if(exists) list[listSize + __popc(m & ((1u << lane) - 1u))] = i;
+        listSize += __popc(m);
+    }
+    __syncwarp();
+
+    // forwardSearch (:682-729): fixpoint of "a cell is forward accessible if a parent is".
+    for(;;) {
+        bool changed = false;
+        for(uint32_t t = lane; t < listSize; t += 32) {
+            const uint32_t i = list[t];
+            uint8_t f = flags[i];
+            if(f & 8) continue;
+            const int32_t iX = int32_t(i % nIX), iY = int32_t(i / nIX);
+            bool reach = false;
+            for(int dY = -1; dY <= 1 && !reach; dY++) {
+                const int32_t pY = iY - dY;
+                if(pY < 0 || pY >= int32_t(nIY)) continue;
+                for(int dX = 0; dX <= 1; dX++) {
+                    if(dX == 0 && dY == 0) continue;
+                    const int32_t pX = iX - dX;
+                    if(pX < 0) continue;
+                    if(flags[uint32_t(pY) * nIX + uint32_t(pX)] & 8) { reach = true; break; }
+                }
+            }
+            if(reach) { flags[i] = f | 8; changed = true; }
+        }
+        __syncwarp();
+        if(!__any_sync(0xffffffffu, changed)) break;
+    }
+    // backwardSearch (:736-787): seeds = near right/bottom and forward accessible.
+    for(uint32_t t = lane; t < listSize; t += 32) {
+        const uint32_t i = list[t];
+        const uint8_t f = flags[i];
+        if((f & 4) && (f & 8)) flags[i] = f | 16;
+    }
+    __syncwarp();
+    for(;;) {
+        bool changed = false;
+        for(uint32_t t = lane; t < listSize; t += 32) {
+            const uint32_t i = list[t];
+            uint8_t f = flags[i];
+            if(f & 16) continue;
+            const int32_t iX = int32_t(i % nIX), iY = int32_t(i / nIX);
+            bool reach = false;
+            // this cell is a backward child of c0 = (iX - dX, iY - dY), dX in {-1,0}, dY in {-1,0,1}
+            for(int dY = -1; dY <= 1 && !reach; dY++) {
+                const int32_t pY = iY - dY;
+                if(pY < 0 || pY >= int32_t(nIY)) continue;
+                for(int dX = -1; dX <= 0; dX++) {
+                    if(dX == 0 && dY == 0) continue;
+                    const int32_t pX = iX - dX;
+                    if(pX >= int32_t(nIX)) continue;
+                    if(flags[uint32_t(pY) * nIX + uint32_t(pX)] & 16) { reach = true; break; }
+                }
+            }
+            if(reach) { flags[i] = f | 16; changed = true; }
+        }
+        __syncwarp();
+        if(!__any_sync(0xffffffffu, changed)) break;
+    }
+
+    // Connected components of the active cells (8-neighbourhood): min-label propagation; counts[] holds labels.
+    for(uint32_t t = lane; t < listSize; t += 32) {
+        const uint32_t i = list[t];
+        counts[i] = ((flags[i] & 24) == 24) ? i : 0xffffffffu;
+    }
+    __syncwarp();
+    for(;;) {
+        bool changed = false;
+        for(uint32_t t = lane; t < listSize; t += 32) {
+            const uint32_t i = list[t];
+            uint32_t label = counts[i];
+            if(label == 0xffffffffu) continue;
+            const int32_t iX = int32_t(i % nIX), iY = int32_t(i / nIX);
+            uint32_t best = label;
+            for(int dY = -1; dY <= 1; dY++) for(int dX = -1; dX <= 1; dX++) {
+                if(!dX && !dY) continue;
+                const int32_t qX = iX + dX, qY = iY + dY;
+                if(qX < 0 || qY < 0 || qX >= int32_t(nIX) || qY >= int32_t(nIY)) continue;
+                const uint32_t j = uint32_t(qY) * nIX + uint32_t(qX);
+                if((flags[j] & 24) != 24) continue;
+                best = min(best, counts[j]);
+            }
+            if(best < label) { counts[i] = best; changed = true; }
+        }
+        __syncwarp();
+        if(!__any_sync(0xffffffffu, changed)) break;
+    }
+    // Per component: root = the cell whose label is its own raster index = the component's first cell in raster
+    // order, so YMin is the root's row; YMax by atomicMax into aux[root].
+    for(uint32_t t = lane; t < listSize; t += 32) {
+        const uint32_t i = list[t];
+        if(counts[i] == i) aux[i] = i / nIX;
+    }
+    __syncwarp();
+    for(uint32_t t = lane; t < listSize; t += 32) {
+        const uint32_t i = list[t];
+        const uint32_t label = counts[i];
+        if(label != 0xffffffffu && label != i) atomicMax(&aux[label], i / nIX);
+    }
+    __syncwarp();
+    // One band per component (:890-934), components in raster order of their first cell; too-wide bands dropped.
+    uint32_t nBands = 0;
+    for(uint32_t t0 = 0; t0 < listSize; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        bool emit = false;
+        int32_t bandMin = 0, bandMax = 0;
+        if(t < listSize) {
+            const uint32_t i = list[t];
+            if(counts[i] == i) {
+                const uint32_t iYMin = i / nIX, iYMax = aux[i];
+                const uint32_t YMin = iYMin * g.deltaY, YMax = (iYMax + 1) * g.deltaY - 1;
+                bandMin = int32_t(nx) - 1 - int32_t(YMax);
+                bandMax = int32_t(nx) - 1 - int32_t(YMin);
+                emit = !(int64_t(bandMax - bandMin + 1) > g.maxBand);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if(emit) {
+            const uint32_t slot = nBands + __popc(m & ((1u << lane) - 1u));
+            bands[2 * slot] = bandMin;
+            bands[2 * slot + 1] = bandMax;
+        }
+        nBands += __popc(m);
+    }
+    if(lane == 0) g.componentCount[p] = nBands;
+}
+
+// Expand (candidate, component) into DP jobs. jobOffsets = exclusive scan of componentCount.
+static __global__ void align4MakeJobsKernel(const uint32_t* __restrict__ candidates, uint32_t n, const uint64_t* __restrict__ toc,
+                                            const unsigned long long* __restrict__ cellOffsets, const int32_t* __restrict__ bands,
+                                            const uint32_t* __restrict__ componentCount, const uint32_t* __restrict__ jobOffsets,
+                                            DpJob* __restrict__ jobs, unsigned long long* __restrict__ traceWords,
+                                            unsigned long long* __restrict__ outCount)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const uint32_t r0 = candidates[3ull * p], r1 = candidates[3ull * p + 1];
+    const bool same = (candidates[3ull * p + 2] & 0xffu) != 0;
+    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    DpJob j;
+    j.aOffset = toc[o0]; j.nx = uint32_t(toc[o0 + 1] - toc[o0]);
+    j.bOffset = toc[o1]; j.ny = uint32_t(toc[o1 + 1] - toc[o1]);
+    j.traceOffset = 0; j.outOffset = 0; j.pad = p;
+    const int32_t* b = bands + cellOffsets[p];
+    const uint32_t first = jobOffsets[p];
+    for(uint32_t c = 0; c < componentCount[p]; c++) {
+        const int32_t bandMin = b[2 * c], bandMax = b[2 * c + 1];
+        // SeqAn returns MinValue when the band misses the matrix: "SeqAn banded alignment computation failed."
+        // and the component yields an empty alignment (src/Align4.cpp:1034-1036).
+        const bool misses = bandMin > bandMax || bandMax < -int32_t(j.ny) || bandMin > int32_t(j.nx);
+        j.lo = max(bandMin, -int32_t(j.ny));
+        j.hi = min(bandMax, int32_t(j.nx));
+        j.state = misses ? kStateEmpty : kStateRun;
+        jobs[first + c] = j;
+        traceWords[first + c] = misses ? 0ull : dpTraceWords(j.nx, j.lo, j.hi);
+        outCount[first + c] = min(j.nx, j.ny);
+    }
+}
+
+// Per candidate: among its jobs kept by the Align4-internal filters, the one with the most aligned markers
+// (first wins ties, src/Align4.cpp:128-147); then the driver's own filter chain, which only adds the
+// containment test (src/AssemblerAlign.cpp:438-473). selected[p] = job index or 0xffffffff.
+static __global__ void align4SelectKernel(uint32_t n, const uint32_t* __restrict__ jobOffsets, const uint32_t* __restrict__ componentCount,
+                                          const uint32_t* __restrict__ jobKeep, const uint32_t* __restrict__ jobInfoWords,
+                                          const uint32_t* __restrict__ jobBytes, uint32_t suppressContainments, uint32_t maxTrim,
+                                          uint32_t* __restrict__ selected, uint32_t* __restrict__ keep, uint32_t* __restrict__ bytes)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    uint32_t best = 0xffffffffu, bestCount = 0;
+    const uint32_t first = jobOffsets[p];
+    for(uint32_t c = 0; c < componentCount[p]; c++) {
+        const uint32_t j = first + c;
+        if(!jobKeep[j]) continue;
+        const uint32_t markerCount = jobInfoWords[13ull * j + 6];
+        if(best == 0xffffffffu || markerCount > bestCount) { best = j; bestCount = markerCount; }
+    }
+    uint32_t k = best != 0xffffffffu;
+    if(k && suppressContainments) {
+        const uint32_t* w = jobInfoWords + 13ull * best;
+        const bool c0 = w[1] <= maxTrim && w[0] - 1 - w[2] <= maxTrim;
+        const bool c1 = w[4] <= maxTrim && w[3] - 1 - w[5] <= maxTrim;
+        if(c0 || c1) k = 0;
+    }
+    selected[p] = k ? best : 0xffffffffu;
+    keep[p] = k;
+    bytes[p] = k ? jobBytes[best] : 0u;
+}
+
+// (rowIndex<<32 | kmerId, ordinal) keys for the per-read sort of computeSortedMarkers (src/AssemblerAlign4.cpp:190-261).
+static __global__ void sortedMarkerKeysKernel(const uint32_t* __restrict__ kmerIds, const uint64_t* __restrict__ toc,
+                                              uint32_t rowBegin, uint32_t rowEnd, uint64_t markerBegin, uint32_t n,
+                                              uint64_t* __restrict__ keys, uint32_t* __restrict__ ordinals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const uint64_t p = markerBegin + i;
+    uint32_t lo = rowBegin, hi = rowEnd;            // largest row with toc[row] <= p
+    while(hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if(toc[mid] <= p) lo = mid; else hi = mid; }
+    keys[i] = (uint64_t(lo - rowBegin) << 32) | kmerIds[p];
+    ordinals[i] = uint32_t(p - toc[lo]);
+}
+
+static __global__ void sortedMarkerUnpackKernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ sortedKmer)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) sortedKmer[i] = uint32_t(keys[i]);
 }
 
 } // namespace shb

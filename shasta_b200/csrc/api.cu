@@ -42,6 +42,7 @@ static void setCommonMarkerState(shb_context* c, uint64_t readCountTotal, uint64
     for(uint64_t i = 0; i < rows; i++) {
         SHB_REQUIRE(toc[i] <= toc[i+1], SHB_ERR_INVALID, "The marker toc is not monotonic.");
     }
+    c->markerGeneration++;
     c->readCountTotal = readCountTotal;
     c->readBegin = readBegin;
     c->readEnd = readEnd;

@@ -13,6 +13,7 @@ struct shb_context {
 
     // ---- markers (a1, a4) -------------------------------------------------------------------
     bool haveMarkers = false;
+    uint64_t markerGeneration = 0;      // bumped by every shb_set_markers*: invalidates derived caches
     uint64_t readCountTotal = 0;        // R of the whole assembly
     uint64_t readBegin = 0, readEnd = 0; // reads whose rows live on this GPU
     uint64_t totalMarkerCount = 0;      // over all reads (bucket-count rule)

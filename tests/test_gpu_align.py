@@ -94,3 +94,34 @@ def test_alignment_properties(ctx):
         assert ords[0, 0] == rec[i, 4] and ords[-1, 0] == rec[i, 5] and ords[0, 1] == rec[i, 7] and ords[-1, 1] == rec[i, 8]
         off = ords[:, 0].astype(np.int64) - ords[:, 1].astype(np.int64)
         assert off.min() == np.int32(rec[i, 10]) and off.max() == np.int32(rec[i, 11])
+
+
+def test_method4_default_cells(ctx):
+    # Align4 (north_star's method): deltaX 200, deltaY 10, minEntryCountPerCell 10, maxDistanceFromBoundary 100
+    # (src/AssemblerOptions.cpp:471-489); May2022-style filter values.
+    d, cand = _dataset(300, 10, 5)
+    rec, res = _compare(ctx, d, cand[:1200], alignMethod=4, k=10, maxSkip=100, maxDrift=100, maxTrim=100,
+                        minAlignedMarkerCount=10, minAlignedFraction=0.1, maxBand=1000)
+    assert len(rec) > 100 and res.dpCells > 0
+
+
+def test_method4_small_cells_strict_and_containments(ctx):
+    d, cand = _dataset(250, 14, 9)
+    _compare(ctx, d, cand[:800], alignMethod=4, k=14, maxSkip=30, maxDrift=30, maxTrim=30, minAlignedMarkerCount=60,
+             minAlignedFraction=0.4, align4DeltaX=100, align4DeltaY=5, align4MinEntryCountPerCell=4,
+             align4MaxDistanceFromBoundary=50, maxBand=300)
+    _compare(ctx, d, cand[:800], alignMethod=4, k=14, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
+             minAlignedFraction=0.1, align4DeltaX=50, align4DeltaY=20, align4MinEntryCountPerCell=1,
+             align4MaxDistanceFromBoundary=1000, maxBand=100, suppressContainments=1)
+
+
+def test_method4_random_pairs(ctx):
+    d, _ = _dataset(120, 10, 21)
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 119, 500)
+    b = rng.integers(0, 119, 500)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    ok = lo < hi
+    cand = np.stack([lo[ok], hi[ok], rng.integers(0, 2, ok.sum())], 1).astype(np.uint32)
+    _compare(ctx, d, cand, alignMethod=4, k=10, maxSkip=100, maxDrift=100, maxTrim=1000, minAlignedMarkerCount=5,
+             minAlignedFraction=0.05, align4MinEntryCountPerCell=2, maxBand=2000)
