@@ -123,6 +123,38 @@ shb_status shb_find_alignment_candidates_lowhash0(
     void** candidates, uint64_t* candidateCount, uint64_t* stats, shb_lowhash_result* result);
 
 /* ------------------------------------------------------------------------------------------
+ * Staged LowHash0 for read-sharded multi-GPU runs. Each rank holds the marker rows of
+ * a contiguous read range (shb_set_markers with readBegin/readEnd); buckets are owned by ranks; between the
+ * sweep and the bucket inspection the low-hash entries are exchanged (all-to-all over NCCL, done by the host:
+ * shasta_b200/distributed.py), and once at the end the per-owner pair counts are exchanged by readId0 range.
+ * The single-GPU shb_lowhash0 is exactly  begin; { sweep; process_entries per slab }; emit.
+ * All device pointers returned here are context scratch, valid until the next LowHash call on the context.
+ */
+shb_status shb_lowhash_begin(shb_context* ctx, const shb_lowhash_params* params, uint64_t* log2BucketCount);
+/* pass 1 (src/LowHash0.cpp:314-360) for iterationCount (<= 16) consecutive iterations over the local reads.
+ * lowHashCounts[s] receives the number of entries of slab s. */
+shb_status shb_lowhash_sweep(shb_context* ctx, uint64_t iterationBegin, uint32_t iterationCount, uint64_t* lowHashCounts);
+/* Slab s of the last sweep: keys uint64 (bucketId<<32 | hashHighBits), vals uint32 (orientedReadId). */
+shb_status shb_lowhash_slab(shb_context* ctx, uint32_t slab, void** keysDevice, void** valsDevice);
+/* Stable grouping of n (uint64 key, uint32 value) items by the `bits` (<= 8) key bits starting at `shift`;
+ * counts[1<<bits] receives the group sizes; the grouped arrays are returned as device pointers. */
+shb_status shb_device_partition(shb_context* ctx, void* keysDevice, void* valsDevice, uint64_t n, uint32_t shift,
+                                uint32_t bits, uint64_t* counts, void** keysOutDevice, void** valsOutDevice);
+/* passes 2+3 (src/LowHash0.cpp:365-484) on the entries of ONE iteration whose buckets this rank owns
+ * (device arrays, clobbered): statistics, pair hits, accumulation. */
+shb_status shb_lowhash_process_entries(shb_context* ctx, void* keysDevice, void* valsDevice, uint64_t n);
+/* Merged local accumulator: uint64 pair keys (readId0<<32 | readId1<<1 | strand), uint32 counts. */
+shb_status shb_lowhash_local_pairs(shb_context* ctx, void** pairKeysDevice, void** pairCountsDevice, uint64_t* n);
+/* Replace the accumulator by the (pairKey,count) items received from all ranks for this rank's readId0 range. */
+shb_status shb_lowhash_set_pairs(shb_context* ctx, const void* pairKeysDevice, const void* pairCountsDevice, uint64_t n);
+/* Final merge and emission (src/LowHash0.cpp:204-214) of the accumulator: host buffer of 12-byte records. */
+shb_status shb_lowhash_emit(shb_context* ctx, void** candidates, uint64_t* candidateCount);
+/* Device pointer of the (partial) ReadLowHashStatistics, uint64[readCountTotal*3], for the final all-reduce. */
+shb_status shb_lowhash_stats_device(shb_context* ctx, void** statsDevice);
+/* Counters of the staged run so far (iterations is not tracked by the staged calls and is returned as 0). */
+shb_status shb_lowhash_counters(shb_context* ctx, shb_lowhash_result* result);
+
+/* ------------------------------------------------------------------------------------------
  * Alignments.  Replaces Assembler::computeAlignments (src/AssemblerAlign.cpp:208-304, declaration
  * src/Assembler.hpp:264-270; Python binding src/PythonModule.cpp:344-345).
  * shb_align_options mirrors AlignOptions field for field (src/AssemblerOptions.hpp:177-199); k is the
@@ -179,16 +211,30 @@ shb_status shb_compute_alignments(shb_context* ctx, const void* candidates, uint
                                   uint64_t** compressedToc, uint8_t** compressedData,
                                   shb_align_result* result);
 
+/* Replaces Assembler::computeAlignmentTable (src/AssemblerAlign.cpp:509-571): for every oriented read the
+ * indices of the alignments it is involved in (4 entries per alignment: both reads x both strands), each row
+ * sorted by the other OrientedReadId (OrientedReadPair::getOther, src/OrientedReadPair.hpp:63-85).
+ *   alignmentData : n 64-byte AlignmentData records (host); only readIds/isSameStrand are read.
+ *   tableToc      : receives uint32[2*readCount+1]; tableData: uint32[4n]  (= Data/AlignmentTable.toc/.data
+ *                   payload, VectorOfVectors<uint32_t,uint32_t>). Free both with shb_free.
+ */
+shb_status shb_compute_alignment_table(shb_context* ctx, const void* alignmentData, uint64_t alignmentCount,
+                                       uint64_t readCount, uint32_t** tableToc, uint32_t** tableData);
+
 /* ------------------------------------------------------------------------------------------
  * Bench / test utilities (not part of the reference's interface): the marker-space synthetic read
  * generator of shasta_b200/synth.py on the device, and helpers for the device buffers it returns.
  */
 shb_status shb_synth_generate(shb_context* ctx, uint64_t seed, uint32_t k, double drop, double ins,
                               uint64_t genomeMarkers, const uint32_t* genomeKmerHost, const uint64_t* genomePosHost,
-                              uint64_t readCount, const int64_t* startHost, const int64_t* spanHost,
-                              const uint8_t* revHost, uint64_t* tocOut /* 2*readCount+1 */,
+                              uint64_t readOffset /* global id of the first read generated here */, uint64_t readCount,
+                              const int64_t* startHost, const int64_t* spanHost,
+                              const uint8_t* revHost, uint64_t* tocOut /* 2*readCount+1, relative */,
                               uint32_t** kmerIdsDevice, uint8_t** data7Device /* may be NULL */);
 shb_status shb_device_free(void* devicePtr);
+/* Device pointer and length of the uint32 k-mer id SoA held by ctx (for the all-gather that replicates the
+ * markers on every GPU before the alignment step). */
+shb_status shb_markers_device(shb_context* ctx, void** kmerIdsDevice, uint64_t* localMarkerCount);
 shb_status shb_copy_device_to_host(void* dstHost, const void* srcDevice, uint64_t bytes);
 
 #ifdef __cplusplus

@@ -620,3 +620,43 @@ int orc_compute_alignments(const uint64_t* toc, const uint32_t* kmerIds, const u
     free(keep); free(rec); free(comp); free(compBytes); free(th); free(w);
     return 0;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * computeAlignmentTable — src/AssemblerAlign.cpp:509-571 with OrientedReadPair::getOther
+ * (src/OrientedReadPair.hpp:63-85). records: uint32[n][16] AlignmentData records.
+ * Outputs (caller allocated): toc uint32[2R+1], table uint32[4n]: for each oriented read the indices of
+ * the alignments it is involved in, sorted by (other OrientedReadId, alignment index).
+ */
+typedef struct { uint32_t other, index; } orc_te;
+static int cmp_te(const void* a, const void* b)
+{
+    const orc_te* x = (const orc_te*)a; const orc_te* y = (const orc_te*)b;
+    if(x->other != y->other) return x->other < y->other ? -1 : 1;
+    return x->index < y->index ? -1 : (x->index > y->index ? 1 : 0);
+}
+void orc_compute_alignment_table(const uint32_t* records, uint64_t n, uint64_t R, uint32_t* toc, uint32_t* table)
+{
+    memset(toc, 0, sizeof(uint32_t) * (2 * R + 1));
+    for(uint64_t i = 0; i < n; i++) {
+        const uint32_t r0 = records[16*i], r1 = records[16*i+1], same = records[16*i+2] & 0xff;
+        const uint32_t o0 = 2 * r0, o1 = 2 * r1 + (same ? 0 : 1);
+        toc[o0 + 1]++; toc[o1 + 1]++; toc[(o0 ^ 1) + 1]++; toc[(o1 ^ 1) + 1]++;
+    }
+    for(uint64_t o = 0; o < 2 * R; o++) toc[o + 1] += toc[o];
+    uint32_t* fill = (uint32_t*)calloc(2 * R + 1, sizeof(uint32_t));
+    orc_te* e = (orc_te*)malloc(sizeof(orc_te) * (4 * n + 1));
+    for(uint64_t i = 0; i < n; i++) {
+        const uint32_t r0 = records[16*i], r1 = records[16*i+1], same = records[16*i+2] & 0xff;
+        const uint32_t o0 = 2 * r0, o1 = 2 * r1 + (same ? 0 : 1);
+        const uint32_t rows[4] = {o0, o1, o0 ^ 1, o1 ^ 1};
+        const uint32_t others[4] = {o1, o0, o1 ^ 1, o0 ^ 1};
+        for(int k = 0; k < 4; k++) {
+            orc_te* slot = &e[toc[rows[k]] + fill[rows[k]]++];
+            slot->other = others[k]; slot->index = (uint32_t)i;
+        }
+    }
+    for(uint64_t o = 0; o < 2 * R; o++) qsort(e + toc[o], toc[o+1] - toc[o], sizeof(orc_te), cmp_te);
+    for(uint64_t i = 0; i < 4 * n; i++) table[i] = e[i].index;
+    free(fill); free(e);
+}

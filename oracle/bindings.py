@@ -119,6 +119,8 @@ def oracle_lowhash0(toc, data, flags, p: LowHashParams, max_iters=4096):
                           p["minBucketSize"], p["maxBucketSize"], p["minFrequency"],
                           C.byref(cand), C.byref(n), stats.ctypes.data, summ.ctypes.data, max_iters,
                           C.byref(iters))
+    if rc == 2:
+        raise RuntimeError("alignmentCandidatesPerRead was not reached within max_iters iterations")
     if rc != 0:
         raise RuntimeError("log2MinHashBucketCount is unreasonably small.")
     out = np.ctypeslib.as_array(C.cast(cand, C.POINTER(C.c_uint32)), (n.value, 3)).copy() if n.value else np.zeros((0, 3), np.uint32)
@@ -375,3 +377,14 @@ def ref_compress(ordinals):
     buf = np.zeros(8 * len(o) + 16, np.uint8)
     n = lib.ref_compress_alignment(o.ctypes.data, len(o) // 2, buf.ctypes.data)
     return buf[:n].copy()
+
+
+def oracle_compute_alignment_table(records, read_count):
+    """Returns (toc uint32[2R+1], table uint32[4n]) — src/AssemblerAlign.cpp:509-571."""
+    lib = _olib()
+    rec = np.ascontiguousarray(records, np.uint32).reshape(-1, 16)
+    toc = np.zeros(2 * read_count + 1, np.uint32)
+    table = np.zeros(4 * len(rec) + 1, np.uint32)
+    lib.orc_compute_alignment_table.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.orc_compute_alignment_table(rec.ctypes.data, len(rec), read_count, toc.ctypes.data, table.ctypes.data)
+    return toc, table[:4 * len(rec)].copy()

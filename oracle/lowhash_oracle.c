@@ -171,6 +171,13 @@ int orc_lowhash0(
         if(minHashIterationCount == 0) {
             const double current = 2. * (double)highFrequency / (double)R;
             if(current >= alignmentCandidatesPerRead) break;
+            /* The reference spins forever when the target cannot be reached; the oracle gives up
+               (return code 2) once maxIters iterations have run. */
+            if(iteration >= maxIters) {
+                free(kmerIds); free(entries); free(newPairs); free(acc);
+                *candidatesOut = NULL; *candidateCountOut = 0;
+                return 2;
+            }
         } else if(iteration == minHashIterationCount) break;
 
         /* pass1, src/LowHash0.cpp:314-360: low hashes of every non-palindromic oriented read. */

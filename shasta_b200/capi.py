@@ -92,10 +92,23 @@ def lib():
         L.shb_compute_alignments.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(AlignOptions), C.POINTER(C.c_void_p),
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                              C.POINTER(AlignResult)]
+        L.shb_compute_alignment_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.shb_synth_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p,
-                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.shb_device_free.argtypes = [C.c_void_p]
+        L.shb_markers_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.shb_lowhash_begin.argtypes = [C.c_void_p, C.POINTER(LowHashParams), C.POINTER(C.c_uint64)]
+        L.shb_lowhash_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.shb_lowhash_slab.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_device_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_lowhash_process_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.shb_lowhash_local_pairs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.shb_lowhash_set_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.shb_lowhash_emit.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.shb_lowhash_stats_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.shb_lowhash_counters.argtypes = [C.c_void_p, C.POINTER(LowHashResult)]
         L.shb_copy_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
@@ -230,19 +243,24 @@ class DeviceMarkers:
                 setattr(self, name, None)
 
 
-def synth_generate_device(ctx: Context, p, want_data7=True) -> DeviceMarkers:
-    """shasta_b200.synth.generate(p) on the GPU: bit-identical markers, device resident."""
+def synth_generate_device(ctx: Context, p, want_data7=True, read_begin=0, read_end=None) -> DeviceMarkers:
+    """shasta_b200.synth.generate(p) on the GPU: bit-identical markers, device resident. With read_begin/read_end
+    only that read range is generated (toc relative to it; flags cover all reads)."""
     from . import synth
     gk, gpos = synth.genome(p)
     start, span, rev = synth.read_windows(p)
+    if read_end is None:
+        read_end = p.reads
+    n = read_end - read_begin
     gk = np.ascontiguousarray(gk, np.uint32)
     gpos = np.ascontiguousarray(gpos, np.uint64)
-    toc = np.zeros(2 * p.reads + 1, np.uint64)
+    toc = np.zeros(2 * n + 1, np.uint64)
     kptr = C.c_void_p()
     dptr = C.c_void_p()
-    _check(lib().shb_synth_generate(ctx._h, p.seed, p.k, p.drop, p.ins, len(gk), _ptr(gk), _ptr(gpos), p.reads,
-                                    _ptr(np.ascontiguousarray(start, np.int64)), _ptr(np.ascontiguousarray(span, np.int64)),
-                                    _ptr(np.ascontiguousarray(rev, np.uint8)), _ptr(toc), C.byref(kptr),
+    _check(lib().shb_synth_generate(ctx._h, p.seed, p.k, p.drop, p.ins, len(gk), _ptr(gk), _ptr(gpos), read_begin, n,
+                                    _ptr(np.ascontiguousarray(start[read_begin:read_end], np.int64)),
+                                    _ptr(np.ascontiguousarray(span[read_begin:read_end], np.int64)),
+                                    _ptr(np.ascontiguousarray(rev[read_begin:read_end], np.uint8)), _ptr(toc), C.byref(kptr),
                                     C.byref(dptr) if want_data7 else None))
     return DeviceMarkers(toc, synth.read_flags(p), kptr.value, dptr.value if want_data7 else None)
 
@@ -273,6 +291,19 @@ def compute_alignments(ctx: Context, candidates, options: AlignOptions):
     for p in (rec, toc, data):
         lib().shb_free(p)
     return records, tocn, datan, res
+
+
+def compute_alignment_table(ctx: Context, records, read_count):
+    """Assembler::computeAlignmentTable. Returns (toc uint32[2R+1], table uint32[4n])."""
+    rec = np.ascontiguousarray(records, np.uint32).reshape(-1, 16)
+    toc = C.c_void_p()
+    data = C.c_void_p()
+    _check(lib().shb_compute_alignment_table(ctx._h, _ptr(rec), len(rec), read_count, C.byref(toc), C.byref(data)))
+    tocn = np.ctypeslib.as_array(C.cast(toc, C.POINTER(C.c_uint32)), (2 * read_count + 1,)).copy()
+    datan = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint32)), (4 * len(rec),)).copy() if len(rec) else np.zeros(0, np.uint32)
+    lib().shb_free(toc)
+    lib().shb_free(data)
+    return tocn, datan
 
 
 def _records_to_array(ptr, n):

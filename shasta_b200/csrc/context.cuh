@@ -6,6 +6,23 @@
 
 #include <vector>
 
+namespace shb {
+struct LowHashAccumulator {
+    uint64_t count = 0;
+    bool inB = false;       // which of the acc ping-pong buffers holds the data
+};
+// State of a staged LowHash0 run (shb_lowhash_begin ... shb_lowhash_emit).
+struct LowHashState {
+    bool active = false;
+    shb_lowhash_params p{};
+    uint64_t log2BucketCount = 0, bucketMask = 0, hashThreshold = 0, capacity = 0;
+    uint32_t readBits = 1, slabGroup = 0;
+    LowHashAccumulator acc;
+    uint64_t lowHashCount = 0, pairCount = 0, sweepLaunches = 0;
+    double sweepMs = 0.;
+};
+}
+
 struct shb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -39,6 +56,9 @@ struct shb_context {
     shb::DeviceBuffer<uint32_t> accValsA, accValsB;
     shb::DeviceBuffer<unsigned long long> stats;
     shb::DeviceBuffer<uint32_t> candidatesDev;
+
+    shb::DeviceBuffer<uint64_t> partKeys; shb::DeviceBuffer<uint32_t> partVals;
+    void* lowhashState = nullptr;
 
     // ---- alignment cache (downsampled markers; see align.cu) ------------------------------------
     void* alignCache = nullptr;

@@ -70,10 +70,7 @@ uint32_t buildSegments(shb_context* c, const uint64_t* sortedKeys, uint32_t n, i
     return readScalar<uint32_t>(total, st);
 }
 
-struct Accumulator {
-    uint64_t count = 0;
-    bool inB = false;       // which of the acc ping-pong buffers holds the data
-};
+using Accumulator = LowHashAccumulator;
 
 uint64_t* accKeys(shb_context* c, const Accumulator& a) { return a.inB ? c->accKeysB.get() : c->accKeysA.get(); }
 uint32_t* accVals(shb_context* c, const Accumulator& a) { return a.inB ? c->accValsB.get() : c->accValsA.get(); }
@@ -137,6 +134,248 @@ uint64_t countHighFrequency(shb_context* c, const Accumulator& acc, uint64_t min
 } // namespace
 
 
+// ---------------------------------------------------------------------------------------------
+// Staged LowHash0. The single-GPU call is begin -> { sweep -> processEntries per slab } -> finish;
+// a multi-GPU run inserts the bucket exchange between sweep and processEntries and the pair exchange
+// before emit (shasta_b200/distributed.py).
+LowHashState& lowhashState(shb_context* c)
+{
+    if(!c->lowhashState) c->lowhashState = new LowHashState();
+    return *static_cast<LowHashState*>(c->lowhashState);
+}
+void destroyLowhashState(shb_context* c)
+{
+    if(c->lowhashState) { delete static_cast<LowHashState*>(c->lowhashState); c->lowhashState = nullptr; }
+}
+
+void lowhashBegin(shb_context* c, const shb_lowhash_params& p)
+{
+    SHB_REQUIRE(c->haveMarkers, SHB_ERR_STATE, "Markers are not accessible.");
+    SHB_REQUIRE(p.m >= 1 && p.m <= 32, SHB_ERR_INVALID, "MinHash.m must be between 1 and 32 in this implementation.");
+    SHB_REQUIRE(c->readCountTotal < (1ull << 31), SHB_ERR_INVALID, "Too many reads.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    LowHashState& S = lowhashState(c);
+    S = LowHashState();
+    S.p = p;
+    const uint64_t R = c->readCountTotal;
+
+    // Bucket-count rule, src/LowHash0.cpp:69-98.
+    const uint64_t totalLowHashCountEstimate = uint64_t(p.hashFraction * double(c->totalMarkerCount));
+    const uint32_t log2Estimate = totalLowHashCountEstimate ? uint32_t(64 - __builtin_clzll(totalLowHashCountEstimate)) : 0;
+    uint64_t log2BucketCount = p.log2MinHashBucketCount;
+    if(log2BucketCount == 0) log2BucketCount = 5 + log2Estimate;
+    else SHB_REQUIRE(log2BucketCount >= log2Estimate, SHB_ERR_INVALID, "log2MinHashBucketCount is unreasonably small.");
+    if(log2BucketCount > 31) log2BucketCount = 31;
+    S.log2BucketCount = log2BucketCount;
+    S.bucketMask = (1ull << log2BucketCount) - 1ull;
+    // src/LowHash0.cpp:109
+    S.hashThreshold = uint64_t(double(p.hashFraction) * double(std::numeric_limits<uint64_t>::max()));
+    S.readBits = bitsFor(R ? R - 1 : 0);
+    // Capacity of one iteration's low-hash slab.
+    const uint64_t M = c->localMarkerCount;
+    S.capacity = uint64_t(1.25 * p.hashFraction * double(M)) + 65536;
+    if(S.capacity > M + 1) S.capacity = M + 1;
+    c->stats.reserve(3 * R + 1);
+    SHB_CUDA(cudaMemsetAsync(c->stats.get(), 0, (3 * R + 1) * sizeof(unsigned long long), st));
+    c->scalars.reserve(64);
+    S.active = true;
+}
+
+// pass 1 for `group` consecutive iterations in one pass over the local k-mer ids. counts[s] = low hashes of
+// iteration iterationBegin+s; slab s = (sweepKeys + s*capacity, sweepVals + s*capacity).
+void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsigned long long* counts)
+{
+    LowHashState& S = lowhashState(c);
+    SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
+    SHB_REQUIRE(group >= 1 && group <= (uint32_t)kMaxFusedIterations, SHB_ERR_INVALID, "Invalid iteration group.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint64_t M = c->localMarkerCount;
+    EventTimer sweepTimer;
+    for(;;) {
+        c->sweepKeys.reserve(S.capacity * group);
+        c->sweepVals.reserve(S.capacity * group);
+        SHB_CUDA(cudaMemsetAsync(c->scalars.get(), 0, kMaxFusedIterations * sizeof(unsigned long long), st));
+        SweepArgs a;
+        a.kmerIds = c->kmerIds;
+        a.markerCount = M;
+        a.toc = c->toc.get();
+        a.orientedReadCount = uint32_t(2 * (c->readEnd - c->readBegin));
+        a.orientedReadBase = uint32_t(2 * c->readBegin);
+        a.readFlags = c->readFlags.get();
+        a.m = uint32_t(S.p.m);
+        a.hashThreshold = S.hashThreshold;
+        a.bucketMask = S.bucketMask;
+        a.iterationBegin = uint32_t(iterationBegin);
+        a.iterationCount = group;
+        a.keys = c->sweepKeys.get();
+        a.vals = c->sweepVals.get();
+        a.capacity = S.capacity;
+        a.counts = c->scalars.get();
+        const bool run = M >= S.p.m && M > 0;
+        if(run) {
+            SHB_CUDA(cudaEventRecord(sweepTimer.a, st));
+            launchSweep(a, ceilDiv(M, kSweepTile), st);
+            SHB_CUDA(cudaEventRecord(sweepTimer.b, st));
+            S.sweepLaunches++;
+        }
+        SHB_CUDA(cudaMemcpyAsync(counts, c->scalars.get(), group * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        SHB_CUDA(cudaStreamSynchronize(st));
+        if(run) {
+            float ms = 0.f;
+            SHB_CUDA(cudaEventElapsedTime(&ms, sweepTimer.a, sweepTimer.b));
+            S.sweepMs += ms;
+        }
+        const unsigned long long worst = *std::max_element(counts, counts + group);
+        if(worst <= S.capacity) break;
+        S.capacity = worst + worst / 8 + 1024;        // slab overflow: grow and redo this group
+    }
+    S.slabGroup = group;
+}
+
+// passes 2 and 3 on one iteration's entries (keys = bucketId<<32 | hashHigh, vals = orientedReadId), which must all
+// belong to buckets owned by this GPU: bucket sort, per-read statistics, pair hits, unique (pair,count) appended to the
+// local accumulator. keysA/valsA are clobbered.
+void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uint64_t n64)
+{
+    LowHashState& S = lowhashState(c);
+    SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
+    SHB_REQUIRE(n64 < (1ull << 32), SHB_ERR_INVALID, "LowHash0: more than 2^32-1 low hashes in one iteration.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const shb_lowhash_params& p = S.p;
+    const uint32_t n = uint32_t(n64);
+    S.lowHashCount += n;
+    if(n == 0) return;
+    c->entryKeysTmp.reserve(n);
+    c->entryValsTmp.reserve(n);
+    const int bucketRange[1][2] = {{32, 32 + int(S.log2BucketCount)}};
+    const bool inTmp = radixSort<true>(keysA, c->entryKeysTmp.get(), valsA, c->entryValsTmp.get(), n, bucketRange, 1, c->sortWs, st);
+    const uint64_t* keys = inTmp ? c->entryKeysTmp.get() : keysA;
+    const uint32_t* vals = inTmp ? c->entryValsTmp.get() : valsA;
+
+    buildSegments(c, keys, n, 32);
+
+    // Count pass (also per-read statistics), scan, emit pass.
+    c->countsBuf.reserve(n);
+    unsigned long long* pairTotal = c->scalars.get() + 40;
+    SHB_CUDA(cudaMemsetAsync(pairTotal, 0, sizeof(unsigned long long), st));
+    SHB_LAUNCH(bucketPairsKernel<false>, ceilDiv(n, 256), 256, 0, st, keys, vals, n,
+               (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(),
+               (const uint32_t*)c->segStartBuf.get(), p.minBucketSize, p.maxBucketSize,
+               c->stats.get(), pairTotal, c->countsBuf.get(), (uint64_t*)nullptr);
+    c->scanWs.reserve(scanWorkspaceElements(n));
+    exclusiveScan<uint32_t>(c->countsBuf.get(), c->countsBuf.get(), n, (uint32_t*)nullptr, c->scanWs.get(), st);
+    // The exact 64-bit total guards the 32-bit offsets.
+    const unsigned long long np64 = readScalar<unsigned long long>(pairTotal, st);
+    SHB_REQUIRE(np64 < (1ull << 32), SHB_ERR_INVALID,
+                "LowHash0: more than 2^32-1 candidate pair hits in one iteration (maxBucketSize too large).");
+    const uint32_t np = uint32_t(np64);
+    S.pairCount += np;
+    if(np == 0) return;
+    c->pairsA.reserve(np);
+    c->pairsB.reserve(np);
+    SHB_LAUNCH(bucketPairsKernel<true>, ceilDiv(n, 256), 256, 0, st, keys, vals, n,
+               (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(),
+               (const uint32_t*)c->segStartBuf.get(), p.minBucketSize, p.maxBucketSize,
+               (unsigned long long*)nullptr, (unsigned long long*)nullptr, c->countsBuf.get(), c->pairsA.get());
+    const int pairRanges[2][2] = {{0, int(S.readBits) + 1}, {32, 32 + int(S.readBits)}};
+    const bool inB = radixSort<false>(c->pairsA.get(), c->pairsB.get(), nullptr, nullptr, np, pairRanges, 2, c->sortWs, st);
+    const uint64_t* sortedPairs = inB ? c->pairsB.get() : c->pairsA.get();
+    const uint32_t numUnique = buildSegments(c, sortedPairs, np, 0);
+    accReserve(c, S.acc, S.acc.count + numUnique);
+    SHB_LAUNCH(uniqueCountsKernel, ceilDiv(numUnique, 256), 256, 0, st, sortedPairs,
+               (const uint32_t*)c->segStartBuf.get(), numUnique,
+               accKeys(c, S.acc) + S.acc.count, accVals(c, S.acc) + S.acc.count);
+    S.acc.count += numUnique;
+    if(S.acc.count > (1ull << 30)) mergeAccumulator(c, S.acc, S.readBits);     // keep the accumulator below 2^32 items
+}
+
+// Merge the local accumulator; returns its device arrays (valid until the next LowHash call on this context).
+void lowhashLocalPairs(shb_context* c, uint64_t** keys, uint32_t** counts, uint64_t* n)
+{
+    LowHashState& S = lowhashState(c);
+    SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    mergeAccumulator(c, S.acc, S.readBits);
+    *keys = accKeys(c, S.acc); *counts = accVals(c, S.acc); *n = S.acc.count;
+}
+
+// Replace the accumulator by externally supplied (pairKey,count) items (multi-GPU: what the other ranks sent).
+void lowhashSetPairs(shb_context* c, const uint64_t* keys, const uint32_t* counts, uint64_t n)
+{
+    LowHashState& S = lowhashState(c);
+    SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    S.acc = Accumulator();
+    accReserve(c, S.acc, n);
+    if(n) {
+        SHB_CUDA(cudaMemcpyAsync(accKeys(c, S.acc), keys, 8 * n, cudaMemcpyDeviceToDevice, st));
+        SHB_CUDA(cudaMemcpyAsync(accVals(c, S.acc), counts, 4 * n, cudaMemcpyDeviceToDevice, st));
+        SHB_CUDA(cudaStreamSynchronize(st));
+    }
+    S.acc.count = n;
+}
+
+// Final merge + emission, src/LowHash0.cpp:204-214. Returns a malloc'ed host buffer of 12-byte records.
+void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountOut)
+{
+    LowHashState& S = lowhashState(c);
+    SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    mergeAccumulator(c, S.acc, S.readBits);
+    const uint64_t nOut = countHighFrequency(c, S.acc, S.p.minFrequency, true);
+    void* host = malloc(nOut ? nOut * 12 : 1);
+    SHB_REQUIRE(host != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment candidates.");
+    if(nOut) {
+        c->candidatesDev.reserve(3 * nOut);
+        SHB_LAUNCH(emitCandidatesKernel, ceilDiv(S.acc.count, 256), 256, 0, st, (const uint64_t*)accKeys(c, S.acc),
+                   (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(), uint32_t(S.acc.count),
+                   c->candidatesDev.get());
+        SHB_CUDA(cudaMemcpyAsync(host, c->candidatesDev.get(), nOut * 12, cudaMemcpyDeviceToHost, st));
+    }
+    SHB_CUDA(cudaStreamSynchronize(st));
+    *candidatesOut = host;
+    *candidateCountOut = nOut;
+}
+
+// One stable radix pass on `bits` key bits starting at `shift` (bits <= 8): groups the items by destination.
+// counts[d] = items with digit d. Output pointers are context scratch, valid until the next call.
+void devicePartition(shb_context* c, uint64_t* keys, uint32_t* vals, uint64_t n, uint32_t shift, uint32_t bits,
+                     uint64_t* counts, uint64_t** keysOut, uint32_t** valsOut)
+{
+    SHB_REQUIRE(bits <= 8 && shift + bits <= 64, SHB_ERR_INVALID, "Invalid partition digit.");
+    SHB_REQUIRE(n < (1ull << 32), SHB_ERR_INVALID, "Too many items to partition.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint32_t buckets = 1u << bits;
+    for(uint32_t d = 0; d < buckets; d++) counts[d] = 0;
+    if(n == 0 || bits == 0) {
+        if(bits == 0) counts[0] = n;
+        *keysOut = keys; *valsOut = vals;
+        return;
+    }
+    c->partKeys.reserve(n);
+    c->partVals.reserve(n);
+    const int range[1][2] = {{int(shift), int(shift + bits)}};
+    const bool inB = radixSort<true>(keys, c->partKeys.get(), vals, c->partVals.get(), n, range, 1, c->sortWs, st);
+    uint64_t* sortedKeys = inB ? c->partKeys.get() : keys;
+    // Digit boundaries by binary search on the host-visible sorted keys would need a copy; count on the device instead.
+    c->scalars.reserve(64 + 256);
+    unsigned long long* dCounts = c->scalars.get() + 64;
+    SHB_CUDA(cudaMemsetAsync(dCounts, 0, buckets * sizeof(unsigned long long), st));
+    SHB_LAUNCH(digitCountKernel, ceilDiv(n, 256), 256, 0, st, (const uint64_t*)sortedKeys, uint32_t(n), int(shift), buckets - 1u, dCounts);
+    std::vector<unsigned long long> h(buckets);
+    SHB_CUDA(cudaMemcpyAsync(h.data(), dCounts, buckets * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SHB_CUDA(cudaStreamSynchronize(st));
+    for(uint32_t d = 0; d < buckets; d++) counts[d] = h[d];
+    *keysOut = sortedKeys;
+    *valsOut = inB ? c->partVals.get() : vals;
+}
+
 // The whole LowHash0 computation on the markers held by the context (single GPU).
 void lowhash0(shb_context* c, const shb_lowhash_params& p,
               void** candidatesOut, uint64_t* candidateCountOut,
@@ -146,184 +385,52 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
     SHB_REQUIRE(c->haveMarkers, SHB_ERR_STATE, "Markers are not accessible.");
     SHB_REQUIRE(c->readBegin == 0 && c->readEnd == c->readCountTotal, SHB_ERR_STATE,
                 "shb_lowhash0 needs all reads on this GPU (use the staged multi-GPU calls otherwise).");
-    SHB_REQUIRE(p.m >= 1 && p.m <= 32, SHB_ERR_INVALID, "MinHash.m must be between 1 and 32 in this implementation.");
-    SHB_REQUIRE(c->readCountTotal < (1ull << 31), SHB_ERR_INVALID, "Too many reads.");
-    SHB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
     g_launchCount = 0;
-
     const uint64_t R = c->readCountTotal;
-    const uint64_t M = c->localMarkerCount;
     if(R == 0) {        // the reference would spin forever on 0/0 in its iteration control; return nothing
         *candidatesOut = malloc(1);
         *candidateCountOut = 0;
         if(result) memset(result, 0, sizeof(*result));
         return;
     }
-
-    // Bucket-count rule, src/LowHash0.cpp:69-98.
-    const uint64_t totalLowHashCountEstimate = uint64_t(p.hashFraction * double(c->totalMarkerCount));
-    const uint32_t log2Estimate = totalLowHashCountEstimate ? uint32_t(64 - __builtin_clzll(totalLowHashCountEstimate)) : 0;
-    uint64_t log2BucketCount = p.log2MinHashBucketCount;
-    if(log2BucketCount == 0) log2BucketCount = 5 + log2Estimate;
-    else SHB_REQUIRE(log2BucketCount >= log2Estimate, SHB_ERR_INVALID, "log2MinHashBucketCount is unreasonably small.");
-    if(log2BucketCount > 31) log2BucketCount = 31;
-    const uint64_t bucketMask = (1ull << log2BucketCount) - 1ull;
-
-    // src/LowHash0.cpp:109
-    const uint64_t hashThreshold = uint64_t(double(p.hashFraction) * double(std::numeric_limits<uint64_t>::max()));
-
-    const bool perIteration = (p.perIterationMerge != 0) || (p.minHashIterationCount == 0);
-    const uint32_t readBits = bitsFor(R ? R - 1 : 0);
-
-    EventTimer totalTimer, sweepTimer;
+    lowhashBegin(c, p);
+    LowHashState& S = lowhashState(c);
+    cudaStream_t st = c->stream;
+    EventTimer totalTimer;
     SHB_CUDA(cudaEventRecord(totalTimer.a, st));
-    double sweepMs = 0.;
-    uint64_t sweepLaunches = 0, lowHashCount = 0, pairCount = 0;
+    const bool perIteration = (p.perIterationMerge != 0) || (p.minHashIterationCount == 0);
 
-    c->stats.reserve(3 * R + 1);
-    SHB_CUDA(cudaMemsetAsync(c->stats.get(), 0, (3 * R + 1) * sizeof(unsigned long long), st));
-    c->scalars.reserve(64);
-
-    // Capacity of one iteration's low-hash slab.
-    uint64_t capacity = uint64_t(1.25 * p.hashFraction * double(M)) + 65536;
-    if(capacity > M + 1) capacity = M + 1;
-
-    Accumulator acc;
     uint64_t highFrequency = 0;
     uint64_t iteration = 0;
-    bool done = false;
-
-    while(!done) {
+    for(;;) {
         // Iteration control, src/LowHash0.cpp:136-157.
         uint32_t group = 1;
         if(p.minHashIterationCount == 0) {
             const double current = 2. * double(highFrequency) / double(R);
             if(current >= p.alignmentCandidatesPerRead) break;
+            // The reference spins forever when the target cannot be reached (src/LowHash0.cpp:137-149); give up instead.
+            SHB_REQUIRE(iteration < 4096, SHB_ERR_INVALID,
+                        "MinHash.alignmentCandidatesPerRead was not reached after 4096 LowHash iterations.");
         } else {
             if(iteration == p.minHashIterationCount) break;
             if(!perIteration) group = uint32_t(std::min<uint64_t>(kMaxFusedIterations, p.minHashIterationCount - iteration));
         }
-
-        // ---- pass 1: hash sweep for `group` iterations in one pass over the k-mer ids -----------
-        std::vector<unsigned long long> counts(group, 0);
-        for(;;) {
-            c->sweepKeys.reserve(capacity * group);
-            c->sweepVals.reserve(capacity * group);
-            SHB_CUDA(cudaMemsetAsync(c->scalars.get(), 0, kMaxFusedIterations * sizeof(unsigned long long), st));
-            SweepArgs a;
-            a.kmerIds = c->kmerIds;
-            a.markerCount = M;
-            a.toc = c->toc.get();
-            a.orientedReadCount = uint32_t(2 * (c->readEnd - c->readBegin));
-            a.orientedReadBase = uint32_t(2 * c->readBegin);
-            a.readFlags = c->readFlags.get();
-            a.m = uint32_t(p.m);
-            a.hashThreshold = hashThreshold;
-            a.bucketMask = bucketMask;
-            a.iterationBegin = uint32_t(iteration);
-            a.iterationCount = group;
-            a.keys = c->sweepKeys.get();
-            a.vals = c->sweepVals.get();
-            a.capacity = capacity;
-            a.counts = c->scalars.get();
-            if(M >= p.m) {
-                SHB_CUDA(cudaEventRecord(sweepTimer.a, st));
-                launchSweep(a, ceilDiv(M, kSweepTile), st);
-                SHB_CUDA(cudaEventRecord(sweepTimer.b, st));
-                sweepLaunches++;
-            }
-            SHB_CUDA(cudaMemcpyAsync(counts.data(), c->scalars.get(), group * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            SHB_CUDA(cudaStreamSynchronize(st));
-            if(M >= p.m) {
-                float ms = 0.f;
-                SHB_CUDA(cudaEventElapsedTime(&ms, sweepTimer.a, sweepTimer.b));
-                sweepMs += ms;
-            }
-            const unsigned long long worst = *std::max_element(counts.begin(), counts.end());
-            if(worst <= capacity) break;
-            capacity = worst + worst / 8 + 1024;        // slab overflow: grow and redo this group
-        }
-
-        // ---- passes 2 and 3 for each iteration of the group ---------------------------------------
+        unsigned long long counts[kMaxFusedIterations];
+        lowhashSweep(c, iteration, group, counts);
         for(uint32_t s = 0; s < group; s++, iteration++) {
-            const uint64_t n64 = counts[s];
-            SHB_REQUIRE(n64 < (1ull << 32), SHB_ERR_INVALID, "LowHash0: more than 2^32-1 low hashes in one iteration.");
-            const uint32_t n = uint32_t(n64);
-            lowHashCount += n;
-            if(n) {
-                uint64_t* keysA = c->sweepKeys.get() + uint64_t(s) * capacity;
-                uint32_t* valsA = c->sweepVals.get() + uint64_t(s) * capacity;
-                c->entryKeysTmp.reserve(n);
-                c->entryValsTmp.reserve(n);
-                const int bucketRange[1][2] = {{32, 32 + int(log2BucketCount)}};
-                const bool inTmp = radixSort<true>(keysA, c->entryKeysTmp.get(), valsA, c->entryValsTmp.get(), n,
-                                                   bucketRange, 1, c->sortWs, st);
-                const uint64_t* keys = inTmp ? c->entryKeysTmp.get() : keysA;
-                const uint32_t* vals = inTmp ? c->entryValsTmp.get() : valsA;
-
-                buildSegments(c, keys, n, 32);
-
-                // Count pass (also per-read statistics), scan, emit pass.
-                c->countsBuf.reserve(n);
-                unsigned long long* pairTotal = c->scalars.get() + 40;
-                SHB_CUDA(cudaMemsetAsync(pairTotal, 0, sizeof(unsigned long long), st));
-                SHB_LAUNCH(bucketPairsKernel<false>, ceilDiv(n, 256), 256, 0, st, keys, vals, n,
-                           (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(),
-                           (const uint32_t*)c->segStartBuf.get(), p.minBucketSize, p.maxBucketSize,
-                           c->stats.get(), pairTotal, c->countsBuf.get(), (uint64_t*)nullptr);
-                c->scanWs.reserve(scanWorkspaceElements(n));
-                exclusiveScan<uint32_t>(c->countsBuf.get(), c->countsBuf.get(), n, (uint32_t*)nullptr, c->scanWs.get(), st);
-                // The exact 64-bit total guards the 32-bit offsets.
-                const unsigned long long np64 = readScalar<unsigned long long>(pairTotal, st);
-                SHB_REQUIRE(np64 < (1ull << 32), SHB_ERR_INVALID,
-                            "LowHash0: more than 2^32-1 candidate pair hits in one iteration (maxBucketSize too large).");
-                const uint32_t np = uint32_t(np64);
-                pairCount += np;
-                if(np) {
-                    c->pairsA.reserve(np);
-                    c->pairsB.reserve(np);
-                    SHB_LAUNCH(bucketPairsKernel<true>, ceilDiv(n, 256), 256, 0, st, keys, vals, n,
-                               (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(),
-                               (const uint32_t*)c->segStartBuf.get(), p.minBucketSize, p.maxBucketSize,
-                               (unsigned long long*)nullptr, (unsigned long long*)nullptr, c->countsBuf.get(), c->pairsA.get());
-                    const int pairRanges[2][2] = {{0, int(readBits) + 1}, {32, 32 + int(readBits)}};
-                    const bool inB = radixSort<false>(c->pairsA.get(), c->pairsB.get(), nullptr, nullptr, np,
-                                                      pairRanges, 2, c->sortWs, st);
-                    const uint64_t* sortedPairs = inB ? c->pairsB.get() : c->pairsA.get();
-                    const uint32_t numUnique = buildSegments(c, sortedPairs, np, 0);
-                    accReserve(c, acc, acc.count + numUnique);
-                    SHB_LAUNCH(uniqueCountsKernel, ceilDiv(numUnique, 256), 256, 0, st, sortedPairs,
-                               (const uint32_t*)c->segStartBuf.get(), numUnique,
-                               accKeys(c, acc) + acc.count, accVals(c, acc) + acc.count);
-                    acc.count += numUnique;
-                }
-            }
+            lowhashProcessEntries(c, c->sweepKeys.get() + uint64_t(s) * S.capacity, c->sweepVals.get() + uint64_t(s) * S.capacity, counts[s]);
             if(perIteration) {
-                mergeAccumulator(c, acc, readBits);
-                highFrequency = countHighFrequency(c, acc, p.minFrequency, false);
+                mergeAccumulator(c, S.acc, S.readBits);
+                highFrequency = countHighFrequency(c, S.acc, p.minFrequency, false);
                 if(iterSummary && iteration < maxIterSummary) {
                     iterSummary[2 * iteration] = highFrequency;
-                    iterSummary[2 * iteration + 1] = acc.count;
+                    iterSummary[2 * iteration + 1] = S.acc.count;
                 }
-            } else if(acc.count > (1ull << 30)) {
-                mergeAccumulator(c, acc, readBits);     // keep the deferred accumulator below 2^32 items
             }
         }
     }
 
-    // ---- final merge + emission, src/LowHash0.cpp:204-214 ----------------------------------------
-    if(!perIteration) mergeAccumulator(c, acc, readBits);
-    const uint64_t nOut = countHighFrequency(c, acc, p.minFrequency, true);
-    void* host = malloc(nOut ? nOut * 12 : 1);
-    SHB_REQUIRE(host != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment candidates.");
-    if(nOut) {
-        c->candidatesDev.reserve(3 * nOut);
-        SHB_LAUNCH(emitCandidatesKernel, ceilDiv(acc.count, 256), 256, 0, st, (const uint64_t*)accKeys(c, acc),
-                   (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(), uint32_t(acc.count),
-                   c->candidatesDev.get());
-        SHB_CUDA(cudaMemcpyAsync(host, c->candidatesDev.get(), nOut * 12, cudaMemcpyDeviceToHost, st));
-    }
+    lowhashEmit(c, candidatesOut, candidateCountOut);
     if(statsOut) {
         SHB_CUDA(cudaMemcpyAsync(statsOut, c->stats.get(), 3 * R * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     }
@@ -331,18 +438,15 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
     SHB_CUDA(cudaStreamSynchronize(st));
     float totalMs = 0.f;
     SHB_CUDA(cudaEventElapsedTime(&totalMs, totalTimer.a, totalTimer.b));
-
-    *candidatesOut = host;
-    *candidateCountOut = nOut;
     if(result) {
         result->iterations = iteration;
-        result->log2BucketCount = log2BucketCount;
-        result->lowHashCount = lowHashCount;
-        result->pairCount = pairCount;
-        result->candidateCount = nOut;
-        result->sweepMs = sweepMs;
+        result->log2BucketCount = S.log2BucketCount;
+        result->lowHashCount = S.lowHashCount;
+        result->pairCount = S.pairCount;
+        result->candidateCount = *candidateCountOut;
+        result->sweepMs = S.sweepMs;
         result->totalMs = totalMs;
-        result->sweepLaunches = sweepLaunches;
+        result->sweepLaunches = S.sweepLaunches;
         result->kernelLaunches = g_launchCount;
     }
 }

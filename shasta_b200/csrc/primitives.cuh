@@ -228,6 +228,17 @@ bool radixSort(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* vals
     return inB;
 }
 
+// counts[digit] += 1 for every key (warp-aggregated atomics; the input is sorted by digit so runs are long).
+static __global__ void digitCountKernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t digitMask,
+                                        unsigned long long* __restrict__ counts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    const uint32_t d = active ? (uint32_t(keys[i] >> shift) & digitMask) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if(active && (__ffs(peers) - 1) == int(threadIdx.x & 31u)) atomicAdd(&counts[d], (unsigned long long)__popc(peers));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Run detection on a sorted key array: flags[i] = 1 where (keys[i] >> shift) differs from its
 // predecessor (or i == 0).

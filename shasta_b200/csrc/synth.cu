@@ -29,14 +29,16 @@ struct SynthArgs {
     uint64_t seed; uint32_t k; double drop; double ins;
     const uint32_t* genomeKmer; const uint64_t* genomePos;
     uint64_t readCount; const int64_t* start; const int64_t* span; const uint8_t* rev;
+    uint64_t readOffset;            // global id of local read 0 (the RNG is keyed by the global read id)
 };
 
 // One block per read: number of markers of the read (kept genome markers + inserted markers).
 __global__ void __launch_bounds__(256) synthCountKernel(SynthArgs a, uint64_t* counts)
 {
     __shared__ uint32_t smem[8];
-    const uint64_t r = blockIdx.x;
-    const int64_t start = a.start[r], span = a.span[r];
+    const uint64_t local = blockIdx.x;
+    const uint64_t r = local + a.readOffset;
+    const int64_t start = a.start[local], span = a.span[local];
     uint32_t c = 0;
     for(int64_t j = threadIdx.x; j < span; j += 256) {
         const uint64_t g = uint64_t(start + j);
@@ -45,17 +47,18 @@ __global__ void __launch_bounds__(256) synthCountKernel(SynthArgs a, uint64_t* c
     }
     uint32_t total;
     blockExclusiveScan256<uint32_t>(c, total, smem);
-    if(threadIdx.x == 0) counts[r] = total;
+    if(threadIdx.x == 0) counts[local] = total;
 }
 
 // One block per read: fill both strand rows. toc is the final (2R+1) table.
 __global__ void __launch_bounds__(256) synthFillKernel(SynthArgs a, const uint64_t* toc, uint32_t* kmerOut, uint32_t* posOut)
 {
     __shared__ uint32_t smem[8];
-    const uint64_t r = blockIdx.x;
-    const int64_t start = a.start[r], span = a.span[r];
-    const bool rev = a.rev[r] != 0;
-    const uint64_t row0 = toc[2*r], row1 = toc[2*r+1];
+    const uint64_t local = blockIdx.x;
+    const uint64_t r = local + a.readOffset;
+    const int64_t start = a.start[local], span = a.span[local];
+    const bool rev = a.rev[local] != 0;
+    const uint64_t row0 = toc[2*local], row1 = toc[2*local+1];
     const uint64_t n = row1 - row0;
     const uint64_t base = a.genomePos[start];
     const uint64_t totalLen = (a.genomePos[start + span - 1] - base) + a.k + 2;
@@ -129,7 +132,8 @@ shb_status shb_copy_device_to_host(void* dstHost, const void* srcDevice, uint64_
 //   data7Device   : if not NULL receives a device allocation of the 7-byte records (7*M bytes).
 shb_status shb_synth_generate(shb_context* c, uint64_t seed, uint32_t k, double drop, double ins,
                               uint64_t genomeMarkers, const uint32_t* genomeKmerHost, const uint64_t* genomePosHost,
-                              uint64_t readCount, const int64_t* startHost, const int64_t* spanHost, const uint8_t* revHost,
+                              uint64_t readOffset, uint64_t readCount,
+                              const int64_t* startHost, const int64_t* spanHost, const uint8_t* revHost,
                               uint64_t* tocOut, uint32_t** kmerIdsDevice, uint8_t** data7Device)
 {
     try {
@@ -145,7 +149,7 @@ shb_status shb_synth_generate(shb_context* c, uint64_t seed, uint32_t k, double 
         SHB_CUDA(cudaMemcpyAsync(start.get(), startHost, readCount * 8, cudaMemcpyHostToDevice, st));
         SHB_CUDA(cudaMemcpyAsync(span.get(), spanHost, readCount * 8, cudaMemcpyHostToDevice, st));
         SHB_CUDA(cudaMemcpyAsync(rev.get(), revHost, readCount, cudaMemcpyHostToDevice, st));
-        SynthArgs a{seed, k, drop, ins, gk.get(), gp.get(), readCount, start.get(), span.get(), rev.get()};
+        SynthArgs a{seed, k, drop, ins, gk.get(), gp.get(), readCount, start.get(), span.get(), rev.get(), readOffset};
         std::vector<uint64_t> hostCounts(readCount);
         if(readCount) {
             SHB_LAUNCH(synthCountKernel, (unsigned)readCount, 256, 0, st, a, counts.get());

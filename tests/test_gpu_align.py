@@ -125,3 +125,18 @@ def test_method4_random_pairs(ctx):
     cand = np.stack([lo[ok], hi[ok], rng.integers(0, 2, ok.sum())], 1).astype(np.uint32)
     _compare(ctx, d, cand, alignMethod=4, k=10, maxSkip=100, maxDrift=100, maxTrim=1000, minAlignedMarkerCount=5,
              minAlignedFraction=0.05, align4MinEntryCountPerCell=2, maxBand=2000)
+
+
+def test_alignment_table(ctx):
+    from shasta_b200 import capi
+    d, cand = _dataset(200, 10, 33)
+    ctx.set_markers(d["toc"], d["data"], d["flags"])
+    rec, _, _, _ = capi.compute_alignments(ctx, cand[:900], capi.make_align_options(k=10, minAlignedMarkerCount=50))
+    toc, table = capi.compute_alignment_table(ctx, rec, 200)
+    otoc, otable = B.oracle_compute_alignment_table(rec, 200)
+    assert len(rec) > 50
+    assert np.array_equal(toc, otoc) and np.array_equal(table, otable)
+    # every alignment appears exactly 4 times
+    assert np.array_equal(np.bincount(table, minlength=len(rec)), np.full(len(rec), 4))
+    toc0, table0 = capi.compute_alignment_table(ctx, rec[:0], 200)
+    assert toc0.sum() == 0 and len(table0) == 0

@@ -105,7 +105,7 @@ def test_edge_cases_against_oracle(ctx):
     for kw in (dict(m=4, hashFraction=0.05, minHashIterationCount=3, minBucketSize=0, maxBucketSize=6, minFrequency=1),
                dict(m=4, hashFraction=0.9, minHashIterationCount=2, minBucketSize=3, maxBucketSize=50, minFrequency=2),
                dict(m=4, hashFraction=0.01, minHashIterationCount=17, minBucketSize=0, maxBucketSize=1000000, minFrequency=1),
-               dict(m=4, hashFraction=0.03, minHashIterationCount=0, alignmentCandidatesPerRead=3.0, minBucketSize=0, maxBucketSize=10, minFrequency=2)):
+               dict(m=4, hashFraction=0.03, minHashIterationCount=0, alignmentCandidatesPerRead=1.2, minBucketSize=0, maxBucketSize=10, minFrequency=2)):
         ctx.set_markers(newtoc, data, d["flags"])
         cand, stats, _, res = ctx.lowhash0(capi.make_lowhash_params(**kw))
         oc, os_, osum = B.oracle_lowhash0(newtoc, data, d["flags"], B.LowHashParams(**kw))
