@@ -2,13 +2,18 @@
 """bench.py — the hot path of BASELINE.json on synthetic Nanopore-shaped reads.
 
   python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU LowHash0 (oracle/_ref)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref + oracle port)
 
-A "step" is one pass of the hot path over one batch: Assembler::findAlignmentCandidatesLowHash0 on the
-whole read set (all MinHash iterations). `value` = candidate read pairs emitted per second with the
-marker k-mer ids already resident in HBM; `e2e` = the same through the reference-facing C-ABI call with
-HOST buffers (7-byte CompressedMarker records, pinned), host->device and device->host copies inside the
-timed region. One JSON line is printed by rank 0.
+A "step" is one pass of the hot path over one batch of reads:
+    Assembler::findAlignmentCandidatesLowHash0 (all MinHash iterations)  ->  Assembler::computeAlignments (method 3)
+on the BASELINE.json workload (configs[1]: 1 M synthetic Nanopore reads, N50 30 kb, ~30x, Nanopore-May2022.conf).
+`value` = candidate read pairs found AND aligned per second (candidates / (LowHash time + alignment time)) with the marker
+k-mer ids resident in HBM; the two halves are reported separately as lowhash_pairs_per_s and aligned_pairs_per_s.
+`e2e` = the same through the reference-facing C-ABI calls with HOST buffers (7-byte CompressedMarker records, pinned):
+host->device and device->host copies inside the timed region.
+N > 1 (torchrun): the SAME read set is sharded by read id across the ranks (strong scaling): bucket all-to-all over
+NCCL per LowHash iteration, all-gather of the k-mer ids, alignment of each rank's candidates.
+One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -23,18 +28,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# conf/Nanopore-May2022.conf [MinHash] (+ defaults of src/AssemblerOptions.cpp:327-378)
+# conf/Nanopore-May2022.conf (+ defaults of src/AssemblerOptions.cpp:327-489)
 MINHASH_MAY2022 = dict(m=4, hashFraction=0.01, minHashIterationCount=10, alignmentCandidatesPerRead=20.0,
                        log2MinHashBucketCount=0, minBucketSize=5, maxBucketSize=30, minFrequency=5)
+ALIGN_MAY2022 = dict(alignMethod=3, k=14, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
+                     minAlignedFraction=0.1, matchScore=6, mismatchScore=-1, gapScore=-1, downsamplingFactor=0.05,
+                     bandExtend=10, maxBand=1000, suppressContainments=0)
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: 1M synthetic Nanopore reads (N50 30 kb, ~30x), Nanopore-May2022.conf
-    "nanopore-may2022-1M": dict(reads=1_000_000, n50=30_000, coverage=30.0, minhash=MINHASH_MAY2022),
-    # Smaller variants for quick runs / N>1 development
-    "nanopore-may2022-100k": dict(reads=100_000, n50=30_000, coverage=30.0, minhash=MINHASH_MAY2022),
-    "nanopore-may2022-10k": dict(reads=10_000, n50=30_000, coverage=30.0, minhash=MINHASH_MAY2022),
+    # BASELINE.json configs[1]/[2]: 1M synthetic Nanopore reads (N50 30 kb, ~30x), Nanopore-May2022.conf
+    "nanopore-may2022-1M": dict(reads=1_000_000, n50=30_000, coverage=30.0),
+    # Smaller variants for quick runs
+    "nanopore-may2022-100k": dict(reads=100_000, n50=30_000, coverage=30.0),
+    "nanopore-may2022-10k": dict(reads=10_000, n50=30_000, coverage=30.0),
 }
-CPU_SAMPLE_READS = int(os.environ.get("SHB_CPU_SAMPLE_READS", "40000"))     # bounded sample of the same workload (same coverage, smaller genome)
+CPU_SAMPLE_READS = int(os.environ.get("SHB_CPU_SAMPLE_READS", "20000"))   # bounded sample: same coverage, smaller genome
 
 
 def synth_params(reads, n50, coverage, seed=1):
@@ -101,46 +109,53 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def run_reference(args, wl, rank, world):
-    """The reference's own CPU LowHash0 (oracle/_ref, unmodified TUs; the oracle port if _ref is absent)
-    on a bounded sample of the same workload, all host threads."""
+def cpu_reference_once(d, cores):
+    """The reference's CPU path on one read set: LowHash0 through the unmodified reference TUs (oracle/_ref) when they
+    are present (else the oracle port), then computeAlignments method 3 through the oracle port (reference control flow
+    restated + the SeqAn stand-in DP; 'not SeqAn'), one thread per core.
+    Returns (candidates, lowhash seconds, stored alignments, alignment seconds, kind)."""
+    from oracle import bindings as B
+    bp = B.LowHashParams(**MINHASH_MAY2022)
+    if B.have_ref():
+        c, _, _, sec_l = B.ref_lowhash0(d["toc"], d["data"], d["flags"], bp, threads=cores)
+        kind = "reference"
+    else:
+        t0 = time.perf_counter()
+        c, _, _ = B.oracle_lowhash0(d["toc"], d["data"], d["flags"], bp)
+        sec_l = time.perf_counter() - t0
+        kind = "port"
+    oo = B.make_align_options(**{k: v for k, v in ALIGN_MAY2022.items() if k in B.ALIGN_DEFAULTS})
+    t0 = time.perf_counter()
+    rec, _, _, _ = B.oracle_compute_alignments(d["toc"], d["kmer"], c, oo, threads=cores)
+    sec_a = time.perf_counter() - t0
+    return len(c), sec_l, len(rec), sec_a, kind
+
+
+def run_reference(args, wl, rank):
     if rank != 0:
         return
-    from oracle import bindings as B
     from shasta_b200 import synth
     p = synth_params(CPU_SAMPLE_READS, wl["n50"], wl["coverage"], seed=2)
     d = synth.generate(p)
     cores = os.cpu_count()
-    params = B.LowHashParams(**wl["minhash"])
-    kind = "reference" if B.have_ref() else "port"
-
-    def once():
-        t0 = time.perf_counter()
-        if kind == "reference":
-            c, _, _, sec = B.ref_lowhash0(d["toc"], d["data"], d["flags"], params, threads=cores)
-        else:
-            c, _, _ = B.oracle_lowhash0(d["toc"], d["data"], d["flags"], params)
-            sec = time.perf_counter() - t0
-        return len(c), sec
-
     for _ in range(args.warmup):
-        once()
-    total = 0.0
-    n = 0
+        cpu_reference_once(d, cores)
+    tl = ta = 0.0
     for _ in range(args.steps):
-        n, sec = once()
-        total += sec
-    value = n * args.steps / total
+        n, sec_l, nal, sec_a, kind = cpu_reference_once(d, cores)
+        tl += sec_l
+        ta += sec_a
+    value = n * args.steps / (tl + ta)
     M = int(d["toc"][-1])
+    sample = (f"{CPU_SAMPLE_READS} synthetic reads ({M} markers both strands, {wl['coverage']}x, same generator/config), "
+              f"{n} candidates, {nal} stored alignments; LowHash0 {tl / args.steps:.2f} s ({kind}), alignment {ta / args.steps:.2f} s (port)")
     line = {
-        "impl": "reference", "metric": "lowhash_candidate_read_pairs_per_s", "value": value, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": args.workload, "minhash": wl["minhash"], "sample": f"{CPU_SAMPLE_READS} reads, {M} markers, same coverage"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores if kind == "reference" else 1, "kind": kind,
-                         "sample": f"{CPU_SAMPLE_READS} synthetic reads ({M} markers both strands, {wl['coverage']}x), "
-                                   f"{wl['minhash']['minHashIterationCount']} LowHash iterations, {n} candidates",
-                         "marker_iterations_per_s": M * wl["minhash"]["minHashIterationCount"] * args.steps / total},
+        "impl": "reference", "metric": "candidate_pairs_found_and_aligned_per_s", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tl + ta) / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/i32", "data": "synthetic",
+        "config": {"workload": args.workload, "minhash": MINHASH_MAY2022, "align": ALIGN_MAY2022, "sample": sample},
+        "lowhash_pairs_per_s": n * args.steps / tl, "aligned_pairs_per_s": n * args.steps / ta,
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -155,6 +170,7 @@ def main():
     ap.add_argument("--workload", default="nanopore-may2022-1M", choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-align", action="store_true", help="LowHash0 only (profiling aid)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
 
@@ -163,12 +179,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, wl, rank, world)
+        run_reference(args, wl, rank)
         return
 
     import torch
     import torch.distributed as dist
     from shasta_b200 import capi, synth
+    from shasta_b200 import distributed as D
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -179,133 +196,196 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- synthetic input, generated on the device ------------------------------------------------------
-    # Weak scaling: every rank holds its own read set of the workload's size (independent shards).
-    p = synth_params(wl["reads"], wl["n50"], wl["coverage"], seed=1 + rank)
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- synthetic input, generated on the device; the same read set for every N (strong scaling) ----------------
+    p = synth_params(wl["reads"], wl["n50"], wl["coverage"], seed=1)
+    R = p.reads
     ctx = capi.Context(local_rank)
     t0 = time.perf_counter()
-    want_e2e = not args.no_e2e
-    dm = capi.synth_generate_device(ctx, p, want_data7=want_e2e)
-    M = dm.marker_count
+    want_e2e = (not args.no_e2e) and world == 1
+    if world == 1:
+        rb, re = 0, R
+    else:
+        _, span, _ = synth.read_windows(p)
+        bounds = D.balanced_read_ranges(span, world)
+        rb, re = bounds[rank], bounds[rank + 1]
+    dm = capi.synth_generate_device(ctx, p, want_data7=want_e2e, read_begin=rb, read_end=re)
+    M_local = dm.marker_count
+    M = int(allsum(M_local))
     gen_s = time.perf_counter() - t0
-    params = capi.make_lowhash_params(**wl["minhash"])
-    ctx.set_markers_device(dm.toc, dm.kmer_ptr, dm.flags, keepalive=dm)
+    lparams = capi.make_lowhash_params(**MINHASH_MAY2022)
+    aopts = capi.make_align_options(**ALIGN_MAY2022)
+    ctx.set_markers_device(dm.toc, dm.kmer_ptr, dm.flags, keepalive=dm, read_begin=rb, read_end=re,
+                           read_count_total=R, total_marker_count=M)
+    stages = D.CudaStages(ctx, local_rank) if world > 1 else None
+    actx = capi.Context(local_rank) if world > 1 else ctx       # alignment context (all rows resident)
 
-    # ---- kernel-resident timing: inputs already in HBM ---------------------------------------------------
+    stats_acc = {"sweep_ms": 0.0, "sweep_launches": 0, "launches": 0, "lowhash_s": 0.0, "align_s": 0.0, "gather_s": 0.0,
+                 "dp_ms": 0.0, "dp_cells": 0, "alignments": 0}
+
+    def step(record):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if world == 1:
+            cand, _, _, res = ctx.lowhash0(lparams, want_stats=True)
+            sweep_ms, sweep_launches, launches = res.sweepMs, res.sweepLaunches, res.kernelLaunches
+        else:
+            cand, _, _ = D.lowhash0_sharded(stages, MINHASH_MAY2022, R)
+            res = stages.counters()
+            sweep_ms, sweep_launches, launches = res.sweepMs, res.sweepLaunches, res.kernelLaunches
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        nal = 0
+        t2 = t1
+        if not args.no_align:
+            if world > 1:
+                toc, gathered = D.all_gather_markers(ctx, local_rank, dm.toc)
+                actx.set_markers_device(toc, gathered.data_ptr(), dm.flags, keepalive=gathered)
+                torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            rec, _, _, ares = capi.compute_alignments(actx, cand, aopts)
+            nal = len(rec)
+            launches += ares.kernelLaunches
+            if record:
+                stats_acc["dp_ms"] += ares.dpMs
+                stats_acc["dp_cells"] += ares.dpCells
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        if record:
+            stats_acc["sweep_ms"] += sweep_ms
+            stats_acc["sweep_launches"] += sweep_launches
+            stats_acc["launches"] += launches
+            stats_acc["lowhash_s"] += t1 - t0
+            stats_acc["gather_s"] += t2 - t1
+            stats_acc["align_s"] += t3 - t2
+            stats_acc["alignments"] = nal
+        return cand, nal
+
+    # ---- device-resident timing ----------------------------------------------------------------------------------
     for _ in range(args.warmup):
-        cand, _, _, res = ctx.lowhash0(params, want_stats=True)
+        cand, nal = step(False)
     barrier()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    sweep_ms = 0.0
-    sweep_launches = 0
-    launches = 0
-    device_ms = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        ev0.record()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cand, stats, _, res = ctx.lowhash0(params, want_stats=True)
-            sweep_ms += res.sweepMs
-            device_ms += res.totalMs
-            sweep_launches += res.sweepLaunches
-            launches += res.kernelLaunches
+            cand, nal = step(True)
+        ev1.record()
         barrier()
         wall = time.perf_counter() - t0
-    # Device timing: the library brackets every call with CUDA events on the stream it launches on
-    # (res.totalMs, includes the result copies); the wall clock around the K blocking calls is reported beside it.
-    wall_host = wall
-    wall = 1e-3 * device_ms
-    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    ncand = torch.tensor([float(len(cand))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ncand, op=dist.ReduceOp.SUM)
-    wall = float(t.item())
-    total_cand = float(ncand.item())
+    wall = allmax(wall)
+    total_cand = allsum(len(cand))
+    total_al = allsum(nal)
+    lowhash_s = allmax(stats_acc["lowhash_s"])
+    align_s = allmax(stats_acc["align_s"] + stats_acc["gather_s"])
     value = total_cand * args.steps / wall
 
-    # ---- end to end through the reference-facing call with host buffers -----------------------------------
+    # ---- end to end through the reference-facing calls with host buffers (single GPU) ------------------------------
     e2e = None
     if want_e2e:
         host = torch.empty(M * 7, dtype=torch.uint8, pin_memory=True)
         data7 = host.numpy()
         dm.data7_to_host(out=data7)
         e2e_steps = max(2, args.steps)
-        ctx.find_alignment_candidates_lowhash0(dm.toc, data7, dm.flags, params)      # warm-up
+
+        def e2e_step():
+            c2, s2, _ = ctx.find_alignment_candidates_lowhash0(dm.toc, data7, dm.flags, lparams)
+            n2 = 0
+            d2h = len(c2) * 12 + s2.nbytes
+            if not args.no_align:
+                rec, ctoc, cdata, _ = capi.compute_alignments(ctx, c2, aopts)     # candidates go host -> device again
+                n2 = len(rec)
+                d2h += rec.nbytes + ctoc.nbytes + cdata.nbytes
+            return c2, n2, d2h
+
+        e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            c2, s2, r2 = ctx.find_alignment_candidates_lowhash0(dm.toc, data7, dm.flags, params)
+            c2, n2, d2h = e2e_step()
         barrier()
         e2e_wall = time.perf_counter() - t0
-        assert np.array_equal(c2, cand), "host-buffer path and device-resident path disagree"
-        t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_wall = float(t.item())
+        assert np.array_equal(c2, cand) and n2 == nal, "host-buffer path and device-resident path disagree"
         e2e = {"value": total_cand * e2e_steps / e2e_wall, "unit": "pairs/s",
-               "h2d_bytes_per_step": int(M * 7 + dm.toc.nbytes + dm.flags.nbytes),
-               "d2h_bytes_per_step": int(len(c2) * 12 + s2.nbytes), "steps": e2e_steps,
-               "ms_per_step": 1e3 * e2e_wall / e2e_steps}
+               "h2d_bytes_per_step": int(M * 7 + dm.toc.nbytes + dm.flags.nbytes + (0 if args.no_align else len(c2) * 12)),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps}
+        # restore the device-resident markers for anything that follows
+        ctx.set_markers_device(dm.toc, dm.kmer_ptr, dm.flags, keepalive=dm, read_begin=rb, read_end=re,
+                               read_count_total=R, total_marker_count=M)
 
+    sweep_ms = allmax(stats_acc["sweep_ms"])
     if rank != 0:
         return
 
-    # ---- roofline of the dominant kernel (hash sweep) --------------------------------------------------
-    iters = wl["minhash"]["minHashIterationCount"]
-    frac_h = wl["minhash"]["hashFraction"]
+    # ---- roofline of the dominant LowHash kernel (hash sweep) -------------------------------------------------------
+    iters = MINHASH_MAY2022["minHashIterationCount"]
+    frac_h = MINHASH_MAY2022["hashFraction"]
     bytes_per_marker_iteration = 4.0 + 16.0 * frac_h
-    iters_per_launch = iters * args.steps / max(sweep_launches, 1)
-    alg_bytes_per_launch = M * bytes_per_marker_iteration * iters_per_launch
-    avg_launch_s = 1e-3 * sweep_ms / max(sweep_launches, 1)
+    launches = max(stats_acc["sweep_launches"], 1)
+    iters_per_launch = iters * args.steps / launches
+    alg_bytes_per_launch = M_local * bytes_per_marker_iteration * iters_per_launch
+    avg_launch_s = 1e-3 * stats_acc["sweep_ms"] / launches
     achieved = alg_bytes_per_launch / avg_launch_s / 1e9
     peak, peak_src = measured_hbm_peak()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # measured on the 100k-read workload: scale per marker to this launch
+            traffic = tj["dram_bytes_per_marker_per_launch"] * M_local
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "lowhashSweepKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "lowhashSweepKernel<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": 1e3 * avg_launch_s,
-                "iterations_fused_per_launch": iters_per_launch, "sweep_share_of_step": sweep_ms / (1e3 * wall)}
+                "iterations_fused_per_launch": iters_per_launch, "sweep_share_of_step": 1e-3 * sweep_ms / wall,
+                "alignment_gcups": (stats_acc["dp_cells"] / (1e-3 * stats_acc["dp_ms"]) / 1e9) if stats_acc["dp_ms"] else None}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        from oracle import bindings as B
         ps = synth_params(CPU_SAMPLE_READS, wl["n50"], wl["coverage"], seed=2)
         # Same generator as the numpy one (bit-identical), run on the device to save minutes of host time.
         dms = capi.synth_generate_device(ctx, ps, want_data7=True)
-        d = {"toc": dms.toc, "data": dms.data7_to_host(), "flags": dms.flags}
+        d = {"toc": dms.toc, "data": dms.data7_to_host(), "flags": dms.flags, "kmer": dms.kmer_ids_to_host()}
         dms.free()
         cores = os.cpu_count()
-        bp = B.LowHashParams(**wl["minhash"])
-        if B.have_ref():
-            c, _, _, sec = B.ref_lowhash0(d["toc"], d["data"], d["flags"], bp, threads=cores)
-            kind = "reference"
-        else:
-            t0 = time.perf_counter()
-            c, _, _ = B.oracle_lowhash0(d["toc"], d["data"], d["flags"], bp)
-            sec = time.perf_counter() - t0
-            kind, cores = "port", 1
+        n, sec_l, nalc, sec_a, kind = cpu_reference_once(d, cores)
         Ms = int(d["toc"][-1])
-        cpu_baseline = {"value": len(c) / sec, "unit": "pairs/s", "cores": cores, "kind": kind,
-                        "sample": f"{CPU_SAMPLE_READS} synthetic reads ({Ms} markers both strands, same coverage/config), "
-                                  f"{iters} iterations, {len(c)} candidates in {sec:.2f} s",
-                        "marker_iterations_per_s": Ms * iters / sec}
+        cpu_baseline = {"value": n / (sec_l + sec_a), "unit": "pairs/s", "cores": cores, "kind": kind,
+                        "sample": f"{CPU_SAMPLE_READS} synthetic reads ({Ms} markers both strands, same coverage/config), {n} candidates, "
+                                  f"{nalc} stored alignments; LowHash0 {sec_l:.2f} s ({kind}: unmodified reference TUs), "
+                                  f"alignment {sec_a:.2f} s (port: reference control flow + SeqAn stand-in DP)",
+                        "lowhash_pairs_per_s": n / sec_l, "aligned_pairs_per_s": n / sec_a}
 
     line = {
-        "metric": "lowhash_candidate_read_pairs_per_s", "value": value, "unit": "pairs/s",
+        "metric": "candidate_pairs_found_and_aligned_per_s", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-        "host_wall_ms_per_step": 1e3 * wall_host / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": args.workload, "reads_per_gpu": wl["reads"], "markers_per_gpu": M, "minhash": wl["minhash"],
-                   "parallelism": "independent read shards" if world > 1 else "single GPU",
-                   "l2": "inputs (k-mer ids %.1f GB) larger than L2" % (4e-9 * M), "generation_s": gen_s},
-        "candidates": total_cand, "marker_iterations_per_s": world * M * iters * args.steps / wall,
-        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/i32", "data": "synthetic",
+        "config": {"workload": args.workload, "reads": R, "markers": M, "minhash": MINHASH_MAY2022, "align": ALIGN_MAY2022,
+                   "parallelism": ("reads sharded by id over %d GPUs, bucket all-to-all per LowHash iteration, markers all-gathered for alignment" % world)
+                   if world > 1 else "single GPU",
+                   "l2": "inputs (k-mer ids %.1f GB) larger than L2" % (4e-9 * M_local), "generation_s": gen_s,
+                   "align_included": not args.no_align},
+        "candidates": total_cand, "alignments": total_al,
+        "lowhash_pairs_per_s": total_cand * args.steps / lowhash_s,
+        "aligned_pairs_per_s": (total_cand * args.steps / align_s) if align_s else None,
+        "lowhash_ms_per_step": 1e3 * lowhash_s / args.steps, "align_ms_per_step": 1e3 * align_s / args.steps,
+        "marker_iterations_per_s": M * iters * args.steps / lowhash_s,
+        "device_event_ms_per_step": ev0.elapsed_time(ev1) / args.steps,
+        "gpu_launches": int(stats_acc["launches"]), "clocks": clocks.summary(),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }
     print(json.dumps(line), flush=True)

@@ -158,6 +158,7 @@ void lowhashBegin(shb_context* c, const shb_lowhash_params& p)
     LowHashState& S = lowhashState(c);
     S = LowHashState();
     S.p = p;
+    g_launchCount = 0;
     const uint64_t R = c->readCountTotal;
 
     // Bucket-count rule, src/LowHash0.cpp:69-98.
@@ -385,7 +386,6 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
     SHB_REQUIRE(c->haveMarkers, SHB_ERR_STATE, "Markers are not accessible.");
     SHB_REQUIRE(c->readBegin == 0 && c->readEnd == c->readCountTotal, SHB_ERR_STATE,
                 "shb_lowhash0 needs all reads on this GPU (use the staged multi-GPU calls otherwise).");
-    g_launchCount = 0;
     const uint64_t R = c->readCountTotal;
     if(R == 0) {        // the reference would spin forever on 0/0 in its iteration control; return nothing
         *candidatesOut = malloc(1);
