@@ -29,17 +29,55 @@ struct Events {
     ~Events() { cudaEventDestroy(a); cudaEventDestroy(b); }
 };
 
-// Band-width classes: one launch per class so that shared memory is sized for the class.
-const uint32_t kClassLimits[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384};
-constexpr int kClassCount = 9;
+// Band-width classes, one launch per class. Up to 1024 offsets the register-resident wavefront kernel runs with
+// C = offsets/64 per sub-chunk (no shared memory); wider bands use the shared-memory scan kernel (C = 0).
+struct DpClass { uint32_t wMax; int c; };
+const DpClass kClasses[] = {{64, 1}, {128, 2}, {192, 3}, {256, 4}, {384, 6}, {512, 8}, {768, 12}, {1024, 16},
+                            {2048, 0}, {4096, 0}, {8192, 0}, {16384, 0}};
+constexpr int kClassCount = 12;
 constexpr uint32_t kMaxBandWidth = 16384;
 
-uint32_t warpsForClass(uint32_t wMax)
+uint32_t warpsForClass(const DpClass& k)
 {
-    // 3 * (wMax + 1) ints per warp; keep a block under ~200 KB of shared memory.
-    const uint64_t perWarp = 3ull * (wMax + 1) * 4;
+    if(k.c > 0) return kDpMaxWarpsPerBlock;
+    // scan kernel: 3 * (wMax + 1) ints per warp; keep a block under ~200 KB of shared memory.
+    const uint64_t perWarp = 3ull * (k.wMax + 1) * 4;
     const uint32_t w = uint32_t(std::min<uint64_t>(kDpMaxWarpsPerBlock, (200ull * 1024) / perWarp));
     return w ? w : 1;
+}
+size_t smemForClass(const DpClass& k, uint32_t warps) { return k.c > 0 ? 0 : size_t(warps) * 3 * (k.wMax + 1) * 4; }
+
+template<class... Args> void launchStage1(const DpClass& k, uint32_t blocks, uint32_t threads, size_t smem, cudaStream_t st, Args... args)
+{
+    switch(k.c) {
+    case 1: SHB_LAUNCH(method3Stage1Kernel<1>, blocks, threads, smem, st, args...); break;
+    case 2: SHB_LAUNCH(method3Stage1Kernel<2>, blocks, threads, smem, st, args...); break;
+    case 3: SHB_LAUNCH(method3Stage1Kernel<3>, blocks, threads, smem, st, args...); break;
+    case 4: SHB_LAUNCH(method3Stage1Kernel<4>, blocks, threads, smem, st, args...); break;
+    case 6: SHB_LAUNCH(method3Stage1Kernel<6>, blocks, threads, smem, st, args...); break;
+    case 8: SHB_LAUNCH(method3Stage1Kernel<8>, blocks, threads, smem, st, args...); break;
+    case 12: SHB_LAUNCH(method3Stage1Kernel<12>, blocks, threads, smem, st, args...); break;
+    case 16: SHB_LAUNCH(method3Stage1Kernel<16>, blocks, threads, smem, st, args...); break;
+    default:
+        SHB_CUDA(cudaFuncSetAttribute(method3Stage1Kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        SHB_LAUNCH(method3Stage1Kernel<0>, blocks, threads, smem, st, args...); break;
+    }
+}
+template<class... Args> void launchBanded(const DpClass& k, uint32_t blocks, uint32_t threads, size_t smem, cudaStream_t st, Args... args)
+{
+    switch(k.c) {
+    case 1: SHB_LAUNCH(bandedAlignKernel<1>, blocks, threads, smem, st, args...); break;
+    case 2: SHB_LAUNCH(bandedAlignKernel<2>, blocks, threads, smem, st, args...); break;
+    case 3: SHB_LAUNCH(bandedAlignKernel<3>, blocks, threads, smem, st, args...); break;
+    case 4: SHB_LAUNCH(bandedAlignKernel<4>, blocks, threads, smem, st, args...); break;
+    case 6: SHB_LAUNCH(bandedAlignKernel<6>, blocks, threads, smem, st, args...); break;
+    case 8: SHB_LAUNCH(bandedAlignKernel<8>, blocks, threads, smem, st, args...); break;
+    case 12: SHB_LAUNCH(bandedAlignKernel<12>, blocks, threads, smem, st, args...); break;
+    case 16: SHB_LAUNCH(bandedAlignKernel<16>, blocks, threads, smem, st, args...); break;
+    default:
+        SHB_CUDA(cudaFuncSetAttribute(bandedAlignKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        SHB_LAUNCH(bandedAlignKernel<0>, blocks, threads, smem, st, args...); break;
+    }
 }
 
 // Derived per-marker data cached in the context (per marker generation).
@@ -189,13 +227,12 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     SHB_CUDA(cudaEventRecord(ev.a, st));
     uint32_t wMin = 0;
     for(int k = 0; k < kClassCount; k++) {
-        const uint32_t wMax = kClassLimits[k];
-        const uint32_t warps = warpsForClass(wMax);
-        const size_t smem = size_t(warps) * 3 * (wMax + 1) * 4;
+        const uint32_t wMax = kClasses[k].wMax;
+        const uint32_t warps = warpsForClass(kClasses[k]);
+        const size_t smem = smemForClass(kClasses[k], warps);
         g.wMin = wMin; g.wMax = wMax;
-        SHB_CUDA(cudaFuncSetAttribute(bandedAlignKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        SHB_LAUNCH(bandedAlignKernel, ceilDiv(nJobs, warps), warps * 32, smem, st, g, (const DpJob*)b.jobs.get(), b.trace.get(),
-                   b.ordinals.get(), b.counts.get());
+        launchBanded(kClasses[k], ceilDiv(nJobs, warps), warps * 32, smem, st, g, (const DpJob*)b.jobs.get(), b.trace.get(),
+                     b.ordinals.get(), b.counts.get());
         wMin = wMax;
         if(wMax >= maxWidth) break;
     }
@@ -244,11 +281,11 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         buildSortedMarkers(c, o.k);
     } else {
         buildDownsampled(c, o.k, o.downsamplingFactor);
-        maxStage1Width = 2 * ac.dsMaxRow + 2;
+        maxStage1Width = 2 * ac.dsMaxRow + 2 + 64;
         SHB_REQUIRE(maxStage1Width <= kMaxBandWidth, SHB_ERR_INVALID,
                     "Downsampled reads are too long for the stage-1 kernel (limit 8191 downsampled markers).");
     }
-    const uint32_t maxStage2Width = uint32_t(std::max(0, o.maxBand)) + 2;
+    const uint32_t maxStage2Width = uint32_t(std::max(0, o.maxBand)) + 2 + 64;     // padded to a multiple of 64
     SHB_REQUIRE(maxStage2Width <= kMaxBandWidth, SHB_ERR_INVALID, "Align.maxBand too large for this implementation (limit 16382).");
 
     // Method 3 uses the configured scores; Align4 hard-codes 6/-1/-1 (src/Align4.hpp:159-161: never overwritten).
@@ -317,12 +354,11 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             SHB_CUDA(cudaEventRecord(dpEv1.a, st));
             uint32_t wMin = 0;
             for(int k = 0; k < kClassCount; k++) {
-                const uint32_t wMax = kClassLimits[k];
-                const uint32_t warps = warpsForClass(wMax);
-                const size_t smem = size_t(warps) * 3 * (wMax + 1) * 4;
+                const uint32_t wMax = kClasses[k].wMax;
+                const uint32_t warps = warpsForClass(kClasses[k]);
+                const size_t smem = smemForClass(kClasses[k], warps);
                 g1.wMin = wMin; g1.wMax = wMax;
-                SHB_CUDA(cudaFuncSetAttribute(method3Stage1Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                SHB_LAUNCH(method3Stage1Kernel, ceilDiv(nb, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get());
+                launchStage1(kClasses[k], ceilDiv(nb, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get());
                 wMin = wMax;
                 if(wMax >= maxStage1Width) break;
             }

@@ -94,7 +94,7 @@ struct DpScores { int32_t match, mismatch, gap; };
 constexpr int32_t kNegInf = -(1 << 29);
 constexpr int kDpMaxWarpsPerBlock = 4;
 
-__host__ __device__ inline uint32_t dpPaddedWidth(int32_t lo, int32_t hi) { return (uint32_t(hi - lo + 1) + 31u) & ~31u; }
+__host__ __device__ inline uint32_t dpPaddedWidth(int32_t lo, int32_t hi) { return (uint32_t(hi - lo + 1) + 63u) & ~63u; }
 __host__ __device__ inline uint64_t dpTraceWords(uint32_t nx, int32_t lo, int32_t hi)
 {
     return uint64_t(nx / 16 + 1) * dpPaddedWidth(lo, hi);
@@ -191,6 +191,101 @@ __device__ inline void bandedOverlapDp(const uint32_t* __restrict__ a, uint32_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident wavefront version of the same DP for bands of up to 64*C offsets (C <= 16).
+// The band offsets are cut into 64 sub-chunks of C consecutive offsets; lane l owns sub-chunks 2l ("A") and 2l+1
+// ("B"). Cell (i, e) depends on (i-1, e), (i-1, e+1) and (i, e-1), so sub-chunk s can process column i at step
+// T = 2i + s: on even steps every lane advances its A sub-chunk, on odd steps its B sub-chunk (no divergence, every
+// lane busy every step), and the only inter-lane traffic is one shuffle per step (the neighbouring sub-chunk's
+// boundary score). All scores of the previous column live in registers; no shared memory, no scan.
+// Same recurrence, tie-break and end-cell rules as bandedOverlapDp (bit-identical results, tested against the oracle);
+// the end cell is selected with the order-independent formulation "maximum score, then smallest i, then smallest j".
+template<int C> __device__ __forceinline__ void systolicSubChunk(
+    int32_t (&H)[C], uint32_t (&Tr)[C], int32_t e0, int32_t i, bool colValid, uint32_t ai,
+    int32_t below /* H(i, e0-1) */, int32_t top /* H(i-1, e0+C) */,
+    const uint32_t* __restrict__ b, int32_t nx, int32_t ny, int32_t W, int32_t hi, uint32_t WpadJob, DpScores sc,
+    uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
+{
+    const int32_t jBase = e0 + i - hi;
+    const bool storeNow = colValid && (((i & 15) == 15) || (i == nx));
+    const uint32_t storeShift = 2u * (15u - uint32_t(i & 15));
+    uint32_t* traceRow = trace + uint64_t(uint32_t(i) >> 4) * WpadJob;
+    int32_t vertIn = below;
+#pragma unroll
+    for(int c = 0; c < C; c++) {
+        const int32_t e = e0 + c;
+        const int32_t j = jBase + c;
+        const bool valid = colValid && (e < W) && (j >= 0) && (j <= ny);
+        const int32_t oldSame = H[c];                               // H(i-1, e)
+        const int32_t oldNext = (c + 1 < C) ? H[c + 1] : top;       // H(i-1, e+1)
+        int32_t h = kNegInf;
+        uint32_t code = 0;
+        if(valid) {
+            if(i == 0 || j == 0) h = 0;
+            else {
+                const int32_t diag = oldSame + ((ai == __ldg(b + (j - 1))) ? sc.match : sc.mismatch);
+                const int32_t vert = vertIn + sc.gap;
+                const int32_t horz = oldNext + sc.gap;
+                h = diag; code = 1u;
+                if(vert > h) { h = vert; code = 2u; }
+                if(horz > h) { h = horz; code = 3u; }
+            }
+            if(j == ny || i == nx) {
+                if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && j < bestJ)))) { bestScore = h; bestI = i; bestJ = j; }
+            }
+        }
+        H[c] = h;
+        vertIn = h;
+        if(colValid) {
+            const uint32_t acc = (Tr[c] >> 2) | (code << 30);
+            Tr[c] = acc;
+            if(storeNow) {
+                if(uint32_t(e) < WpadJob) traceRow[e] = acc >> storeShift;
+                Tr[c] = 0;
+            }
+        }
+    }
+}
+
+template<int C> __device__ inline void bandedOverlapDpSystolic(
+    const uint32_t* __restrict__ a, uint32_t nxU, const uint32_t* __restrict__ b, uint32_t nyU, int32_t lo, int32_t hi, DpScores sc,
+    uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
+{
+    const int32_t lane = int32_t(threadIdx.x & 31u);
+    const int32_t nx = int32_t(nxU), ny = int32_t(nyU);
+    const int32_t W = hi - lo + 1;
+    const uint32_t WpadJob = dpPaddedWidth(lo, hi);
+    int32_t HA[C], HB[C];
+    uint32_t TA[C], TB[C];
+#pragma unroll
+    for(int c = 0; c < C; c++) { HA[c] = kNegInf; HB[c] = kNegInf; TA[c] = 0; TB[c] = 0; }
+    bestScore = kNegInf * 2; bestI = 0x7fffffff; bestJ = 0x7fffffff;
+    const int32_t eA = (2 * lane) * C, eB = (2 * lane + 1) * C;
+    for(int32_t t2 = 0; t2 <= nx + 31; t2++) {
+        const int32_t i = t2 - lane;
+        const bool colValid = (i >= 0) && (i <= nx);
+        const uint32_t ai = (colValid && i > 0) ? __ldg(a + (i - 1)) : 0u;
+        // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
+        int32_t below = __shfl_up_sync(0xffffffffu, HB[C - 1], 1);
+        if(lane == 0) below = kNegInf;
+        systolicSubChunk<C>(HA, TA, eA, i, colValid, ai, below, HB[0], b, nx, ny, W, hi, WpadJob, sc, trace, bestScore, bestI, bestJ);
+        // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
+        int32_t top = __shfl_down_sync(0xffffffffu, HA[0], 1);
+        if(lane == 31) top = kNegInf;
+        systolicSubChunk<C>(HB, TB, eB, i, colValid, ai, HA[C - 1], top, b, nx, ny, W, hi, WpadJob, sc, trace, bestScore, bestI, bestJ);
+    }
+    // Warp reduction of the end cell: maximum score, then smallest i, then smallest j.
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1) {
+        const int32_t s2 = __shfl_xor_sync(0xffffffffu, bestScore, d);
+        const int32_t i2 = __shfl_xor_sync(0xffffffffu, bestI, d);
+        const int32_t j2 = __shfl_xor_sync(0xffffffffu, bestJ, d);
+        if(s2 > bestScore || (s2 == bestScore && (i2 < bestI || (i2 == bestI && j2 < bestJ)))) { bestScore = s2; bestI = i2; bestJ = j2; }
+    }
+    if(bestI == 0x7fffffff) { bestI = -1; bestJ = -1; }
+    __syncwarp();
+}
+
 // Traceback (executed redundantly by all lanes; loads are warp-uniform). F(x, y) is called for every
 // diagonal step, last step first.
 template<class F> __device__ inline void tracebackPath(const uint32_t* __restrict__ trace, int32_t lo, int32_t hi,
@@ -225,7 +320,7 @@ struct Method3Args {
     uint32_t wMin, wMax;            // only jobs with wMin < Wpad <= wMax are processed by this launch
 };
 
-static __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
+template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
 method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restrict__ trace, DpJob* __restrict__ jobs2)
 {
     extern __shared__ int32_t smem[];
@@ -236,16 +331,22 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
     if(job.state != kStateRun) return;
     const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
     if(Wpad <= g.wMin || Wpad > g.wMax) return;
-    const uint32_t stride = g.wMax + 1;
-    int32_t* hPrev = smem + warp * 3 * stride;
-    int32_t* hCur = hPrev + stride;
-    uint32_t* traceAcc = reinterpret_cast<uint32_t*>(hCur + stride);
     const uint32_t* a = g.dsKmer + job.aOffset;
     const uint32_t* b = g.dsKmer + job.bOffset;
     int32_t bestScore, bestI, bestJ;
-    bandedOverlapDp(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, hPrev, hCur, traceAcc, trace + job.traceOffset,
-                    bestScore, bestI, bestJ);
+    if constexpr(C > 0) {
+        bandedOverlapDpSystolic<C>(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, trace + job.traceOffset, bestScore, bestI, bestJ);
+        (void)warp;
+    } else {
+        const uint32_t stride = g.wMax + 1;
+        int32_t* hPrev = smem + warp * 3 * stride;
+        int32_t* hCur = hPrev + stride;
+        uint32_t* traceAcc = reinterpret_cast<uint32_t*>(hCur + stride);
+        bandedOverlapDp(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, hPrev, hCur, traceAcc, trace + job.traceOffset,
+                        bestScore, bestI, bestJ);
+    }
     __syncwarp();
+    __threadfence_block();
     const uint32_t* oa = g.dsOrdinal + job.aOffset;
     const uint32_t* ob = g.dsOrdinal + job.bOffset;
     int32_t offsetMin = INT32_MAX, offsetMax = INT32_MIN;
@@ -286,7 +387,7 @@ struct BandedArgs {
     uint32_t wMin, wMax;
 };
 
-static __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
+template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
 bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __restrict__ trace,
                   uint2* __restrict__ ordinals, uint32_t* __restrict__ counts)
 {
@@ -298,16 +399,22 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
     if(job.state != kStateRun) return;          // counts[] is zeroed by the host
     const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
     if(Wpad <= g.wMin || Wpad > g.wMax) return;
-    const uint32_t stride = g.wMax + 1;
-    int32_t* hPrev = smem + warp * 3 * stride;
-    int32_t* hCur = hPrev + stride;
-    uint32_t* traceAcc = reinterpret_cast<uint32_t*>(hCur + stride);
     const uint32_t* a = g.kmerIds + job.aOffset;
     const uint32_t* b = g.kmerIds + job.bOffset;
     int32_t bestScore, bestI, bestJ;
-    bandedOverlapDp(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, hPrev, hCur, traceAcc, trace + job.traceOffset,
-                    bestScore, bestI, bestJ);
+    if constexpr(C > 0) {
+        bandedOverlapDpSystolic<C>(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, trace + job.traceOffset, bestScore, bestI, bestJ);
+        (void)warp;
+    } else {
+        const uint32_t stride = g.wMax + 1;
+        int32_t* hPrev = smem + warp * 3 * stride;
+        int32_t* hCur = hPrev + stride;
+        uint32_t* traceAcc = reinterpret_cast<uint32_t*>(hCur + stride);
+        bandedOverlapDp(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, hPrev, hCur, traceAcc, trace + job.traceOffset,
+                        bestScore, bestI, bestJ);
+    }
     __syncwarp();
+    __threadfence_block();
     uint2* out = ordinals + job.outOffset;
     uint32_t count = 0;
     tracebackPath(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, [&](uint32_t x, uint32_t y) {
