@@ -296,7 +296,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     fo.minAlignedFraction = o.minAlignedFraction;
     fo.suppressContainments = (!method4 && o.suppressContainments) ? 1u : 0u;     // method 4 applies it after the selection
 
-    const uint32_t batchMax = 32768;
+    const uint32_t batchMax = method4 ? 32768 : 131072;
     const uint64_t cellBudget = 192ull << 20;      // method 4: cells of scratch per batch
     Batch b;
     c->scanWs.reserve(scanWorkspaceElements(4ull * batchMax * 64));
@@ -304,11 +304,14 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     unsigned long long* total64 = c->scalars.get() + 48;
     uint32_t* total32 = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
 
-    std::vector<uint32_t> hostRecords;
-    std::vector<uint64_t> hostToc;
-    std::vector<uint8_t> hostData;
-    hostToc.push_back(0);
-    uint64_t skipped = 0, dpCells = 0;
+    // Kept alignments accumulate on the device and are copied to the host once at the end.
+    DeviceBuffer<uint32_t> outRecords;
+    DeviceBuffer<unsigned long long> outToc;
+    DeviceBuffer<uint8_t> outData;
+    uint64_t outCount = 0, outBytes = 0;
+    unsigned long long* skippedDev = c->scalars.get() + 56;
+    SHB_CUDA(cudaMemsetAsync(skippedDev, 0, sizeof(unsigned long long), st));
+    uint64_t dpCells = 0;
     const std::vector<uint64_t>& toc = c->tocHost;
 
     for(uint64_t begin = 0; begin < n; ) {
@@ -334,6 +337,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         uint32_t nJobs = 0;
         const uint32_t* jobIndex = nullptr;
         DpTotals totals;
+        bool stage1Timed = false;
 
         if(!method4) {
             // ---- method 3 ---------------------------------------------------------------------------
@@ -347,6 +351,12 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             dpCells += 16ull * traceWords1;
             SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nb, 256), 256, 0, st, b.jobs1.get(), nb, (const unsigned long long*)b.twOff.get(),
                        (const unsigned long long*)nullptr);
+            // Ordinal slots (also the stage-1 path scratch): offsets must be in jobs[] before stage 1 runs.
+            b.outOff.reserve(nb);
+            exclusiveScan<unsigned long long>(b.outCnt.get(), b.outOff.get(), nb, total64, b.scanWs64.get(), st);
+            const unsigned long long slots1 = readBack<unsigned long long>(total64, st);
+            b.ordinals.reserve(slots1 + 1);
+            SHB_LAUNCH(setOutOffsetsKernel, ceilDiv(nb, 256), 256, 0, st, b.jobs.get(), nb, (const unsigned long long*)b.outOff.get());
             Method3Args g1;
             g1.candidates = b.cand.get(); g1.candidateBegin = begin; g1.n = nb;
             g1.toc = c->toc.get(); g1.dsToc = ac.dsToc.get(); g1.dsKmer = ac.dsKmer.get(); g1.dsOrdinal = ac.dsOrdinal.get();
@@ -358,7 +368,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 const uint32_t warps = warpsForClass(kClasses[k]);
                 const size_t smem = smemForClass(kClasses[k], warps);
                 g1.wMin = wMin; g1.wMax = wMax;
-                launchStage1(kClasses[k], ceilDiv(nb, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get());
+                launchStage1(kClasses[k], ceilDiv(nb, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
                 wMin = wMax;
                 if(wMax >= maxStage1Width) break;
             }
@@ -368,17 +378,8 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             // Epilogue per job == per candidate.
             b.infoWords.reserve(13ull * nJobs);
             SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 128), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
-                       (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.keep.get(), b.bytes32.get());
-            // Candidates the reference would skip with a logged exception.
-            {
-                std::vector<DpJob> hj(nb);
-                SHB_CUDA(cudaMemcpyAsync(hj.data(), b.jobs.get(), sizeof(DpJob) * nb, cudaMemcpyDeviceToHost, st));
-                SHB_CUDA(cudaStreamSynchronize(st));
-                for(const DpJob& j : hj) if(j.state == kStateSkipped) skipped++;
-                float ms = 0.f;
-                SHB_CUDA(cudaEventElapsedTime(&ms, dpEv1.a, dpEv1.b));
-                dpMs += ms;
-            }
+                       (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.keep.get(), b.bytes32.get(), skippedDev);
+            stage1Timed = true;
         } else {
             // ---- method 4 ---------------------------------------------------------------------------
             b.cellCnt.reserve(nb); b.cellOff.reserve(nb); b.componentCount.reserve(nb); b.jobOffsets.reserve(nb); b.selected.reserve(nb);
@@ -408,7 +409,8 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 b.infoWords.reserve(13ull * nJobs); b.jobKeep.reserve(nJobs); b.jobBytes.reserve(nJobs);
                 // Align4's own filters (src/Align4.cpp:944-985), identical thresholds, no containment test.
                 SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 128), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
-                           (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.jobKeep.get(), b.jobBytes.get());
+                           (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.jobKeep.get(), b.jobBytes.get(),
+                           (unsigned long long*)nullptr);
             } else {
                 b.infoWords.reserve(13); b.jobKeep.reserve(1); b.jobBytes.reserve(1); b.jobs.reserve(1); b.counts.reserve(1); b.ordinals.reserve(1);
             }
@@ -431,41 +433,42 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             SHB_CUDA(cudaEventElapsedTime(&ms, dpEv2.a, dpEv2.b));
             dpMs += ms;
         }
+        if(stage1Timed) {
+            float ms = 0.f;
+            SHB_CUDA(cudaEventElapsedTime(&ms, dpEv1.a, dpEv1.b));
+            dpMs += ms;
+        }
         if(kept) {
-            b.records.reserve(16ull * kept); b.ctoc.reserve(kept); b.cdata.reserve(bytes + 16);
+            outRecords.reserve(16ull * (outCount + kept), true, st);
+            outToc.reserve(outCount + kept + 1, true, st);
+            outData.reserve(outBytes + bytes + 16, true, st);
             SHB_LAUNCH(alignmentWriteKernel, ceilDiv(nb, 128), 128, 0, st, nb, (const uint32_t*)b.cand.get(), (const DpJob*)b.jobs.get(),
                        (const uint2*)b.ordinals.get(), (const uint32_t*)b.counts.get(), (const uint32_t*)b.infoWords.get(), jobIndex,
                        (const uint32_t*)b.keep.get(), (const uint32_t*)b.keepIndex.get(), (const unsigned long long*)b.bytesOff.get(),
-                       b.records.get(), b.ctoc.get(), b.cdata.get());
-            const size_t r0 = hostRecords.size(), b0 = hostData.size();
-            hostRecords.resize(r0 + 16ull * kept);
-            hostData.resize(b0 + bytes);
-            std::vector<unsigned long long> tocBatch(kept);
-            SHB_CUDA(cudaMemcpyAsync(hostRecords.data() + r0, b.records.get(), 64ull * kept, cudaMemcpyDeviceToHost, st));
-            SHB_CUDA(cudaMemcpyAsync(tocBatch.data(), b.ctoc.get(), 8ull * kept, cudaMemcpyDeviceToHost, st));
-            if(bytes) SHB_CUDA(cudaMemcpyAsync(hostData.data() + b0, b.cdata.get(), bytes, cudaMemcpyDeviceToHost, st));
-            SHB_CUDA(cudaStreamSynchronize(st));
-            for(uint32_t i = 0; i < kept; i++) {
-                const uint64_t end = (i + 1 < kept) ? tocBatch[i + 1] : bytes;
-                hostToc.push_back(b0 + end);
-            }
+                       outCount, outBytes, outRecords.get(), outToc.get(), outData.get());
+            outCount += kept;
+            outBytes += bytes;
         }
         begin += nb;
     }
 
+    const uint64_t count = outCount;
+    void* recOut = malloc(count ? 64 * count : 1);
+    uint64_t* tocOut = (uint64_t*)malloc(8 * (count + 1));
+    uint8_t* dataOut = (uint8_t*)malloc(outBytes ? outBytes : 1);
+    SHB_REQUIRE(recOut && tocOut && dataOut, SHB_ERR_OOM, "Out of host memory for the alignments.");
+    if(count) {
+        SHB_CUDA(cudaMemcpyAsync(recOut, outRecords.get(), 64 * count, cudaMemcpyDeviceToHost, st));
+        SHB_CUDA(cudaMemcpyAsync(tocOut, outToc.get(), 8 * count, cudaMemcpyDeviceToHost, st));
+        if(outBytes) SHB_CUDA(cudaMemcpyAsync(dataOut, outData.get(), outBytes, cudaMemcpyDeviceToHost, st));
+    }
+    const unsigned long long skipped = readBack<unsigned long long>(skippedDev, st);
+    tocOut[count] = outBytes;
+    if(count == 0) tocOut[0] = 0;
     SHB_CUDA(cudaEventRecord(totalEv.b, st));
     SHB_CUDA(cudaStreamSynchronize(st));
     float totalMs = 0.f;
     SHB_CUDA(cudaEventElapsedTime(&totalMs, totalEv.a, totalEv.b));
-
-    const uint64_t count = hostRecords.size() / 16;
-    void* recOut = malloc(count ? 64 * count : 1);
-    uint64_t* tocOut = (uint64_t*)malloc(8 * (count + 1));
-    uint8_t* dataOut = (uint8_t*)malloc(hostData.size() ? hostData.size() : 1);
-    SHB_REQUIRE(recOut && tocOut && dataOut, SHB_ERR_OOM, "Out of host memory for the alignments.");
-    if(count) memcpy(recOut, hostRecords.data(), 64 * count);
-    memcpy(tocOut, hostToc.data(), 8 * (count + 1));
-    if(!hostData.empty()) memcpy(dataOut, hostData.data(), hostData.size());
     *alignmentDataOut = recOut; *alignmentCountOut = count; *compressedTocOut = tocOut; *compressedDataOut = dataOut;
     if(result) {
         result->candidateCount = n; result->alignmentCount = count; result->skippedCount = skipped;

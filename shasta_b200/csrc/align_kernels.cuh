@@ -206,43 +206,38 @@ template<int C> __device__ __forceinline__ void systolicSubChunk(
     const uint32_t* __restrict__ b, int32_t nx, int32_t ny, int32_t W, int32_t hi, uint32_t WpadJob, DpScores sc,
     uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
 {
+    // Written for predication: the common case (interior cell) is straight-line code; boundary / out-of-matrix cells
+    // are fixed up with selects; only the rare end-cell bookkeeping and the 1-in-16 trace store branch.
     const int32_t jBase = e0 + i - hi;
     const bool storeNow = colValid && (((i & 15) == 15) || (i == nx));
     const uint32_t storeShift = 2u * (15u - uint32_t(i & 15));
-    uint32_t* traceRow = trace + uint64_t(uint32_t(i) >> 4) * WpadJob;
     int32_t vertIn = below;
 #pragma unroll
     for(int c = 0; c < C; c++) {
-        const int32_t e = e0 + c;
         const int32_t j = jBase + c;
-        const bool valid = colValid && (e < W) && (j >= 0) && (j <= ny);
-        const int32_t oldSame = H[c];                               // H(i-1, e)
-        const int32_t oldNext = (c + 1 < C) ? H[c + 1] : top;       // H(i-1, e+1)
-        int32_t h = kNegInf;
-        uint32_t code = 0;
-        if(valid) {
-            if(i == 0 || j == 0) h = 0;
-            else {
-                const int32_t diag = oldSame + ((ai == __ldg(b + (j - 1))) ? sc.match : sc.mismatch);
-                const int32_t vert = vertIn + sc.gap;
-                const int32_t horz = oldNext + sc.gap;
-                h = diag; code = 1u;
-                if(vert > h) { h = vert; code = 2u; }
-                if(horz > h) { h = horz; code = 3u; }
-            }
-            if(j == ny || i == nx) {
-                if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && j < bestJ)))) { bestScore = h; bestI = i; bestJ = j; }
-            }
-        }
+        const bool inMatrix = colValid && (e0 + c < W) && (j >= 0) && (j <= ny);
+        const bool interior = inMatrix && (i > 0) && (j > 0);
+        const uint32_t bv = interior ? __ldg(b + (j - 1)) : 0xffffffffu;
+        const int32_t diag = H[c] + ((ai == bv) ? sc.match : sc.mismatch);      // H(i-1, e)
+        const int32_t vert = vertIn + sc.gap;                                   // H(i, e-1)
+        const int32_t horz = ((c + 1 < C) ? H[c + 1] : top) + sc.gap;           // H(i-1, e+1)
+        const int32_t dv = max(diag, vert);
+        int32_t h = max(dv, horz);
+        uint32_t code = (horz > dv) ? 3u : ((vert > diag) ? 2u : 1u);
+        h = interior ? h : (inMatrix ? 0 : kNegInf);
+        code = interior ? code : 0u;
         H[c] = h;
         vertIn = h;
-        if(colValid) {
-            const uint32_t acc = (Tr[c] >> 2) | (code << 30);
-            Tr[c] = acc;
-            if(storeNow) {
-                if(uint32_t(e) < WpadJob) traceRow[e] = acc >> storeShift;
-                Tr[c] = 0;
-            }
+        Tr[c] = (Tr[c] >> 2) | (code << 30);        // always holds the codes of the last 16 columns
+        if(inMatrix && (j == ny || i == nx)) {
+            if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && j < bestJ)))) { bestScore = h; bestI = i; bestJ = j; }
+        }
+    }
+    if(storeNow) {
+        uint32_t* traceRow = trace + uint64_t(uint32_t(i) >> 4) * WpadJob;
+#pragma unroll
+        for(int c = 0; c < C; c++) {
+            if(uint32_t(e0 + c) < WpadJob) traceRow[e0 + c] = Tr[c] >> storeShift;
         }
     }
 }
@@ -286,6 +281,72 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     __syncwarp();
 }
 
+// Warp-cooperative traceback. Every lane holds the trace word of one band offset of a 32-offset window around the
+// current path position for the current 16-column block (one coalesced 128-byte load per block, the next block
+// prefetched), so that a step costs a shuffle instead of a dependent global load. Records EVERY diagonal step
+// (x, y), last step first, into steps[]; returns how many. All control flow is warp-uniform.
+__device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, int32_t lo, int32_t hi,
+                                            int32_t bestI, int32_t bestJ, uint2* __restrict__ steps)
+{
+    const int32_t lane = int32_t(threadIdx.x & 31u);
+    const int32_t Wpad = int32_t(dpPaddedWidth(lo, hi));
+    int32_t i = bestI, j = bestJ;
+    uint32_t n = 0;
+    if(i <= 0 || j <= 0) return 0;
+    auto loadWindow = [&](int32_t block, int32_t base) -> uint32_t {
+        const int32_t e = base + lane;
+        return (block >= 0 && e >= 0 && e < Wpad) ? trace[uint64_t(uint32_t(block)) * uint32_t(Wpad) + uint32_t(e)] : 0u;
+    };
+    int32_t block = i >> 4;
+    int32_t eb = (j - i + hi) - 16;
+    uint32_t cur = loadWindow(block, eb);
+    int32_t ebNext = eb;
+    uint32_t nxt = loadWindow(block - 1, ebNext);
+    while(i > 0 && j > 0) {
+        const int32_t e = j - i + hi;
+        if((i >> 4) != block) {
+            block = i >> 4;
+            if(e - ebNext >= 0 && e - ebNext < 32) { cur = nxt; eb = ebNext; }
+            else { eb = e - 16; cur = loadWindow(block, eb); }
+            ebNext = e - 16;
+            nxt = loadWindow(block - 1, ebNext);
+        } else if(e - eb < 0 || e - eb >= 32) {
+            eb = e - 16;
+            cur = loadWindow(block, eb);
+        }
+        const uint32_t word = __shfl_sync(0xffffffffu, cur, e - eb);
+        const uint32_t code = (word >> (2 * (i & 15))) & 3u;
+        if(code == 1u) {
+            if(lane == 0) steps[n] = make_uint2(uint32_t(i - 1), uint32_t(j - 1));
+            n++; i--; j--;
+        } else if(code == 2u) j--;
+        else if(code == 3u) i--;
+        else break;
+    }
+    __syncwarp();
+    return n;
+}
+
+// Keep, in place and in order, the recorded steps whose k-mers are equal (src/AssemblerAlign3.cpp:279-295,
+// src/Align4.cpp:1052-1068). Returns the number kept.
+__device__ inline uint32_t filterEqualSteps(uint2* __restrict__ steps, uint32_t n, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t count = 0;
+    for(uint32_t base = 0; base < n; base += 32) {
+        const uint32_t k = base + lane;
+        bool keep = false;
+        uint2 s = make_uint2(0, 0);
+        if(k < n) { s = steps[k]; keep = (a[s.x] == b[s.y]); }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if(keep) steps[count + __popc(m & ((1u << lane) - 1u))] = s;
+        count += __popc(m);
+        __syncwarp();
+    }
+    return count;
+}
+
 // Traceback (executed redundantly by all lanes; loads are warp-uniform). F(x, y) is called for every
 // diagonal step, last step first.
 template<class F> __device__ inline void tracebackPath(const uint32_t* __restrict__ trace, int32_t lo, int32_t hi,
@@ -321,7 +382,8 @@ struct Method3Args {
 };
 
 template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
-method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restrict__ trace, DpJob* __restrict__ jobs2)
+method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restrict__ trace, DpJob* __restrict__ jobs2,
+                    uint2* __restrict__ ordinals)
 {
     extern __shared__ int32_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -349,16 +411,23 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
     __threadfence_block();
     const uint32_t* oa = g.dsOrdinal + job.aOffset;
     const uint32_t* ob = g.dsOrdinal + job.bOffset;
+    // The stage-2 ordinal slots of this candidate (min(nx,ny) >= min(n0ds,n1ds)) double as scratch for the path.
+    uint2* scratch = ordinals + jobs2[p].outOffset;
+    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, scratch);
     int32_t offsetMin = INT32_MAX, offsetMax = INT32_MIN;
-    uint32_t steps = 0;
-    tracebackPath(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, [&](uint32_t x, uint32_t y) {
-        steps++;
-        if(a[x] == b[y]) {
-            const int32_t off = int32_t(oa[x]) - int32_t(ob[y]);
+    for(uint32_t k = lane; k < steps; k += 32) {
+        const uint2 s = scratch[k];
+        if(a[s.x] == b[s.y]) {
+            const int32_t off = int32_t(oa[s.x]) - int32_t(ob[s.y]);
             offsetMin = min(offsetMin, off);
             offsetMax = max(offsetMax, off);
         }
-    });
+    }
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1) {
+        offsetMin = min(offsetMin, __shfl_xor_sync(0xffffffffu, offsetMin, d));
+        offsetMax = max(offsetMax, __shfl_xor_sync(0xffffffffu, offsetMax, d));
+    }
     if(lane == 0) {
         DpJob j2 = jobs2[p];
         if(steps == 0) j2.state = kStateEmpty;                                  // :185-191
@@ -416,13 +485,8 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
     __syncwarp();
     __threadfence_block();
     uint2* out = ordinals + job.outOffset;
-    uint32_t count = 0;
-    tracebackPath(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, [&](uint32_t x, uint32_t y) {
-        if(a[x] == b[y]) {
-            if(lane == 0) out[count] = make_uint2(x, y);
-            count++;
-        }
-    });
+    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, out);
+    const uint32_t count = filterEqualSteps(out, steps, a, b);
     if(lane == 0) counts[p] = count;
 }
 
@@ -450,13 +514,14 @@ __device__ __forceinline__ uint32_t compressedStreakBytes(int32_t skip0, int32_t
 static __global__ void alignmentInfoKernel(uint32_t n, const DpJob* __restrict__ jobs, const uint2* __restrict__ ordinals,
                                            const uint32_t* __restrict__ counts, FilterOptions f,
                                            uint32_t* __restrict__ infoWords, uint32_t* __restrict__ keep,
-                                           uint32_t* __restrict__ compressedBytes)
+                                           uint32_t* __restrict__ compressedBytes, unsigned long long* __restrict__ skippedCounter)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n) return;
     const DpJob job = jobs[p];
     keep[p] = 0;
     compressedBytes[p] = 0;
+    if(job.state == kStateSkipped && skippedCounter) atomicAdd(skippedCounter, 1ull);
     if(job.state != kStateRun) return;
     const uint32_t count = counts[p];
     if(count == 0) return;                               // empty alignments are never stored
@@ -546,17 +611,18 @@ static __global__ void alignmentWriteKernel(uint32_t n, const uint32_t* __restri
                                             const uint32_t* __restrict__ infoWords, const uint32_t* __restrict__ jobIndex,
                                             const uint32_t* __restrict__ keep,
                                             const uint32_t* __restrict__ keepIndex, const unsigned long long* __restrict__ byteOffsets,
+                                            uint64_t recordBase, uint64_t byteBase,
                                             uint32_t* __restrict__ records, unsigned long long* __restrict__ compressedToc,
                                             uint8_t* __restrict__ compressedData)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n || !keep[p]) return;
     const uint32_t j = jobIndex ? jobIndex[p] : p;
-    const uint64_t r = keepIndex[p];
+    const uint64_t r = recordBase + keepIndex[p];
     uint32_t* rec = records + 16ull * r;
     rec[0] = candidates[3ull * p]; rec[1] = candidates[3ull * p + 1]; rec[2] = candidates[3ull * p + 2] & 0xffu;
     for(int i = 0; i < 13; i++) rec[3 + i] = infoWords[13ull * j + i];
-    const uint64_t byteOffset = byteOffsets[p];
+    const uint64_t byteOffset = byteBase + byteOffsets[p];
     compressedToc[r] = byteOffset;
     uint8_t* out = compressedData + byteOffset;
     const uint32_t count = counts[j];
@@ -618,6 +684,12 @@ static __global__ void setTraceOffsetsKernel(DpJob* __restrict__ jobs, uint32_t 
     if(p >= n) return;
     jobs[p].traceOffset = traceOffsets[p];
     if(outOffsets) jobs[p].outOffset = outOffsets[p];
+}
+
+static __global__ void setOutOffsetsKernel(DpJob* __restrict__ jobs, uint32_t n, const unsigned long long* __restrict__ outOffsets)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p < n) jobs[p].outOffset = outOffsets[p];
 }
 
 static __global__ void stage2TraceWordsKernel(const DpJob* __restrict__ jobs, uint32_t n, unsigned long long* __restrict__ traceWords)
