@@ -200,9 +200,43 @@ struct Batch {
     DeviceBuffer<uint32_t> gridCounts, gridAux, gridList, componentCount, jobOffsets;
     DeviceBuffer<uint8_t> gridFlags;
     DeviceBuffer<int32_t> gridBands;
+    // band-class ordering of the DP jobs
+    DeviceBuffer<uint32_t> classLimits, orderValsA, orderValsB;
+    DeviceBuffer<uint64_t> orderKeysA, orderKeysB;
+    const uint32_t* order = nullptr;
 };
 
 struct DpTotals { unsigned long long traceWords = 0; double ms = 0.; };
+
+// Groups the runnable jobs by band class (longest first inside a class). Returns per-class counts; b.order holds the
+// job indices, class after class.
+void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs, std::vector<uint64_t>& classCounts)
+{
+    cudaStream_t st = c->stream;
+    classCounts.assign(kClassCount, 0);
+    if(nJobs == 0) return;
+    if(!b.classLimits.get()) {
+        b.classLimits.reserve(kClassCount);
+        uint32_t limits[kClassCount];
+        for(int k = 0; k < kClassCount; k++) limits[k] = kClasses[k].wMax;
+        SHB_CUDA(cudaMemcpyAsync(b.classLimits.get(), limits, sizeof(limits), cudaMemcpyHostToDevice, st));
+        SHB_CUDA(cudaStreamSynchronize(st));
+    }
+    b.orderKeysA.reserve(nJobs); b.orderKeysB.reserve(nJobs); b.orderValsA.reserve(nJobs); b.orderValsB.reserve(nJobs);
+    SHB_LAUNCH(dpClassKeysKernel, ceilDiv(nJobs, 256), 256, 0, st, jobs, nJobs, (const uint32_t*)b.classLimits.get(), uint32_t(kClassCount),
+               b.orderKeysA.get(), b.orderValsA.get());
+    const int ranges[1][2] = {{0, 40}};
+    const bool inB = radixSort<true>(b.orderKeysA.get(), b.orderKeysB.get(), b.orderValsA.get(), b.orderValsB.get(), nJobs, ranges, 1, c->sortWs, st);
+    b.order = inB ? b.orderValsB.get() : b.orderValsA.get();
+    c->scalars.reserve(64 + 256);
+    unsigned long long* dCounts = c->scalars.get() + 64;
+    SHB_CUDA(cudaMemsetAsync(dCounts, 0, 256 * sizeof(unsigned long long), st));
+    SHB_LAUNCH(digitCountKernel, ceilDiv(nJobs, 256), 256, 0, st, (const uint64_t*)(inB ? b.orderKeysB.get() : b.orderKeysA.get()), nJobs, 32, 0xffu, dCounts);
+    unsigned long long h[256];
+    SHB_CUDA(cudaMemcpyAsync(h, dCounts, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SHB_CUDA(cudaStreamSynchronize(st));
+    for(int k = 0; k < kClassCount; k++) classCounts[k] = h[k];
+}
 
 // Scratch offsets + the banded DP + traceback for nJobs jobs whose lo/hi/state are set.
 void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* sequences, DpScores scores, uint32_t maxWidth,
@@ -222,19 +256,23 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nJobs, 256), 256, 0, st, b.jobs.get(), nJobs, (const unsigned long long*)b.twOff.get(),
                (const unsigned long long*)b.outOff.get());
     SHB_CUDA(cudaMemsetAsync(b.counts.get(), 0, 4ull * nJobs, st));
+    std::vector<uint64_t> classCounts;
+    buildClassOrder(c, b, b.jobs.get(), nJobs, classCounts);
     BandedArgs g;
-    g.n = nJobs; g.kmerIds = sequences; g.scores = scores;
+    g.kmerIds = sequences; g.scores = scores;
     SHB_CUDA(cudaEventRecord(ev.a, st));
-    uint32_t wMin = 0;
+    uint64_t offset = 0;
+    (void)maxWidth;
     for(int k = 0; k < kClassCount; k++) {
-        const uint32_t wMax = kClasses[k].wMax;
-        const uint32_t warps = warpsForClass(kClasses[k]);
-        const size_t smem = smemForClass(kClasses[k], warps);
-        g.wMin = wMin; g.wMax = wMax;
-        launchBanded(kClasses[k], ceilDiv(nJobs, warps), warps * 32, smem, st, g, (const DpJob*)b.jobs.get(), b.trace.get(),
-                     b.ordinals.get(), b.counts.get());
-        wMin = wMax;
-        if(wMax >= maxWidth) break;
+        const uint32_t count = uint32_t(classCounts[k]);
+        if(count) {
+            const uint32_t warps = warpsForClass(kClasses[k]);
+            const size_t smem = smemForClass(kClasses[k], warps);
+            g.n = count; g.order = b.order + offset; g.wMin = 0; g.wMax = kClasses[k].wMax;
+            launchBanded(kClasses[k], ceilDiv(count, warps), warps * 32, smem, st, g, (const DpJob*)b.jobs.get(), b.trace.get(),
+                         b.ordinals.get(), b.counts.get());
+        }
+        offset += count;
     }
     SHB_CUDA(cudaEventRecord(ev.b, st));
 }
@@ -361,16 +399,19 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             g1.candidates = b.cand.get(); g1.candidateBegin = begin; g1.n = nb;
             g1.toc = c->toc.get(); g1.dsToc = ac.dsToc.get(); g1.dsKmer = ac.dsKmer.get(); g1.dsOrdinal = ac.dsOrdinal.get();
             g1.scores = scores; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
+            std::vector<uint64_t> classCounts1;
+            buildClassOrder(c, b, b.jobs1.get(), nb, classCounts1);
             SHB_CUDA(cudaEventRecord(dpEv1.a, st));
-            uint32_t wMin = 0;
+            uint64_t offset1 = 0;
             for(int k = 0; k < kClassCount; k++) {
-                const uint32_t wMax = kClasses[k].wMax;
-                const uint32_t warps = warpsForClass(kClasses[k]);
-                const size_t smem = smemForClass(kClasses[k], warps);
-                g1.wMin = wMin; g1.wMax = wMax;
-                launchStage1(kClasses[k], ceilDiv(nb, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
-                wMin = wMax;
-                if(wMax >= maxStage1Width) break;
+                const uint32_t count = uint32_t(classCounts1[k]);
+                if(count) {
+                    const uint32_t warps = warpsForClass(kClasses[k]);
+                    const size_t smem = smemForClass(kClasses[k], warps);
+                    g1.n = count; g1.order = b.order + offset1; g1.wMin = 0; g1.wMax = kClasses[k].wMax;
+                    launchStage1(kClasses[k], ceilDiv(count, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
+                }
+                offset1 += count;
             }
             SHB_CUDA(cudaEventRecord(dpEv1.b, st));
             SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());

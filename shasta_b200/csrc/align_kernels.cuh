@@ -374,6 +374,7 @@ template<class F> __device__ inline void tracebackPath(const uint32_t* __restric
 struct Method3Args {
     const uint32_t* candidates;     // n x 3 (readId0, readId1, isSameStrand)
     uint64_t candidateBegin; uint32_t n;
+    const uint32_t* order;          // job indices of this launch's band class, longest first; n = how many
     const uint64_t* toc;            // global rows (all reads)
     const uint64_t* dsToc; const uint32_t* dsKmer; const uint32_t* dsOrdinal;
     DpScores scores;
@@ -387,12 +388,11 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
 {
     extern __shared__ int32_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + warp;
-    if(p >= g.n) return;
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;
+    if(slot >= g.n) return;
+    const uint32_t p = g.order[slot];
     DpJob job = jobs1[p];
     if(job.state != kStateRun) return;
-    const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
-    if(Wpad <= g.wMin || Wpad > g.wMax) return;
     const uint32_t* a = g.dsKmer + job.aOffset;
     const uint32_t* b = g.dsKmer + job.bOffset;
     int32_t bestScore, bestI, bestJ;
@@ -451,6 +451,7 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
 // steps written LAST STEP FIRST to ordinals[outOffset ...]; counts[p] receives how many.
 struct BandedArgs {
     uint32_t n;
+    const uint32_t* order;          // job indices of this launch's band class, longest first; n = how many
     const uint32_t* kmerIds;
     DpScores scores;
     uint32_t wMin, wMax;
@@ -462,12 +463,11 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
 {
     extern __shared__ int32_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + warp;
-    if(p >= g.n) return;
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;
+    if(slot >= g.n) return;
+    const uint32_t p = g.order[slot];
     const DpJob job = jobs[p];
     if(job.state != kStateRun) return;          // counts[] is zeroed by the host
-    const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
-    if(Wpad <= g.wMin || Wpad > g.wMax) return;
     const uint32_t* a = g.kmerIds + job.aOffset;
     const uint32_t* b = g.kmerIds + job.bOffset;
     int32_t bestScore, bestI, bestJ;
@@ -684,6 +684,23 @@ static __global__ void setTraceOffsetsKernel(DpJob* __restrict__ jobs, uint32_t 
     if(p >= n) return;
     jobs[p].traceOffset = traceOffsets[p];
     if(outOffsets) jobs[p].outOffset = outOffsets[p];
+}
+
+// Sort key of a DP job: band class in bits 32.., then longest sequence first (load balance inside a launch).
+// classLimits[k] = widest padded band of class k; jobs that do not run get class 255.
+static __global__ void dpClassKeysKernel(const DpJob* __restrict__ jobs, uint32_t n, const uint32_t* __restrict__ classLimits,
+                                         uint32_t classCount, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const DpJob j = jobs[p];
+    uint32_t cls = 255;
+    if(j.state == kStateRun) {
+        const uint32_t Wpad = dpPaddedWidth(j.lo, j.hi);
+        for(uint32_t k = 0; k < classCount; k++) if(Wpad <= classLimits[k]) { cls = k; break; }
+    }
+    keys[p] = (uint64_t(cls) << 32) | uint64_t(0xffffffffu - j.nx);
+    vals[p] = p;
 }
 
 static __global__ void setOutOffsetsKernel(DpJob* __restrict__ jobs, uint32_t n, const unsigned long long* __restrict__ outOffsets)
