@@ -113,7 +113,7 @@ void buildDownsampled(shb_context* c, uint32_t k, double factor)
     c->flagsBuf.reserve(std::min<uint64_t>(chunk, M) + 1);
     c->indexBuf.reserve(std::min<uint64_t>(chunk, M) + 1);
     c->scanWs.reserve(scanWorkspaceElements(chunk));
-    c->scalars.reserve(64);
+    // scalars: 512 entries, allocated once at context creation
     uint32_t* totalDev = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
     // Pass 0 sizes the output exactly; pass 1 compacts.
     uint64_t total = 0;
@@ -228,7 +228,7 @@ void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs
     const int ranges[1][2] = {{0, 40}};
     const bool inB = radixSort<true>(b.orderKeysA.get(), b.orderKeysB.get(), b.orderValsA.get(), b.orderValsB.get(), nJobs, ranges, 1, c->sortWs, st);
     b.order = inB ? b.orderValsB.get() : b.orderValsA.get();
-    c->scalars.reserve(64 + 256);
+    // scalars: 512 entries, allocated once at context creation
     unsigned long long* dCounts = c->scalars.get() + 64;
     SHB_CUDA(cudaMemsetAsync(dCounts, 0, 256 * sizeof(unsigned long long), st));
     SHB_LAUNCH(digitCountKernel, ceilDiv(nJobs, 256), 256, 0, st, (const uint64_t*)(inB ? b.orderKeysB.get() : b.orderKeysA.get()), nJobs, 32, 0xffu, dCounts);
@@ -338,7 +338,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     const uint64_t cellBudget = 192ull << 20;      // method 4: cells of scratch per batch
     Batch b;
     c->scanWs.reserve(scanWorkspaceElements(4ull * batchMax * 64));
-    c->scalars.reserve(64);
+    // scalars: 512 entries, allocated once at context creation
     unsigned long long* total64 = c->scalars.get() + 48;
     uint32_t* total32 = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
 

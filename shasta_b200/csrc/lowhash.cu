@@ -61,7 +61,7 @@ uint32_t buildSegments(shb_context* c, const uint64_t* sortedKeys, uint32_t n, i
     c->indexBuf.reserve(n);
     c->segStartBuf.reserve(uint64_t(n) + 1);
     c->scanWs.reserve(scanWorkspaceElements(n));
-    c->scalars.reserve(64);
+    // scalars: 512 entries, allocated once at context creation
     SHB_LAUNCH(headFlagsKernel, ceilDiv(n, 256), 256, 0, st, sortedKeys, n, shift, c->flagsBuf.get());
     uint32_t* total = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
     exclusiveScan<uint32_t>(c->flagsBuf.get(), c->indexBuf.get(), n, total, c->scanWs.get(), st);
@@ -123,7 +123,7 @@ uint64_t countHighFrequency(shb_context* c, const Accumulator& acc, uint64_t min
     c->flagsBuf.reserve(n);
     c->indexBuf.reserve(n);
     c->scanWs.reserve(scanWorkspaceElements(n));
-    c->scalars.reserve(64);
+    // scalars: 512 entries, allocated once at context creation
     SHB_LAUNCH(frequencyFlagsKernel, ceilDiv(n, 256), 256, 0, st, (const uint32_t*)accVals(c, acc), n, minFrequency, c->flagsBuf.get());
     uint32_t* total = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
     exclusiveScan<uint32_t>(c->flagsBuf.get(), c->indexBuf.get(), n, total, c->scanWs.get(), st);
@@ -179,7 +179,7 @@ void lowhashBegin(shb_context* c, const shb_lowhash_params& p)
     if(S.capacity > M + 1) S.capacity = M + 1;
     c->stats.reserve(3 * R + 1);
     SHB_CUDA(cudaMemsetAsync(c->stats.get(), 0, (3 * R + 1) * sizeof(unsigned long long), st));
-    c->scalars.reserve(64);
+    // scalars: 512 entries, allocated once at context creation
     S.active = true;
 }
 
@@ -365,7 +365,7 @@ void devicePartition(shb_context* c, uint64_t* keys, uint32_t* vals, uint64_t n,
     const bool inB = radixSort<true>(keys, c->partKeys.get(), vals, c->partVals.get(), n, range, 1, c->sortWs, st);
     uint64_t* sortedKeys = inB ? c->partKeys.get() : keys;
     // Digit boundaries by binary search on the host-visible sorted keys would need a copy; count on the device instead.
-    c->scalars.reserve(64 + 256);
+    // scalars: 512 entries, allocated once at context creation
     unsigned long long* dCounts = c->scalars.get() + 64;
     SHB_CUDA(cudaMemsetAsync(dCounts, 0, buckets * sizeof(unsigned long long), st));
     SHB_LAUNCH(digitCountKernel, ceilDiv(n, 256), 256, 0, st, (const uint64_t*)sortedKeys, uint32_t(n), int(shift), buckets - 1u, dCounts);
