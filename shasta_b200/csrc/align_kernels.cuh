@@ -200,40 +200,73 @@ __device__ inline void bandedOverlapDp(const uint32_t* __restrict__ a, uint32_t 
 // boundary score). All scores of the previous column live in registers; no shared memory, no scan.
 // Same recurrence, tie-break and end-cell rules as bandedOverlapDp (bit-identical results, tested against the oracle);
 // the end cell is selected with the order-independent formulation "maximum score, then smallest i, then smallest j".
+// Per-offset constants of a sub-chunk, fixed for the whole job. The cell of band offset e is inside the matrix for
+// columns first <= i <= min(nx, ny + hi - e), where first = max(0, hi - e); in column `first` it is a boundary cell
+// (i == 0 or j == 0, score 0). rowEnd = the column in which it reaches the last row j == ny when that column is inside
+// the matrix (else INT_MIN). cap = INT_MAX inside the band, "minus infinity" for the padding offsets e >= W, which
+// must never carry a finite score (they would open a path around the band edge).
+template<int C> struct SubChunkLimits { int32_t first[C]; int32_t rowEnd[C]; int32_t cap[C]; };
+
+template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimits<C>& lim, int32_t e0, int32_t W, int32_t hi, int32_t nx, int32_t ny)
+{
+#pragma unroll
+    for(int c = 0; c < C; c++) {
+        const int32_t e = e0 + c;
+        const bool inBand = e < W;
+        const int32_t first = max(0, hi - e);
+        const int32_t rowEnd = ny + hi - e;
+        lim.first[c] = inBand ? first : 0x7fffffff;
+        lim.rowEnd[c] = (inBand && rowEnd >= first && rowEnd <= nx) ? rowEnd : int32_t(0x80000000);
+        lim.cap[c] = inBand ? 0x7fffffff : kNegInf;
+    }
+}
+
+// One sub-chunk (C consecutive band offsets starting at e0) of column i. Straight-line code for the common interior
+// cell; cells outside the matrix are NOT masked: above the matrix they only ever combine "minus infinity" values
+// (kNegInf plus a bounded drift), below the matrix their values are never read by an in-matrix cell, and their trace
+// codes are never visited by the traceback. bestJ is tracked as j + hi (fixed up by the caller).
 template<int C> __device__ __forceinline__ void systolicSubChunk(
-    int32_t (&H)[C], uint32_t (&Tr)[C], int32_t e0, int32_t i, bool colValid, uint32_t ai,
+    int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t e0, int32_t i, uint32_t ai,
     int32_t below /* H(i, e0-1) */, int32_t top /* H(i-1, e0+C) */,
-    const uint32_t* __restrict__ b, int32_t nx, int32_t ny, int32_t W, int32_t hi, uint32_t WpadJob, DpScores sc,
+    const uint32_t* __restrict__ b, int32_t jFirst /* e0 + i - hi */, int32_t nx, int32_t ny, uint32_t WpadJob, DpScores sc,
     uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
 {
-    // Written for predication: the common case (interior cell) is straight-line code; boundary / out-of-matrix cells
-    // are fixed up with selects; only the rare end-cell bookkeeping and the 1-in-16 trace store branch.
-    const int32_t jBase = e0 + i - hi;
-    const bool storeNow = colValid && (((i & 15) == 15) || (i == nx));
-    const uint32_t storeShift = 2u * (15u - uint32_t(i & 15));
     int32_t vertIn = below;
 #pragma unroll
     for(int c = 0; c < C; c++) {
-        const int32_t j = jBase + c;
-        const bool inMatrix = colValid && (e0 + c < W) && (j >= 0) && (j <= ny);
-        const bool interior = inMatrix && (i > 0) && (j > 0);
-        const uint32_t bv = interior ? __ldg(b + (j - 1)) : 0xffffffffu;
+        // b[j-1], with the index clamped into the row so that the load is always legal (the value only matters for
+        // interior cells, whose index is in range).
+        const uint32_t bIndex = min(uint32_t(jFirst + c - 1), uint32_t(ny - 1));
+        const uint32_t bv = __ldg(b + bIndex);
         const int32_t diag = H[c] + ((ai == bv) ? sc.match : sc.mismatch);      // H(i-1, e)
         const int32_t vert = vertIn + sc.gap;                                   // H(i, e-1)
         const int32_t horz = ((c + 1 < C) ? H[c + 1] : top) + sc.gap;           // H(i-1, e+1)
         const int32_t dv = max(diag, vert);
-        int32_t h = max(dv, horz);
-        uint32_t code = (horz > dv) ? 3u : ((vert > diag) ? 2u : 1u);
-        h = interior ? h : (inMatrix ? 0 : kNegInf);
-        code = interior ? code : 0u;
+        int32_t h = min(max(dv, horz), lim.cap[c]);
+        const uint32_t code = (horz > dv) ? 3u : ((vert > diag) ? 2u : 1u);
+        h = (i == lim.first[c]) ? 0 : h;
         H[c] = h;
         vertIn = h;
         Tr[c] = (Tr[c] >> 2) | (code << 30);        // always holds the codes of the last 16 columns
-        if(inMatrix && (j == ny || i == nx)) {
-            if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && j < bestJ)))) { bestScore = h; bestI = i; bestJ = j; }
+        if(i == lim.rowEnd[c]) {                     // last row, j == ny
+            if(h > bestScore || (h == bestScore && i < bestI)) { bestScore = h; bestI = i; bestJ = e0 + c + i; }
         }
     }
-    if(storeNow) {
+    if(i == nx) {
+        // Last column: every in-matrix cell is an end-cell candidate (ties: smaller j, i.e. smaller offset, first).
+#pragma unroll
+        for(int c = 0; c < C; c++) {
+            const int32_t e = e0 + c;
+            const int32_t hi = e0 + i - jFirst;
+            if(lim.cap[c] == 0x7fffffff && lim.first[c] <= nx && nx <= ny + hi - e) {
+                const int32_t h = H[c];
+                const int32_t jPlusHi = e + i;
+                if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && jPlusHi < bestJ)))) { bestScore = h; bestI = i; bestJ = jPlusHi; }
+            }
+        }
+    }
+    if(((i & 15) == 15 || i == nx) && uint32_t(i) <= uint32_t(nx)) {
+        const uint32_t storeShift = 2u * (15u - uint32_t(i & 15));
         uint32_t* traceRow = trace + uint64_t(uint32_t(i) >> 4) * WpadJob;
 #pragma unroll
         for(int c = 0; c < C; c++) {
@@ -252,23 +285,28 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     const uint32_t WpadJob = dpPaddedWidth(lo, hi);
     int32_t HA[C], HB[C];
     uint32_t TA[C], TB[C];
+    SubChunkLimits<C> limA, limB;
+    const int32_t eA = (2 * lane) * C, eB = (2 * lane + 1) * C;
 #pragma unroll
     for(int c = 0; c < C; c++) { HA[c] = kNegInf; HB[c] = kNegInf; TA[c] = 0; TB[c] = 0; }
+    initSubChunkLimits<C>(limA, eA, W, hi, nx, ny);
+    initSubChunkLimits<C>(limB, eB, W, hi, nx, ny);
     bestScore = kNegInf * 2; bestI = 0x7fffffff; bestJ = 0x7fffffff;
-    const int32_t eA = (2 * lane) * C, eB = (2 * lane + 1) * C;
-    for(int32_t t2 = 0; t2 <= nx + 31; t2++) {
+    int32_t jA = eA - lane - hi, jB = eB - lane - hi;          // first row of each sub-chunk in column i = t2 - lane
+    for(int32_t t2 = 0; t2 <= nx + 31; t2++, jA++, jB++) {
         const int32_t i = t2 - lane;
-        const bool colValid = (i >= 0) && (i <= nx);
-        const uint32_t ai = (colValid && i > 0) ? __ldg(a + (i - 1)) : 0u;
+        // a[i-1], index clamped into the row (the value is irrelevant for i <= 0 and i > nx).
+        const uint32_t ai = __ldg(a + min(uint32_t(i - 1), uint32_t(nx - 1)));
         // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
         int32_t below = __shfl_up_sync(0xffffffffu, HB[C - 1], 1);
         if(lane == 0) below = kNegInf;
-        systolicSubChunk<C>(HA, TA, eA, i, colValid, ai, below, HB[0], b, nx, ny, W, hi, WpadJob, sc, trace, bestScore, bestI, bestJ);
+        systolicSubChunk<C>(HA, TA, limA, eA, i, ai, below, HB[0], b, jA, nx, ny, WpadJob, sc, trace, bestScore, bestI, bestJ);
         // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
         int32_t top = __shfl_down_sync(0xffffffffu, HA[0], 1);
         if(lane == 31) top = kNegInf;
-        systolicSubChunk<C>(HB, TB, eB, i, colValid, ai, HA[C - 1], top, b, nx, ny, W, hi, WpadJob, sc, trace, bestScore, bestI, bestJ);
+        systolicSubChunk<C>(HB, TB, limB, eB, i, ai, HA[C - 1], top, b, jB, nx, ny, WpadJob, sc, trace, bestScore, bestI, bestJ);
     }
+    if(bestI != 0x7fffffff) bestJ -= hi;          // bestJ was tracked as j + hi
     // Warp reduction of the end cell: maximum score, then smallest i, then smallest j.
 #pragma unroll
     for(int d = 16; d > 0; d >>= 1) {
