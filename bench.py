@@ -260,6 +260,8 @@ def main():
             if record:
                 stats_acc["dp_ms"] += ares.dpMs
                 stats_acc["dp_cells"] += ares.dpCells
+                stats_acc["align_copy_ms"] = stats_acc.get("align_copy_ms", 0.0) + ares.outputCopyMs
+                stats_acc["align_lib_ms"] = stats_acc.get("align_lib_ms", 0.0) + ares.hostWallMs
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         if record:
@@ -385,6 +387,9 @@ def main():
         "lowhash_ms_per_step": 1e3 * lowhash_s / args.steps, "align_ms_per_step": 1e3 * align_s / args.steps,
         "marker_iterations_per_s": M * iters * args.steps / lowhash_s,
         "device_event_ms_per_step": ev0.elapsed_time(ev1) / args.steps,
+        "align_breakdown_ms_per_step": {"dp_kernels": stats_acc["dp_ms"] / args.steps,
+                                        "result_copy_to_host": stats_acc.get("align_copy_ms", 0.0) / args.steps,
+                                        "library_call": stats_acc.get("align_lib_ms", 0.0) / args.steps},
         "gpu_launches": int(stats_acc["launches"]), "clocks": clocks.summary(),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }

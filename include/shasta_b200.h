@@ -193,6 +193,8 @@ typedef struct {
     double   dpMs;                  /* device time inside the DP kernels (CUDA events) */
     double   totalMs;               /* device time of the whole call */
     uint64_t kernelLaunches;
+    double   outputCopyMs;          /* host wall time of the final device->host copy of the results */
+    double   hostWallMs;            /* host wall time of the whole call */
 } shb_align_result;
 
 /* Computes the marker alignment of every candidate on the markers held by ctx (all reads must be

@@ -51,7 +51,8 @@ class AlignOptions(C.Structure):
 
 class AlignResult(C.Structure):
     _fields_ = [("candidateCount", C.c_uint64), ("alignmentCount", C.c_uint64), ("skippedCount", C.c_uint64),
-                ("dpCells", C.c_uint64), ("dpMs", C.c_double), ("totalMs", C.c_double), ("kernelLaunches", C.c_uint64)]
+                ("dpCells", C.c_uint64), ("dpMs", C.c_double), ("totalMs", C.c_double), ("kernelLaunches", C.c_uint64),
+                ("outputCopyMs", C.c_double), ("hostWallMs", C.c_double)]
 
 
 # Defaults of src/AssemblerOptions.cpp:380-489

@@ -5,6 +5,7 @@
 #include "align_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -300,6 +301,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     SHB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     g_launchCount = 0;
+    const auto wall0 = std::chrono::steady_clock::now();
     Events totalEv, dpEv1, dpEv2;
     SHB_CUDA(cudaEventRecord(totalEv.a, st));
     double dpMs = 0.;
@@ -494,6 +496,8 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     }
 
     const uint64_t count = outCount;
+    SHB_CUDA(cudaStreamSynchronize(st));
+    const auto copy0 = std::chrono::steady_clock::now();
     void* recOut = malloc(count ? 64 * count : 1);
     uint64_t* tocOut = (uint64_t*)malloc(8 * (count + 1));
     uint8_t* dataOut = (uint8_t*)malloc(outBytes ? outBytes : 1);
@@ -514,6 +518,9 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     if(result) {
         result->candidateCount = n; result->alignmentCount = count; result->skippedCount = skipped;
         result->dpCells = dpCells; result->dpMs = dpMs; result->totalMs = totalMs; result->kernelLaunches = g_launchCount;
+        const auto wall1 = std::chrono::steady_clock::now();
+        result->outputCopyMs = std::chrono::duration<double, std::milli>(wall1 - copy0).count();
+        result->hostWallMs = std::chrono::duration<double, std::milli>(wall1 - wall0).count();
     }
 }
 
