@@ -241,7 +241,11 @@ def main():
             cand, _, _, res = ctx.lowhash0(lparams, want_stats=True)
             sweep_ms, sweep_launches, launches = res.sweepMs, res.sweepLaunches, res.kernelLaunches
         else:
-            cand, _, _ = D.lowhash0_sharded(stages, MINHASH_MAY2022, R)
+            cand, _, info = D.lowhash0_sharded(stages, MINHASH_MAY2022, R)
+            if record:
+                for k, v in info["timing_s"].items():
+                    stats_acc["sharded_" + k] = stats_acc.get("sharded_" + k, 0.0) + v
+            cand = D.rebalance_candidates(cand)
             res = stages.counters()
             sweep_ms, sweep_launches, launches = res.sweepMs, res.sweepLaunches, res.kernelLaunches
         torch.cuda.synchronize()
@@ -387,6 +391,8 @@ def main():
         "lowhash_ms_per_step": 1e3 * lowhash_s / args.steps, "align_ms_per_step": 1e3 * align_s / args.steps,
         "marker_iterations_per_s": M * iters * args.steps / lowhash_s,
         "device_event_ms_per_step": ev0.elapsed_time(ev1) / args.steps,
+        "sharded_lowhash_breakdown_ms_per_step": {k[8:]: 1e3 * v / args.steps for k, v in stats_acc.items() if k.startswith("sharded_")},
+        "gather_ms_per_step": 1e3 * stats_acc["gather_s"] / args.steps,
         "align_breakdown_ms_per_step": {"dp_kernels": stats_acc["dp_ms"] / args.steps,
                                         "result_copy_to_host": stats_acc.get("align_copy_ms", 0.0) / args.steps,
                                         "library_call": stats_acc.get("align_lib_ms", 0.0) / args.steps},

@@ -72,6 +72,14 @@ def lowhash0_sharded(stages, params, read_count_total, group=None):
     if iterations == 0:
         raise ValueError("the sharded path needs a fixed minHashIterationCount (all shipped configurations use one); "
                          "the candidate-driven stopping rule needs a merge per iteration")
+    import time
+    timing = {"sweep": 0.0, "partition": 0.0, "exchange": 0.0, "process": 0.0, "final": 0.0}
+
+    def tick():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        return time.perf_counter()
+
     log2_buckets = stages.begin(params)
     if log2_buckets < log2w:
         raise ValueError("fewer buckets than ranks")
@@ -80,19 +88,38 @@ def lowhash0_sharded(stages, params, read_count_total, group=None):
     it = 0
     while it < iterations:
         group_size = min(stages.max_fused_iterations, iterations - it)
+        t0 = tick()
         counts = stages.sweep(it, group_size)
+        t1 = tick()
+        timing["sweep"] += t1 - t0
         # Group every slab by bucket owner first (device scratch is reused by each call), keep torch copies.
         staged = []
         for s in range(group_size):
             keys, vals = stages.slab(s, counts[s])
             pk, pv, pc = stages.partition(keys, vals, entry_shift, log2w)
             staged.append((pk.clone(), pv.clone(), pc))
-        for pk, pv, pc in staged:
-            rk, _ = all_to_all_v(pk, pc, group)
-            rv, _ = all_to_all_v(pv, pc, group)
+        t2 = tick()
+        timing["partition"] += t2 - t1
+        # One exchange for the whole iteration group: slab after slab in each destination's segment would need a
+        # second sort at the receiver, so the slabs are exchanged one by one but the count exchange is batched.
+        send_counts = torch.tensor([pc for _, _, pc in staged], dtype=torch.int64, device=staged[0][0].device)    # [group, world]
+        received = []
+        rc_all = _exchange_counts(send_counts, group)
+        for s, (pk, pv, pc) in enumerate(staged):
+            rc = [int(x) for x in rc_all[s].tolist()]
+            rk = torch.empty(sum(rc), dtype=pk.dtype, device=pk.device)
+            rv = torch.empty(sum(rc), dtype=pv.dtype, device=pv.device)
+            dist.all_to_all_single(rk, pk, rc, pc, group=group)
+            dist.all_to_all_single(rv, pv, rc, pc, group=group)
+            received.append((rk, rv))
+        t3 = tick()
+        timing["exchange"] += t3 - t2
+        for rk, rv in received:
             exchanged += int(rk.numel())
             stages.process_entries(rk, rv)
+        timing["process"] += tick() - t3
         it += group_size
+    t_final = tick()
 
     # Pair counts to the owner of readId0.
     rb = read_bits(read_count_total)
@@ -107,7 +134,41 @@ def lowhash0_sharded(stages, params, read_count_total, group=None):
 
     stats = stages.stats_tensor()
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-    return cand, stats, {"log2BucketCount": log2_buckets, "entriesReceived": exchanged, "pairsReceived": int(rk.numel())}
+    timing["final"] = tick() - t_final
+    return cand, stats, {"log2BucketCount": log2_buckets, "entriesReceived": exchanged, "pairsReceived": int(rk.numel()),
+                         "timing_s": timing}
+
+
+def _exchange_counts(send_counts, group=None):
+    """send_counts[s, d] = items of slab s going to rank d. Returns recv[s, src] = items of slab s coming from src."""
+    world = dist.get_world_size(group)
+    flat = send_counts.t().contiguous().view(-1)             # destination-major: [world, group]
+    out = torch.empty_like(flat)
+    dist.all_to_all_single(out, flat, group=group)           # out[src*group + s] = what src sends me of slab s
+    return out.view(world, -1).t().contiguous()
+
+
+def rebalance_candidates(cand, group=None):
+    """Even out the per-rank candidate slices (owner(readId0) favours low read ids because readId0 < readId1) while
+    keeping the global (rank-order) order: rank g ends up with the g-th contiguous block of the concatenation."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() and dist.get_backend(group) == "nccl" else torch.device("cpu")
+    n_local = torch.tensor([len(cand)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    total = sum(counts)
+    my_begin = sum(counts[:rank])
+    bounds = [total * g // world for g in range(world + 1)]
+    send = []
+    for g in range(world):
+        lo = min(max(bounds[g], my_begin), my_begin + len(cand))
+        hi = min(max(bounds[g + 1], my_begin), my_begin + len(cand))
+        send.append(hi - lo)
+    t = torch.from_numpy(np.ascontiguousarray(cand, dtype=np.uint32).view(np.int32).reshape(-1)).to(dev)
+    recv, _ = all_to_all_v(t, [3 * x for x in send], group)
+    return recv.cpu().numpy().view(np.uint32).reshape(-1, 3)
 
 
 def gather_candidates(cand, group=None, dst=0):

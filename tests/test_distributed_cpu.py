@@ -160,7 +160,14 @@ def _worker(rank, world, port, case, result_path):
             owner = cand[:, 0].astype(np.int64) >> max(D.read_bits(R) - (world.bit_length() - 1), 0)
             assert (owner == rank).all()
         allc = D.gather_candidates(cand)
+        # rebalancing keeps the global order and evens the slice sizes
+        rbc = D.rebalance_candidates(cand)
+        allr = D.gather_candidates(rbc)
+        sizes = [None] * world
+        dist.all_gather_object(sizes, len(rbc))
+        assert max(sizes) - min(sizes) <= 1
         if rank == 0:
+            assert np.array_equal(allr, allc)
             oc, os_, _ = B.oracle_lowhash0(d["toc"], d["data"], d["flags"], B.LowHashParams(**case["params"]))
             ok = np.array_equal(allc, oc) and np.array_equal(stats.numpy().reshape(-1, 3).astype(np.uint64), os_)
             with open(result_path, "w") as f:
