@@ -388,3 +388,23 @@ def oracle_compute_alignment_table(records, read_count):
     lib.orc_compute_alignment_table.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.orc_compute_alignment_table(rec.ctypes.data, len(rec), read_count, toc.ctypes.data, table.ctypes.data)
     return toc, table[:4 * len(rec)].copy()
+
+
+def ref_write_data_dir(fasta, prefix, k=10, probability=0.1, seed=231, min_read_length=10000, threads=4):
+    lib = ref_lib()
+    lib.ref_write_data_dir.restype = C.c_int
+    lib.ref_write_data_dir.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_double, C.c_int, C.c_uint64, C.c_uint64]
+    if lib.ref_write_data_dir(fasta.encode(), prefix.encode(), k, probability, seed, min_read_length, threads):
+        raise RuntimeError("reference failed to write the Data directory")
+
+
+def ref_open_vector(path, object_size):
+    """(count, fnv checksum) of a MemoryMapped::Vector file as seen by the reference's own accessExistingReadOnly."""
+    lib = ref_lib()
+    lib.ref_open_vector.restype = C.c_int
+    lib.ref_open_vector.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    n, h = C.c_uint64(), C.c_uint64()
+    rc = lib.ref_open_vector(path.encode(), object_size, C.byref(n), C.byref(h))
+    if rc:
+        raise RuntimeError(f"the reference could not open {path}")
+    return n.value, h.value

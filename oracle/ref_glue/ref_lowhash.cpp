@@ -259,3 +259,82 @@ uint32_t ref_murmurhash2(const void* key, int len, uint32_t seed) { return Murmu
 void ref_free(void* p) { free(p); }
 
 } // extern "C"
+
+
+// ---------------------------------------------------------------------------------------------
+// Data/ directory interoperability (test infrastructure): the reference's own MemoryMapped code writes the
+// inputs of the path as named files, and opens files written by shasta_b200/assembler.py.
+#include "Alignment.hpp"
+
+// Opens a MemoryMapped::Vector file with the reference's accessExistingReadOnly for the given record size and returns the
+// object count and a byte checksum of the payload. Returns nonzero (and prints the reference's message) on failure.
+template<class T> static int openVector(const char* path, uint64_t* count, uint64_t* checksum)
+{
+    MemoryMapped::Vector<T> v;
+    v.accessExistingReadOnly(path);
+    *count = v.size();
+    uint64_t h = 1469598103934665603ULL;
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(v.begin());
+    for(uint64_t i = 0; i < v.size() * sizeof(T); i++) h = (h ^ bytes[i]) * 1099511628211ULL;
+    *checksum = h;
+    return 0;
+}
+
+extern "C" {
+
+// Writes <prefix>Markers.{toc,data}, <prefix>ReadFlags and <prefix>Kmers exactly as the reference would
+// (Reads::createNew / MarkerFinder / kmerTable with file-backed MemoryMapped vectors).
+int ref_write_data_dir(const char* fastaPath, const char* prefix, uint64_t k, double markerProbability, int seed,
+                       uint64_t minReadLength, uint64_t threadCount)
+{
+    try {
+        QuietCout quiet(true);
+        const string p(prefix);
+        Reads reads;
+        reads.createNew(1, p + "Reads", p + "ReadNames", p + "ReadMetaData", p + "ReadRepeatCounts", p + "ReadFlags",
+                        p + "ReadIdsSortedByName", 4096);
+        {
+            ReadLoader loader(fastaPath, 1, minReadLength, false, threadCount, p, 4096, reads);
+        }
+        MemoryMapped::Vector<KmerInfo> kmerTable;
+        {
+            // buildKmerTable creates an anonymous table; copy it into a named one.
+            MemoryMapped::Vector<KmerInfo> tmp;
+            buildKmerTable(tmp, k, markerProbability, seed);
+            kmerTable.createNew(p + "Kmers", 4096);
+            kmerTable.resize(tmp.size());
+            for(uint64_t i = 0; i < tmp.size(); i++) kmerTable[i] = tmp[i];
+            tmp.remove();
+        }
+        MemoryMapped::VectorOfVectors<CompressedMarker, uint64_t> markers;
+        markers.createNew(p + "Markers", 4096);
+        {
+            MarkerFinder finder(k, kmerTable, reads, markers, threadCount);
+        }
+        return 0;
+    } catch(const std::exception& e) {
+        fprintf(stderr, "ref_write_data_dir: %s\n", e.what());
+        return 1;
+    }
+}
+
+int ref_open_vector(const char* path, uint64_t objectSize, uint64_t* count, uint64_t* checksum)
+{
+    try {
+        switch(objectSize) {
+        case 1: return openVector<uint8_t>(path, count, checksum);
+        case 4: return openVector<uint32_t>(path, count, checksum);
+        case 7: return openVector<CompressedMarker>(path, count, checksum);
+        case 8: return openVector<uint64_t>(path, count, checksum);
+        case 12: return openVector<OrientedReadPair>(path, count, checksum);
+        case 24: return openVector< array<uint64_t, 3> >(path, count, checksum);
+        case 64: return openVector<AlignmentData>(path, count, checksum);
+        default: return 2;
+        }
+    } catch(const std::exception& e) {
+        fprintf(stderr, "ref_open_vector: %s\n", e.what());
+        return 1;
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,252 @@
+"""`shasta.Assembler`-shaped host API for the hot path (src/PythonModule.cpp:135-360 of chanzuckerberg/shasta).
+
+The method names, keyword arguments, defaults and `Data/` file names are the reference's, so the reference's driver scripts
+for this path (scripts/FindAlignmentCandidatesLowHash0.py, scripts/ComputeAlignments.py) run against this class unchanged:
+
+    a = Assembler()                       # largeDataFileNamePrefix="Data/", createNew=False
+    a.accessKmers(); a.accessMarkers()
+    a.findAlignmentCandidatesLowHash0(m=4, hashFraction=0.01, minHashIterationCount=10, alignmentCandidatesPerRead=20.,
+                                      minBucketSize=5, maxBucketSize=30, minFrequency=5)
+    a.accessAlignmentCandidates()
+    a.computeAlignments(alignOptions, threadCount=0)
+
+Files are read and written in the reference's `MemoryMapped::Vector` format (4 KiB header {headerSize, objectSize,
+objectCount, pageSize, pageCount, fileSize, capacity, magic 0xa3756fd4b5d8bcc1} + raw POD array, page rounded;
+src/MemoryMappedVector.hpp:165-231) and `VectorOfVectors` = `name.toc` + `name.data`
+(src/MemoryMappedVectorOfVectors.hpp:28-42), so the unmodified reference can continue from the outputs
+(tests/test_assembler_files.py opens them with the reference's own MemoryMapped code).
+
+All compute goes through the C ABI (libshasta_b200.so); errors surface as RuntimeError like pybind11's mapping of the
+reference's std::runtime_error.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+MAGIC = 0xa3756fd4b5d8bcc1
+HEADER_BYTES = 4096
+
+
+def mm_write_vector(path, array, object_size=None, page_size=4096):
+    """Write a MemoryMapped::Vector<T> file. `array` is any contiguous numpy array; object_size = sizeof(T)
+    (defaults to the array's itemsize)."""
+    a = np.ascontiguousarray(array)
+    raw = a.view(np.uint8).reshape(-1)
+    if object_size is None:
+        object_size = a.dtype.itemsize
+    assert raw.size % object_size == 0
+    n = raw.size // object_size
+    page_count = (HEADER_BYTES + raw.size - 1) // page_size + 1 if (HEADER_BYTES + raw.size) > 0 else 1
+    file_size = page_count * page_size
+    header = np.zeros(HEADER_BYTES // 8, np.uint64)
+    header[0] = HEADER_BYTES
+    header[1] = object_size
+    header[2] = n
+    header[3] = page_size
+    header[4] = page_count
+    header[5] = file_size
+    header[6] = (file_size - HEADER_BYTES) // object_size
+    header[7] = MAGIC
+    with open(path, "wb") as f:
+        f.write(header.tobytes())
+        f.write(raw.tobytes())
+        f.write(b"\0" * (file_size - HEADER_BYTES - raw.size))
+
+
+def mm_read_vector(path, dtype=np.uint8, object_size=None):
+    """Read a MemoryMapped::Vector<T> file; returns a numpy array of `dtype` (memory mapped, read only)."""
+    header = np.fromfile(path, dtype=np.uint64, count=8)
+    if len(header) < 8 or int(header[7]) != MAGIC or int(header[0]) != HEADER_BYTES:
+        raise RuntimeError(f"Error accessing {path}: not a MemoryMapped::Vector file.")
+    obj, n = int(header[1]), int(header[2])
+    if object_size is not None and obj != object_size:
+        raise RuntimeError(f"Unexpected object size {obj} in {path} (expected {object_size}).")
+    itemsize = np.dtype(dtype).itemsize
+    if (obj * n) % itemsize:
+        raise RuntimeError(f"Size of {path} is inconsistent with the requested element type.")
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.memmap(path, dtype=dtype, mode="r", offset=HEADER_BYTES, shape=(obj * n // itemsize,))
+
+
+def mm_write_vector_of_vectors(name, toc, data, data_object_size=None, toc_dtype=np.uint64, page_size=4096):
+    mm_write_vector(name + ".toc", np.asarray(toc, dtype=toc_dtype), page_size=page_size)
+    mm_write_vector(name + ".data", data, object_size=data_object_size, page_size=page_size)
+
+
+class AlignOptions:
+    """shasta.AlignOptions (src/PythonModule.cpp:85-107; defaults src/AssemblerOptions.cpp:380-489)."""
+
+    def __init__(self):
+        self.alignMethod = 3
+        self.maxSkip = 30
+        self.maxDrift = 30
+        self.maxTrim = 30
+        self.maxMarkerFrequency = 10
+        self.minAlignedMarkerCount = 100
+        self.minAlignedFraction = 0.
+        self.matchScore = 6
+        self.mismatchScore = -1
+        self.gapScore = -1
+        self.downsamplingFactor = 0.1
+        self.bandExtend = 10
+        self.maxBand = 1000
+        self.sameChannelReadAlignmentSuppressDeltaThreshold = 0
+        self.suppressContainments = False
+        self.align4DeltaX = 200
+        self.align4DeltaY = 10
+        self.align4MinEntryCountPerCell = 10
+        self.align4MaxDistanceFromBoundary = 100
+
+
+class OrientedReadPair:
+    """shasta.OrientedReadPair (src/PythonModule.cpp:42-45)."""
+
+    def __init__(self, r0, r1, same):
+        self.readIds = [int(r0), int(r1)]
+        self.isSameStrand = bool(same)
+
+
+class Assembler:
+    def __init__(self, largeDataFileNamePrefix="Data/", createNew=False, readRepresentation=1,
+                 largeDataPageSize=2 * 1024 * 1024, device=0):
+        self.prefix = largeDataFileNamePrefix
+        self.page_size = 4096          # files are written with 4 KiB pages (valid for any filesystem)
+        self.device = device
+        if createNew and self.prefix and os.path.dirname(self.prefix):
+            os.makedirs(os.path.dirname(self.prefix), exist_ok=True)
+        self._ctx = None
+        self.k = None
+        self._markers = None
+        self._candidates = None
+        self._alignment_data = None
+        self._compressed = None
+
+    # ------------------------------------------------------------------ helpers
+    def _name(self, n):
+        if not self.prefix:
+            raise RuntimeError("Anonymous memory mode is not supported by this facade: give a Data/ prefix.")
+        return self.prefix + n
+
+    def _context(self):
+        if self._ctx is None:
+            from . import capi
+            self._ctx = capi.Context(self.device)
+            self._markers_on_device = False
+        return self._ctx
+
+    def _upload_markers(self):
+        self.checkMarkersAreOpen()
+        ctx = self._context()
+        if not self._markers_on_device:
+            toc, data, flags = self._markers
+            ctx.set_markers(toc, data, flags)
+            self._markers_on_device = True
+        return ctx
+
+    # ------------------------------------------------------------------ access functions (reference names)
+    def accessKmers(self):
+        """Data/Kmers: Vector<KmerInfo>, 24 bytes each, 4^k entries (src/AssemblerKmers.cpp:15-21). Only k is needed here:
+        the method-3 downsampling hash is recomputed on the device."""
+        kmers = mm_read_vector(self._name("Kmers"), np.uint8, object_size=24)
+        count = len(kmers) // 24
+        k = (count.bit_length() - 1) // 2
+        if count != 1 << (2 * k):
+            raise RuntimeError("Size of k-mer vector is inconsistent with stored value of k.")
+        self.k = k
+
+    def checkKmersAreOpen(self):
+        if self.k is None:
+            raise RuntimeError("Kmers are not accessible.")
+
+    def accessMarkers(self):
+        toc = mm_read_vector(self._name("Markers.toc"), np.uint64, object_size=8)
+        data = mm_read_vector(self._name("Markers.data"), np.uint8, object_size=7)
+        flags = mm_read_vector(self._name("ReadFlags"), np.uint8, object_size=1)
+        if len(toc) != 2 * len(flags) + 1:
+            raise RuntimeError("Markers and ReadFlags are inconsistent.")
+        self._markers = (np.asarray(toc), np.asarray(data), np.asarray(flags))
+        self._markers_on_device = False
+
+    def checkMarkersAreOpen(self):
+        if self._markers is None:
+            raise RuntimeError("Markers are not accessible.")
+
+    def accessAlignmentCandidates(self):
+        c = mm_read_vector(self._name("AlignmentCandidates"), np.uint32, object_size=12)
+        self._candidates = np.asarray(c).reshape(-1, 3).copy()
+        self._candidates[:, 2] &= 0xff
+
+    def checkAlignmentCandidatesAreOpen(self):
+        if self._candidates is None:
+            raise RuntimeError("Alignment candidates are not accessible.")
+
+    def getAlignmentCandidates(self):
+        self.checkAlignmentCandidatesAreOpen()
+        return [OrientedReadPair(r0, r1, s) for r0, r1, s in self._candidates.tolist()]
+
+    def accessAlignmentData(self):
+        self._alignment_data = np.asarray(mm_read_vector(self._name("AlignmentData"), np.uint32, object_size=64)).reshape(-1, 16)
+
+    def accessCompressedAlignments(self):
+        toc = mm_read_vector(self._name("CompressedAlignments.toc"), np.uint64, object_size=8)
+        data = mm_read_vector(self._name("CompressedAlignments.data"), np.uint8, object_size=1)
+        self._compressed = (np.asarray(toc), np.asarray(data))
+
+    # ------------------------------------------------------------------ the two hot-path entry points
+    def findAlignmentCandidatesLowHash0(self, m, hashFraction, minHashIterationCount, alignmentCandidatesPerRead,
+                                        minBucketSize, maxBucketSize, minFrequency, log2MinHashBucketCount=0, threadCount=0):
+        """Assembler::findAlignmentCandidatesLowHash0 (src/AssemblerLowHash.cpp:10-55). Writes Data/AlignmentCandidates and
+        Data/ReadLowHashStatistics."""
+        from . import capi
+        self.checkKmersAreOpen()
+        ctx = self._upload_markers()
+        p = capi.make_lowhash_params(m=m, hashFraction=hashFraction, minHashIterationCount=minHashIterationCount,
+                                     alignmentCandidatesPerRead=alignmentCandidatesPerRead,
+                                     log2MinHashBucketCount=log2MinHashBucketCount, minBucketSize=minBucketSize,
+                                     maxBucketSize=maxBucketSize, minFrequency=minFrequency, threadCount=threadCount)
+        try:
+            cand, stats, _, res = ctx.lowhash0(p, want_stats=True)
+        except capi.ShastaB200Error as e:
+            raise RuntimeError(str(e)) from None
+        print(f"LowHash0 algorithm will use 2^{res.log2BucketCount} = {1 << res.log2BucketCount} buckets. ")
+        print(f"Found {len(cand)} alignment candidates.")
+        rows = 2 * len(self._markers[2])
+        print(f"Average number of alignment candidates per oriented read is {2. * len(cand) / max(rows, 1)}.")
+        self._candidates = cand
+        rec = cand.copy()          # 12-byte OrientedReadPair records: third word = isSameStrand byte + zero padding
+        mm_write_vector(self._name("AlignmentCandidates"), rec, object_size=12, page_size=self.page_size)
+        mm_write_vector(self._name("ReadLowHashStatistics"), stats, object_size=24, page_size=self.page_size)
+
+    def computeAlignments(self, alignOptions, threadCount=0):
+        """Assembler::computeAlignments (src/AssemblerAlign.cpp:208-304). Writes Data/AlignmentData,
+        Data/CompressedAlignments.{toc,data} and Data/AlignmentTable.{toc,data}."""
+        from . import capi
+        self.checkKmersAreOpen()
+        self.checkAlignmentCandidatesAreOpen()
+        ctx = self._upload_markers()
+        o = capi.make_align_options(
+            alignMethod=int(alignOptions.alignMethod), maxSkip=int(alignOptions.maxSkip), maxDrift=int(alignOptions.maxDrift),
+            maxTrim=int(alignOptions.maxTrim), maxMarkerFrequency=int(alignOptions.maxMarkerFrequency),
+            minAlignedMarkerCount=int(alignOptions.minAlignedMarkerCount), minAlignedFraction=float(alignOptions.minAlignedFraction),
+            matchScore=int(alignOptions.matchScore), mismatchScore=int(alignOptions.mismatchScore), gapScore=int(alignOptions.gapScore),
+            downsamplingFactor=float(alignOptions.downsamplingFactor), bandExtend=int(alignOptions.bandExtend),
+            maxBand=int(alignOptions.maxBand),
+            sameChannelReadAlignmentSuppressDeltaThreshold=int(alignOptions.sameChannelReadAlignmentSuppressDeltaThreshold),
+            suppressContainments=int(bool(alignOptions.suppressContainments)), align4DeltaX=int(alignOptions.align4DeltaX),
+            align4DeltaY=int(alignOptions.align4DeltaY), align4MinEntryCountPerCell=int(alignOptions.align4MinEntryCountPerCell),
+            align4MaxDistanceFromBoundary=int(alignOptions.align4MaxDistanceFromBoundary), k=int(self.k))
+        try:
+            rec, ctoc, cdata, res = capi.compute_alignments(ctx, self._candidates, o)
+            ttoc, tdata = capi.compute_alignment_table(ctx, rec, len(self._markers[2]))
+        except capi.ShastaB200Error as e:
+            raise RuntimeError(str(e)) from None
+        print(f"Found and stored {len(rec)} good alignments.")
+        self._alignment_data = rec
+        self._compressed = (ctoc, cdata)
+        mm_write_vector(self._name("AlignmentData"), rec, object_size=64, page_size=self.page_size)
+        mm_write_vector_of_vectors(self._name("CompressedAlignments"), ctoc, cdata, data_object_size=1, page_size=self.page_size)
+        mm_write_vector_of_vectors(self._name("AlignmentTable"), ttoc, tdata, data_object_size=4, toc_dtype=np.uint32,
+                                   page_size=self.page_size)
