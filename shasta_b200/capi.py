@@ -266,6 +266,21 @@ def synth_generate_device(ctx: Context, p, want_data7=True, read_begin=0, read_e
     return DeviceMarkers(toc, synth.read_flags(p), kptr.value, dptr.value if want_data7 else None)
 
 
+def _owned_array(ptr, count, dtype):
+    """numpy view (no copy) of a host buffer returned by the library; shb_free runs when the array is garbage collected."""
+    import weakref
+    dtype = np.dtype(dtype)
+    nbytes = int(count) * dtype.itemsize
+    if not ptr or nbytes == 0:
+        if ptr:
+            lib().shb_free(ptr)
+        return np.zeros(0, dtype)
+    address = ptr.value if isinstance(ptr, C.c_void_p) else int(ptr)
+    buf = (C.c_uint8 * nbytes).from_address(address)
+    weakref.finalize(buf, lib().shb_free, C.c_void_p(address))
+    return np.frombuffer(buf, dtype=dtype)
+
+
 def candidates_to_records(cand):
     """uint32[n,3] (readId0, readId1, isSameStrand) -> n 12-byte OrientedReadPair records (as uint32[n,3])."""
     c = np.ascontiguousarray(cand, dtype=np.uint32).reshape(-1, 3).copy()
@@ -285,12 +300,10 @@ def compute_alignments(ctx: Context, candidates, options: AlignOptions):
     _check(lib().shb_compute_alignments(ctx._h, _ptr(cand), len(cand), C.byref(options), C.byref(rec), C.byref(cnt),
                                         C.byref(toc), C.byref(data), C.byref(res)))
     n = cnt.value
-    records = np.ctypeslib.as_array(C.cast(rec, C.POINTER(C.c_uint32)), (n, 16)).copy() if n else np.zeros((0, 16), np.uint32)
-    tocn = np.ctypeslib.as_array(C.cast(toc, C.POINTER(C.c_uint64)), (n + 1,)).copy()
+    tocn = _owned_array(toc, n + 1, np.uint64)
     nb = int(tocn[-1])
-    datan = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), (nb,)).copy() if nb else np.zeros(0, np.uint8)
-    for p in (rec, toc, data):
-        lib().shb_free(p)
+    records = _owned_array(rec, 16 * n, np.uint32).reshape(n, 16)
+    datan = _owned_array(data, nb, np.uint8)
     return records, tocn, datan, res
 
 
