@@ -209,6 +209,34 @@ struct Batch {
 
 struct DpTotals { unsigned long long traceWords = 0; double ms = 0.; };
 
+// Device -> pageable host copy through two pinned staging buffers: the DMA of chunk k overlaps the host memcpy of
+// chunk k-1 (a plain cudaMemcpy into pageable memory serialises the two).
+void copyToHostPipelined(shb_context* c, void* dstHost, const void* srcDevice, uint64_t bytes)
+{
+    if(bytes == 0) return;
+    constexpr uint64_t kChunk = 32ull << 20;
+    if(!c->pinnedStage[0]) {
+        SHB_CUDA(cudaHostAlloc(&c->pinnedStage[0], kChunk, cudaHostAllocDefault));
+        SHB_CUDA(cudaHostAlloc(&c->pinnedStage[1], kChunk, cudaHostAllocDefault));
+        SHB_CUDA(cudaEventCreateWithFlags(&c->stageEvent[0], cudaEventDisableTiming));
+        SHB_CUDA(cudaEventCreateWithFlags(&c->stageEvent[1], cudaEventDisableTiming));
+    }
+    cudaStream_t st = c->stream;
+    const uint64_t chunks = (bytes + kChunk - 1) / kChunk;
+    for(uint64_t k = 0; k <= chunks; k++) {
+        if(k < chunks) {
+            const uint64_t off = k * kChunk, n = std::min(kChunk, bytes - off);
+            SHB_CUDA(cudaMemcpyAsync(c->pinnedStage[k & 1], static_cast<const uint8_t*>(srcDevice) + off, n, cudaMemcpyDeviceToHost, st));
+            SHB_CUDA(cudaEventRecord(c->stageEvent[k & 1], st));
+        }
+        if(k > 0) {
+            const uint64_t j = k - 1, off = j * kChunk, n = std::min(kChunk, bytes - off);
+            SHB_CUDA(cudaEventSynchronize(c->stageEvent[j & 1]));
+            memcpy(static_cast<uint8_t*>(dstHost) + off, c->pinnedStage[j & 1], n);
+        }
+    }
+}
+
 // Groups the runnable jobs by band class (longest first inside a class). Returns per-class counts; b.order holds the
 // job indices, class after class.
 void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs, std::vector<uint64_t>& classCounts)
@@ -503,9 +531,9 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     uint8_t* dataOut = (uint8_t*)malloc(outBytes ? outBytes : 1);
     SHB_REQUIRE(recOut && tocOut && dataOut, SHB_ERR_OOM, "Out of host memory for the alignments.");
     if(count) {
-        SHB_CUDA(cudaMemcpyAsync(recOut, outRecords.get(), 64 * count, cudaMemcpyDeviceToHost, st));
-        SHB_CUDA(cudaMemcpyAsync(tocOut, outToc.get(), 8 * count, cudaMemcpyDeviceToHost, st));
-        if(outBytes) SHB_CUDA(cudaMemcpyAsync(dataOut, outData.get(), outBytes, cudaMemcpyDeviceToHost, st));
+        copyToHostPipelined(c, recOut, outRecords.get(), 64 * count);
+        copyToHostPipelined(c, tocOut, outToc.get(), 8 * count);
+        copyToHostPipelined(c, dataOut, outData.get(), outBytes);
     }
     const unsigned long long skipped = readBack<unsigned long long>(skippedDev, st);
     tocOut[count] = outBytes;

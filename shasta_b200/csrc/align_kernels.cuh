@@ -97,7 +97,7 @@ constexpr int kDpMaxWarpsPerBlock = 4;
 __host__ __device__ inline uint32_t dpPaddedWidth(int32_t lo, int32_t hi) { return (uint32_t(hi - lo + 1) + 63u) & ~63u; }
 __host__ __device__ inline uint64_t dpTraceWords(uint32_t nx, int32_t lo, int32_t hi)
 {
-    return uint64_t(nx / 16 + 1) * dpPaddedWidth(lo, hi);
+    return (uint64_t(nx + 31u) / 16u + 2u) * dpPaddedWidth(lo, hi);      // rows of the by-step layout (+1 spare row)
 }
 
 // Warp-cooperative banded overlap DP. Band offset e = j - i + hi in [0, W). Lanes own e % 32.
@@ -202,24 +202,25 @@ __device__ inline void bandedOverlapDp(const uint32_t* __restrict__ a, uint32_t 
 // the end cell is selected with the order-independent formulation "maximum score, then smallest i, then smallest j".
 // Per-offset constants of a sub-chunk, fixed for the whole job. The cell of band offset e is inside the matrix for
 // columns first <= i <= min(nx, ny + hi - e), where first = max(0, hi - e); in column `first` it is a boundary cell
-// (i == 0 or j == 0, score 0). rowEnd = the column in which it reaches the last row j == ny when that column is inside
-// the matrix (else INT_MIN). cap = INT_MAX inside the band, "minus infinity" for the padding offsets e >= W, which
+// (i == 0 or j == 0, score 0). cap = INT_MAX inside the band, "minus infinity" for the padding offsets e >= W, which
 // must never carry a finite score (they would open a path around the band edge).
-template<int C> struct SubChunkLimits { int32_t first[C]; int32_t rowEnd[C]; int32_t cap[C]; };
+template<int C> struct SubChunkLimits { int32_t first[C]; int32_t cap[C]; };
 
-template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimits<C>& lim, int32_t e0, int32_t W, int32_t hi, int32_t nx, int32_t ny)
+template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimits<C>& lim, int32_t e0, int32_t W, int32_t hi)
 {
 #pragma unroll
     for(int c = 0; c < C; c++) {
         const int32_t e = e0 + c;
-        const bool inBand = e < W;
-        const int32_t first = max(0, hi - e);
-        const int32_t rowEnd = ny + hi - e;
-        lim.first[c] = inBand ? first : 0x7fffffff;
-        lim.rowEnd[c] = (inBand && rowEnd >= first && rowEnd <= nx) ? rowEnd : int32_t(0x80000000);
-        lim.cap[c] = inBand ? 0x7fffffff : kNegInf;
+        lim.first[c] = (e < W) ? max(0, hi - e) : 0x7fffffff;
+        lim.cap[c] = (e < W) ? 0x7fffffff : kNegInf;
     }
 }
+
+// Trace layout of the wavefront kernel: the codes are stored by STEP, not by column. Lane l works on column
+// i = t2 - l in step t2, and every lane stores the codes of its last 16 steps in the same step (t2 % 16 == 15), so the
+// stores are warp-uniform and fully coalesced: word (t2 >> 4) * Wpad + e holds, at bits 2*(t2 % 16), the code of cell
+// (t2 - e / (2C), e). The traceback re-aligns two such words into a by-column word with one funnel shift.
+__host__ __device__ inline uint64_t dpTraceRows(uint32_t nx) { return uint64_t(nx + 31u) / 16u + 1u; }
 
 // One sub-chunk (C consecutive band offsets starting at e0) of column i. Straight-line code for the common interior
 // cell; cells outside the matrix are NOT masked: above the matrix they only ever combine "minus infinity" values
@@ -228,16 +229,16 @@ template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimit
 template<int C> __device__ __forceinline__ void systolicSubChunk(
     int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t e0, int32_t i, uint32_t ai,
     int32_t below /* H(i, e0-1) */, int32_t top /* H(i-1, e0+C) */,
-    const uint32_t* __restrict__ b, int32_t jFirst /* e0 + i - hi */, int32_t nx, int32_t ny, uint32_t WpadJob, DpScores sc,
-    uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
+    const uint32_t* __restrict__ bp /* &b[jFirst - 1], jFirst = e0 + i - hi */, int32_t jFirst,
+    int32_t rowEndBase /* ny + hi - e0: the column in which offset e0 reaches the last row */,
+    int32_t nx, int32_t ny, DpScores sc, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
 {
     int32_t vertIn = below;
 #pragma unroll
     for(int c = 0; c < C; c++) {
-        // b[j-1], with the index clamped into the row so that the load is always legal (the value only matters for
-        // interior cells, whose index is in range).
-        const uint32_t bIndex = min(uint32_t(jFirst + c - 1), uint32_t(ny - 1));
-        const uint32_t bv = __ldg(b + bIndex);
+        // b[j-1]; the value only matters for interior cells, whose index is inside the row.
+        uint32_t bv = 0xffffffffu;
+        if(uint32_t(jFirst - 1 + c) < uint32_t(ny)) bv = __ldg(bp + c);
         const int32_t diag = H[c] + ((ai == bv) ? sc.match : sc.mismatch);      // H(i-1, e)
         const int32_t vert = vertIn + sc.gap;                                   // H(i, e-1)
         const int32_t horz = ((c + 1 < C) ? H[c + 1] : top) + sc.gap;           // H(i-1, e+1)
@@ -247,30 +248,29 @@ template<int C> __device__ __forceinline__ void systolicSubChunk(
         h = (i == lim.first[c]) ? 0 : h;
         H[c] = h;
         vertIn = h;
-        Tr[c] = (Tr[c] >> 2) | (code << 30);        // always holds the codes of the last 16 columns
-        if(i == lim.rowEnd[c]) {                     // last row, j == ny
-            if(h > bestScore || (h == bestScore && i < bestI)) { bestScore = h; bestI = i; bestJ = e0 + c + i; }
-        }
+        Tr[c] = (Tr[c] >> 2) | (code << 30);        // always holds the codes of the last 16 steps
     }
-    if(i == nx) {
-        // Last column: every in-matrix cell is an end-cell candidate (ties: smaller j, i.e. smaller offset, first).
+    // End-cell candidates (rare): the cell of this sub-chunk that sits on the last row j == ny in this column ...
+    const int32_t cStar = rowEndBase - i;           // its index inside the sub-chunk
+    if(uint32_t(cStar) < uint32_t(C) && uint32_t(i) <= uint32_t(nx)) {
 #pragma unroll
         for(int c = 0; c < C; c++) {
-            const int32_t e = e0 + c;
-            const int32_t hi = e0 + i - jFirst;
-            if(lim.cap[c] == 0x7fffffff && lim.first[c] <= nx && nx <= ny + hi - e) {
+            if(c == cStar && lim.cap[c] == 0x7fffffff && i >= lim.first[c]) {
                 const int32_t h = H[c];
-                const int32_t jPlusHi = e + i;
+                const int32_t jPlusHi = e0 + c + i;
                 if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && jPlusHi < bestJ)))) { bestScore = h; bestI = i; bestJ = jPlusHi; }
             }
         }
     }
-    if(((i & 15) == 15 || i == nx) && uint32_t(i) <= uint32_t(nx)) {
-        const uint32_t storeShift = 2u * (15u - uint32_t(i & 15));
-        uint32_t* traceRow = trace + uint64_t(uint32_t(i) >> 4) * WpadJob;
+    // ... and every in-matrix cell of the last column (ties: smaller j, i.e. smaller offset, first).
+    if(i == nx) {
 #pragma unroll
         for(int c = 0; c < C; c++) {
-            if(uint32_t(e0 + c) < WpadJob) traceRow[e0 + c] = Tr[c] >> storeShift;
+            if(lim.cap[c] == 0x7fffffff && lim.first[c] <= nx && c <= cStar) {        // c <= cStar  <=>  j <= ny
+                const int32_t h = H[c];
+                const int32_t jPlusHi = e0 + c + i;
+                if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && jPlusHi < bestJ)))) { bestScore = h; bestI = i; bestJ = jPlusHi; }
+            }
         }
     }
 }
@@ -289,23 +289,41 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     const int32_t eA = (2 * lane) * C, eB = (2 * lane + 1) * C;
 #pragma unroll
     for(int c = 0; c < C; c++) { HA[c] = kNegInf; HB[c] = kNegInf; TA[c] = 0; TB[c] = 0; }
-    initSubChunkLimits<C>(limA, eA, W, hi, nx, ny);
-    initSubChunkLimits<C>(limB, eB, W, hi, nx, ny);
+    initSubChunkLimits<C>(limA, eA, W, hi);
+    initSubChunkLimits<C>(limB, eB, W, hi);
     bestScore = kNegInf * 2; bestI = 0x7fffffff; bestJ = 0x7fffffff;
-    int32_t jA = eA - lane - hi, jB = eB - lane - hi;          // first row of each sub-chunk in column i = t2 - lane
-    for(int32_t t2 = 0; t2 <= nx + 31; t2++, jA++, jB++) {
+    // Column of this lane in step t2 is i = t2 - lane; first row of each sub-chunk in that column:
+    int32_t jA = eA - lane - hi, jB = eB - lane - hi;
+    const uint32_t* ap = a + (int64_t(-lane) - 1);          // &a[i - 1]
+    const uint32_t* bpA = b + (int64_t(jA) - 1);            // &b[jA - 1]
+    const uint32_t* bpB = b + (int64_t(jB) - 1);
+    const int32_t rowEndA = ny + hi - eA, rowEndB = ny + hi - eB;
+    const bool storesA = uint32_t(eA) < WpadJob, storesB = uint32_t(eB) < WpadJob;     // whole sub-chunks: WpadJob is a multiple of... see below
+    const int32_t tLast = nx + 31;
+    for(int32_t t2 = 0; t2 <= tLast; t2++, jA++, jB++, ap++, bpA++, bpB++) {
         const int32_t i = t2 - lane;
-        // a[i-1], index clamped into the row (the value is irrelevant for i <= 0 and i > nx).
-        const uint32_t ai = __ldg(a + min(uint32_t(i - 1), uint32_t(nx - 1)));
+        uint32_t ai = 0xfffffffeu;
+        if(uint32_t(i - 1) < uint32_t(nx)) ai = __ldg(ap);
         // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
         int32_t below = __shfl_up_sync(0xffffffffu, HB[C - 1], 1);
         if(lane == 0) below = kNegInf;
-        systolicSubChunk<C>(HA, TA, limA, eA, i, ai, below, HB[0], b, jA, nx, ny, WpadJob, sc, trace, bestScore, bestI, bestJ);
+        systolicSubChunk<C>(HA, TA, limA, eA, i, ai, below, HB[0], bpA, jA, rowEndA, nx, ny, sc, bestScore, bestI, bestJ);
         // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
         int32_t top = __shfl_down_sync(0xffffffffu, HA[0], 1);
         if(lane == 31) top = kNegInf;
-        systolicSubChunk<C>(HB, TB, limB, eB, i, ai, HA[C - 1], top, b, jB, nx, ny, WpadJob, sc, trace, bestScore, bestI, bestJ);
+        systolicSubChunk<C>(HB, TB, limB, eB, i, ai, HA[C - 1], top, bpB, jB, rowEndB, nx, ny, sc, bestScore, bestI, bestJ);
+        // Warp-uniform trace store of the last 16 steps.
+        if((t2 & 15) == 15 || t2 == tLast) {
+            const uint32_t shift = 2u * (15u - uint32_t(t2 & 15));
+            uint32_t* row = trace + uint64_t(uint32_t(t2) >> 4) * WpadJob;
+#pragma unroll
+            for(int c = 0; c < C; c++) {
+                if(uint32_t(eA + c) < WpadJob) row[eA + c] = TA[c] >> shift;
+                if(uint32_t(eB + c) < WpadJob) row[eB + c] = TB[c] >> shift;
+            }
+        }
     }
+    (void)storesA; (void)storesB;
     if(bestI != 0x7fffffff) bestJ -= hi;          // bestJ was tracked as j + hi
     // Warp reduction of the end cell: maximum score, then smallest i, then smallest j.
 #pragma unroll
@@ -323,17 +341,28 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
 // current path position for the current 16-column block (one coalesced 128-byte load per block, the next block
 // prefetched), so that a step costs a shuffle instead of a dependent global load. Records EVERY diagonal step
 // (x, y), last step first, into steps[]; returns how many. All control flow is warp-uniform.
+// pairWidth = 2C for traces written by the wavefront kernel (by-step layout, lane = e / pairWidth), 0 for the
+// by-column layout of the scan kernel.
 __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, int32_t lo, int32_t hi,
-                                            int32_t bestI, int32_t bestJ, uint2* __restrict__ steps)
+                                            int32_t bestI, int32_t bestJ, uint2* __restrict__ steps, int32_t pairWidth)
 {
     const int32_t lane = int32_t(threadIdx.x & 31u);
     const int32_t Wpad = int32_t(dpPaddedWidth(lo, hi));
     int32_t i = bestI, j = bestJ;
     uint32_t n = 0;
     if(i <= 0 || j <= 0) return 0;
+    // By-column word (codes of columns 16*block .. 16*block+15) of offset base + lane.
     auto loadWindow = [&](int32_t block, int32_t base) -> uint32_t {
         const int32_t e = base + lane;
-        return (block >= 0 && e >= 0 && e < Wpad) ? trace[uint64_t(uint32_t(block)) * uint32_t(Wpad) + uint32_t(e)] : 0u;
+        if(block < 0 || e < 0 || e >= Wpad) return 0u;
+        if(pairWidth == 0) return trace[uint64_t(uint32_t(block)) * uint32_t(Wpad) + uint32_t(e)];
+        const uint32_t skew = uint32_t(e / pairWidth);                      // the lane that computed this offset
+        const uint64_t row = uint64_t(uint32_t(block)) + (skew >> 4);
+        const uint32_t w0 = trace[row * uint32_t(Wpad) + uint32_t(e)];
+        const uint32_t sh = 2u * (skew & 15u);
+        if(sh == 0) return w0;
+        const uint32_t w1 = trace[(row + 1) * uint32_t(Wpad) + uint32_t(e)];
+        return __funnelshift_r(w0, w1, sh);
     };
     int32_t block = i >> 4;
     int32_t eb = (j - i + hi) - 16;
@@ -451,7 +480,7 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
     const uint32_t* ob = g.dsOrdinal + job.bOffset;
     // The stage-2 ordinal slots of this candidate (min(nx,ny) >= min(n0ds,n1ds)) double as scratch for the path.
     uint2* scratch = ordinals + jobs2[p].outOffset;
-    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, scratch);
+    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, scratch, 2 * C);
     int32_t offsetMin = INT32_MAX, offsetMax = INT32_MIN;
     for(uint32_t k = lane; k < steps; k += 32) {
         const uint2 s = scratch[k];
@@ -523,7 +552,7 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
     __syncwarp();
     __threadfence_block();
     uint2* out = ordinals + job.outOffset;
-    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, out);
+    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, out, 2 * C);
     const uint32_t count = filterEqualSteps(out, steps, a, b);
     if(lane == 0) counts[p] = count;
 }

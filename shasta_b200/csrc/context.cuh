@@ -59,6 +59,8 @@ struct shb_context {
 
     shb::DeviceBuffer<uint64_t> partKeys; shb::DeviceBuffer<uint32_t> partVals;
     void* lowhashState = nullptr;
+    void* pinnedStage[2] = {nullptr, nullptr};      // pinned staging for pipelined device->host result copies
+    cudaEvent_t stageEvent[2] = {nullptr, nullptr};
 
     // ---- alignment cache (downsampled markers; see align.cu) ------------------------------------
     void* alignCache = nullptr;
