@@ -171,8 +171,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-align", action="store_true", help="LowHash0 only (profiling aid)")
+    ap.add_argument("--align-method", type=int, default=3, choices=[3, 4],
+                    help="3 = what Nanopore-May2022.conf selects (default); 4 = Align4, --Align.alignMethod 4")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    ALIGN_MAY2022["alignMethod"] = args.align_method
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

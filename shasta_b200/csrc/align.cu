@@ -448,7 +448,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
             // Epilogue per job == per candidate.
             b.infoWords.reserve(13ull * nJobs);
-            SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 128), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
+            SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
                        (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.keep.get(), b.bytes32.get(), skippedDev);
             stage1Timed = true;
         } else {
@@ -479,7 +479,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
                 b.infoWords.reserve(13ull * nJobs); b.jobKeep.reserve(nJobs); b.jobBytes.reserve(nJobs);
                 // Align4's own filters (src/Align4.cpp:944-985), identical thresholds, no containment test.
-                SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 128), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
+                SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
                            (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.jobKeep.get(), b.jobBytes.get(),
                            (unsigned long long*)nullptr);
             } else {
@@ -513,7 +513,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             outRecords.reserve(16ull * (outCount + kept), true, st);
             outToc.reserve(outCount + kept + 1, true, st);
             outData.reserve(outBytes + bytes + 16, true, st);
-            SHB_LAUNCH(alignmentWriteKernel, ceilDiv(nb, 128), 128, 0, st, nb, (const uint32_t*)b.cand.get(), (const DpJob*)b.jobs.get(),
+            SHB_LAUNCH(alignmentWriteKernel, ceilDiv(nb, 4), 128, 0, st, nb, (const uint32_t*)b.cand.get(), (const DpJob*)b.jobs.get(),
                        (const uint2*)b.ordinals.get(), (const uint32_t*)b.counts.get(), (const uint32_t*)b.infoWords.get(), jobIndex,
                        (const uint32_t*)b.keep.get(), (const uint32_t*)b.keepIndex.get(), (const unsigned long long*)b.bytesOff.get(),
                        outCount, outBytes, outRecords.get(), outToc.get(), outData.get());

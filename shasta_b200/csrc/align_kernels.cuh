@@ -577,52 +577,82 @@ __device__ __forceinline__ uint32_t compressedStreakBytes(int32_t skip0, int32_t
     return 16;
 }
 
-// info words = the 13 words [3..15] of the 64-byte AlignmentData record.
-static __global__ void alignmentInfoKernel(uint32_t n, const DpJob* __restrict__ jobs, const uint2* __restrict__ ordinals,
-                                           const uint32_t* __restrict__ counts, FilterOptions f,
-                                           uint32_t* __restrict__ infoWords, uint32_t* __restrict__ keep,
-                                           uint32_t* __restrict__ compressedBytes, unsigned long long* __restrict__ skippedCounter)
+// Warp-cooperative walk over the streaks of an alignment (stored last-first). For chunk-of-32 position k the lane
+// gets: o = entry k, whether k is the TAIL of a streak (last pair of a run of consecutive diagonal steps), and for
+// tails the streak's first index. Used by both epilogue kernels.
+struct StreakLane { uint2 o, prev; bool valid, tail; uint32_t start; };
+
+__device__ __forceinline__ StreakLane streakChunk(const uint2* __restrict__ ord, uint32_t count, uint32_t base, uint32_t& carryStart)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t k = base + lane;
+    StreakLane r;
+    r.valid = k < count;
+    r.o = make_uint2(0, 0); r.prev = make_uint2(0, 0);
+    uint2 next = make_uint2(0, 0);
+    if(r.valid) {
+        r.o = ord[count - 1 - k];
+        if(k) r.prev = ord[count - k];
+        if(k + 1 < count) next = ord[count - 2 - k];
+    }
+    const bool head = r.valid && (k == 0 || r.o.x != r.prev.x + 1 || r.o.y != r.prev.y + 1);
+    r.tail = r.valid && (k + 1 == count || next.x != r.o.x + 1 || next.y != r.o.y + 1);
+    const unsigned headMask = __ballot_sync(0xffffffffu, head);
+    const unsigned below = headMask & (0xffffffffu >> (31u - lane));       // heads at lanes <= this one
+    r.start = below ? (base + 31u - uint32_t(__clz(below))) : carryStart;
+    if(headMask) carryStart = base + 31u - uint32_t(__clz(headMask));
+    return r;
+}
+
+// info words = the 13 words [3..15] of the 64-byte AlignmentData record. One WARP per job.
+static __global__ void __launch_bounds__(128)
+alignmentInfoKernel(uint32_t n, const DpJob* __restrict__ jobs, const uint2* __restrict__ ordinals,
+                    const uint32_t* __restrict__ counts, FilterOptions f,
+                    uint32_t* __restrict__ infoWords, uint32_t* __restrict__ keep,
+                    uint32_t* __restrict__ compressedBytes, unsigned long long* __restrict__ skippedCounter)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if(p >= n) return;
     const DpJob job = jobs[p];
-    keep[p] = 0;
-    compressedBytes[p] = 0;
-    if(job.state == kStateSkipped && skippedCounter) atomicAdd(skippedCounter, 1ull);
+    if(lane == 0) { keep[p] = 0; compressedBytes[p] = 0; }
+    if(job.state == kStateSkipped && skippedCounter && lane == 0) atomicAdd(skippedCounter, 1ull);
     if(job.state != kStateRun) return;
     const uint32_t count = counts[p];
     if(count == 0) return;                               // empty alignments are never stored
     const uint2* ord = ordinals + job.outOffset;
     int32_t mn = INT32_MAX, mx = INT32_MIN;
-    uint32_t maxSkip = 0, maxDrift = 0;
+    uint32_t maxSkip = 0, maxDrift = 0, bytes = 0;
     long long sum = 0;
-    uint32_t bytes = 0;
-    uint2 prev = make_uint2(0, 0);
-    uint2 streakStart = make_uint2(0, 0);
-    uint2 lastOfPreviousStreak = make_uint2(0, 0);
-    uint32_t streakLen = 0;
-    for(uint32_t k = 0; k < count; k++) {
-        const uint2 o = ord[count - 1 - k];
-        const int32_t off = int32_t(o.x) - int32_t(o.y);
-        mn = min(mn, off); mx = max(mx, off); sum += off;
-        if(k) {
-            maxSkip = max(maxSkip, uint32_t(abs(int32_t(o.x) - int32_t(prev.x))));
-            maxSkip = max(maxSkip, uint32_t(abs(int32_t(o.y) - int32_t(prev.y))));
-            maxDrift = max(maxDrift, uint32_t(abs(off - (int32_t(prev.x) - int32_t(prev.y)))));
-        }
-        if(k && o.x == prev.x + 1 && o.y == prev.y + 1) streakLen++;
-        else {
-            if(k) {
-                bytes += compressedStreakBytes(int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
-                                               int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
-                lastOfPreviousStreak = prev;
+    uint32_t carryStart = 0;
+    for(uint32_t base = 0; base < count; base += 32) {
+        const StreakLane s = streakChunk(ord, count, base, carryStart);
+        if(s.valid) {
+            const int32_t off = int32_t(s.o.x) - int32_t(s.o.y);
+            mn = min(mn, off); mx = max(mx, off); sum += off;
+            if(base + lane) {
+                maxSkip = max(maxSkip, uint32_t(abs(int32_t(s.o.x) - int32_t(s.prev.x))));
+                maxSkip = max(maxSkip, uint32_t(abs(int32_t(s.o.y) - int32_t(s.prev.y))));
+                maxDrift = max(maxDrift, uint32_t(abs(off - (int32_t(s.prev.x) - int32_t(s.prev.y)))));
             }
-            streakStart = o; streakLen = 1;
         }
-        prev = o;
+        if(s.tail) {
+            const uint2 first = ord[count - 1 - s.start];
+            const uint2 before = s.start ? ord[count - s.start] : make_uint2(0, 0);
+            bytes += compressedStreakBytes(int32_t(first.x) - int32_t(before.x), int32_t(first.y) - int32_t(before.y),
+                                           base + lane - s.start + 1);
+        }
     }
-    bytes += compressedStreakBytes(int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
-                                   int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        maxSkip = max(maxSkip, __shfl_xor_sync(0xffffffffu, maxSkip, d));
+        maxDrift = max(maxDrift, __shfl_xor_sync(0xffffffffu, maxDrift, d));
+        bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    }
+    if(lane != 0) return;
     const uint2 first = ord[count - 1], last = ord[0];
     // Filters, in the reference's order.
     if(uint64_t(count) < f.minAlignedMarkerCount) return;
@@ -671,46 +701,54 @@ __device__ __forceinline__ uint32_t writeCompressedStreak(uint8_t* out, int32_t 
     return bytes;
 }
 
-// One thread per kept candidate: 64-byte AlignmentData record + compressed alignment bytes.
+// One WARP per kept candidate: 64-byte AlignmentData record + compressed alignment bytes.
 // jobIndex maps a candidate to the DP job that produced its alignment (NULL = identity, method 3).
-static __global__ void alignmentWriteKernel(uint32_t n, const uint32_t* __restrict__ candidates, const DpJob* __restrict__ jobs,
-                                            const uint2* __restrict__ ordinals, const uint32_t* __restrict__ counts,
-                                            const uint32_t* __restrict__ infoWords, const uint32_t* __restrict__ jobIndex,
-                                            const uint32_t* __restrict__ keep,
-                                            const uint32_t* __restrict__ keepIndex, const unsigned long long* __restrict__ byteOffsets,
-                                            uint64_t recordBase, uint64_t byteBase,
-                                            uint32_t* __restrict__ records, unsigned long long* __restrict__ compressedToc,
-                                            uint8_t* __restrict__ compressedData)
+static __global__ void __launch_bounds__(128)
+alignmentWriteKernel(uint32_t n, const uint32_t* __restrict__ candidates, const DpJob* __restrict__ jobs,
+                     const uint2* __restrict__ ordinals, const uint32_t* __restrict__ counts,
+                     const uint32_t* __restrict__ infoWords, const uint32_t* __restrict__ jobIndex,
+                     const uint32_t* __restrict__ keep,
+                     const uint32_t* __restrict__ keepIndex, const unsigned long long* __restrict__ byteOffsets,
+                     uint64_t recordBase, uint64_t byteBase,
+                     uint32_t* __restrict__ records, unsigned long long* __restrict__ compressedToc,
+                     uint8_t* __restrict__ compressedData)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if(p >= n || !keep[p]) return;
     const uint32_t j = jobIndex ? jobIndex[p] : p;
     const uint64_t r = recordBase + keepIndex[p];
     uint32_t* rec = records + 16ull * r;
-    rec[0] = candidates[3ull * p]; rec[1] = candidates[3ull * p + 1]; rec[2] = candidates[3ull * p + 2] & 0xffu;
-    for(int i = 0; i < 13; i++) rec[3 + i] = infoWords[13ull * j + i];
+    if(lane < 3) rec[lane] = (lane == 2) ? (candidates[3ull * p + 2] & 0xffu) : candidates[3ull * p + lane];
+    else if(lane < 16) rec[lane] = infoWords[13ull * j + (lane - 3)];
     const uint64_t byteOffset = byteBase + byteOffsets[p];
-    compressedToc[r] = byteOffset;
+    if(lane == 0) compressedToc[r] = byteOffset;
     uint8_t* out = compressedData + byteOffset;
     const uint32_t count = counts[j];
     const uint2* ord = ordinals + jobs[j].outOffset;
-    uint2 prev = make_uint2(0, 0), streakStart = make_uint2(0, 0), lastOfPreviousStreak = make_uint2(0, 0);
-    uint32_t streakLen = 0, w = 0;
-    for(uint32_t k = 0; k < count; k++) {
-        const uint2 o = ord[count - 1 - k];
-        if(k && o.x == prev.x + 1 && o.y == prev.y + 1) streakLen++;
-        else {
-            if(k) {
-                w += writeCompressedStreak(out + w, int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
-                                           int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
-                lastOfPreviousStreak = prev;
-            }
-            streakStart = o; streakLen = 1;
+    uint32_t carryStart = 0, written = 0;
+    for(uint32_t base = 0; base < count; base += 32) {
+        const StreakLane s = streakChunk(ord, count, base, carryStart);
+        int32_t skip0 = 0, skip1 = 0;
+        uint32_t len = 0, bytes = 0;
+        if(s.tail) {
+            const uint2 first = ord[count - 1 - s.start];
+            const uint2 before = s.start ? ord[count - s.start] : make_uint2(0, 0);
+            skip0 = int32_t(first.x) - int32_t(before.x);
+            skip1 = int32_t(first.y) - int32_t(before.y);
+            len = base + lane - s.start + 1;
+            bytes = compressedStreakBytes(skip0, skip1, len);
         }
-        prev = o;
+        // Exclusive prefix of the streak sizes inside the chunk.
+        uint32_t inc = bytes;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if(lane >= (unsigned)d) inc += t;
+        }
+        if(s.tail) writeCompressedStreak(out + written + inc - bytes, skip0, skip1, len);
+        written += __shfl_sync(0xffffffffu, inc, 31);
     }
-    w += writeCompressedStreak(out + w, int32_t(streakStart.x) - int32_t(lastOfPreviousStreak.x),
-                               int32_t(streakStart.y) - int32_t(lastOfPreviousStreak.y), streakLen);
 }
 
 } // namespace shb
