@@ -81,6 +81,25 @@ template<class... Args> void launchBanded(const DpClass& k, uint32_t blocks, uin
     }
 }
 
+// Buffers shared by both methods for one batch of candidates.
+struct Batch {
+    DeviceBuffer<uint32_t> cand, counts, infoWords, jobKeep, jobBytes, keep, keepIndex, bytes32, selected, records;
+    DeviceBuffer<DpJob> jobs1, jobs;
+    DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, bytes64, bytesOff, scanWs64, ctoc;
+    DeviceBuffer<uint32_t> trace;
+    DeviceBuffer<uint2> ordinals;
+    DeviceBuffer<uint8_t> cdata;
+    // method 4
+    DeviceBuffer<unsigned long long> cellCnt, cellOff;
+    DeviceBuffer<uint32_t> gridCounts, gridAux, gridList, componentCount, jobOffsets;
+    DeviceBuffer<uint8_t> gridFlags;
+    DeviceBuffer<int32_t> gridBands;
+    // band-class ordering of the DP jobs
+    DeviceBuffer<uint32_t> classLimits, orderValsA, orderValsB;
+    DeviceBuffer<uint64_t> orderKeysA, orderKeysB;
+    const uint32_t* order = nullptr;
+};
+
 // Derived per-marker data cached in the context (per marker generation).
 struct AlignCache {
     // method 3: downsampled marker CSR
@@ -92,6 +111,12 @@ struct AlignCache {
     // method 4: markers sorted by k-mer id within each oriented read
     DeviceBuffer<uint32_t> sortedKmer, sortedOrdinal;
     uint64_t sortedGeneration = ~0ull;
+    // per-batch scratch and the device-side result accumulation: kept across calls so that a steady-state call does
+    // not allocate or free device memory
+    Batch batch;
+    DeviceBuffer<uint32_t> outRecords;
+    DeviceBuffer<unsigned long long> outToc;
+    DeviceBuffer<uint8_t> outData;
 };
 
 AlignCache& cache(shb_context* c)
@@ -188,26 +213,29 @@ void buildSortedMarkers(shb_context* c, uint32_t k)
     sc.sortedGeneration = c->markerGeneration;
 }
 
-// Buffers shared by both methods for one batch of candidates.
-struct Batch {
-    DeviceBuffer<uint32_t> cand, counts, infoWords, jobKeep, jobBytes, keep, keepIndex, bytes32, selected, records;
-    DeviceBuffer<DpJob> jobs1, jobs;
-    DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, bytes64, bytesOff, scanWs64, ctoc;
-    DeviceBuffer<uint32_t> trace;
-    DeviceBuffer<uint2> ordinals;
-    DeviceBuffer<uint8_t> cdata;
-    // method 4
-    DeviceBuffer<unsigned long long> cellCnt, cellOff;
-    DeviceBuffer<uint32_t> gridCounts, gridAux, gridList, componentCount, jobOffsets;
-    DeviceBuffer<uint8_t> gridFlags;
-    DeviceBuffer<int32_t> gridBands;
-    // band-class ordering of the DP jobs
-    DeviceBuffer<uint32_t> classLimits, orderValsA, orderValsB;
-    DeviceBuffer<uint64_t> orderKeysA, orderKeysB;
-    const uint32_t* order = nullptr;
-};
-
 struct DpTotals { unsigned long long traceWords = 0; double ms = 0.; };
+
+// Host-side phase timing, printed to stderr when SHB_TRACE is set (diagnostics only).
+struct PhaseClock {
+    bool on = getenv("SHB_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void lap(int phase, cudaStream_t st)
+    {
+        if(!on) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        acc[phase] += std::chrono::duration<double, std::milli>(now - t).count();
+        t = now;
+    }
+    void report(const char* const* names, int n) const
+    {
+        if(!on) return;
+        fprintf(stderr, "[shb] computeAlignments phases (ms):");
+        for(int i = 0; i < n; i++) fprintf(stderr, " %s=%.1f", names[i], acc[i]);
+        fprintf(stderr, "\n");
+    }
+};
 
 // Device -> pageable host copy through two pinned staging buffers: the DMA of chunk k overlaps the host memcpy of
 // chunk k-1 (a plain cudaMemcpy into pageable memory serialises the two).
@@ -366,22 +394,24 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
 
     const uint32_t batchMax = method4 ? 32768 : 131072;
     const uint64_t cellBudget = 192ull << 20;      // method 4: cells of scratch per batch
-    Batch b;
+    Batch& b = ac.batch;
     c->scanWs.reserve(scanWorkspaceElements(4ull * batchMax * 64));
     // scalars: 512 entries, allocated once at context creation
     unsigned long long* total64 = c->scalars.get() + 48;
     uint32_t* total32 = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
 
     // Kept alignments accumulate on the device and are copied to the host once at the end.
-    DeviceBuffer<uint32_t> outRecords;
-    DeviceBuffer<unsigned long long> outToc;
-    DeviceBuffer<uint8_t> outData;
+    DeviceBuffer<uint32_t>& outRecords = ac.outRecords;
+    DeviceBuffer<unsigned long long>& outToc = ac.outToc;
+    DeviceBuffer<uint8_t>& outData = ac.outData;
     uint64_t outCount = 0, outBytes = 0;
     unsigned long long* skippedDev = c->scalars.get() + 56;
     SHB_CUDA(cudaMemsetAsync(skippedDev, 0, sizeof(unsigned long long), st));
     uint64_t dpCells = 0;
     const std::vector<uint64_t>& toc = c->tocHost;
 
+    PhaseClock phases;
+    phases.lap(0, st);
     for(uint64_t begin = 0; begin < n; ) {
         // Batch size: bounded number of candidates and (method 4) of grid cells.
         uint32_t nb = 0;
@@ -444,8 +474,10 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 offset1 += count;
             }
             SHB_CUDA(cudaEventRecord(dpEv1.b, st));
+            phases.lap(1, st);
             SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());
             runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
+            phases.lap(2, st);
             // Epilogue per job == per candidate.
             b.infoWords.reserve(13ull * nJobs);
             SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
@@ -494,6 +526,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         dpCells += 16ull * totals.traceWords;
 
         // ---- compaction + output of the kept alignments ---------------------------------------------------
+        phases.lap(3, st);
         exclusiveScan<uint32_t>(b.keep.get(), b.keepIndex.get(), nb, total32, c->scanWs.get(), st);
         const uint32_t kept = readBack<uint32_t>(total32, st);
         SHB_LAUNCH(widenBytesKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.bytes32.get(), nb, b.bytes64.get());
@@ -520,6 +553,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             outCount += kept;
             outBytes += bytes;
         }
+        phases.lap(4, st);
         begin += nb;
     }
 
@@ -536,6 +570,11 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         copyToHostPipelined(c, dataOut, outData.get(), outBytes);
     }
     const unsigned long long skipped = readBack<unsigned long long>(skippedDev, st);
+    phases.lap(5, st);
+    {
+        static const char* const names[] = {"prepare", "setup+stage1", "stage2", "epilogue", "compact+write", "copy_to_host"};
+        phases.report(names, 6);
+    }
     tocOut[count] = outBytes;
     if(count == 0) tocOut[0] = 0;
     SHB_CUDA(cudaEventRecord(totalEv.b, st));
