@@ -76,13 +76,41 @@ struct SweepArgs {
     unsigned long long* counts;     // [iterationCount]
 };
 
+// x * 0xc6a4a7935bd1e995 (mod 2^64) as one wide multiply and two multiply-adds chained through the high word.
+__device__ __forceinline__ uint64_t mulM(uint64_t x)
+{
+    const uint32_t MLO = 0x5bd1e995u, MHI = 0xc6a4a793u;
+    const uint32_t lo = uint32_t(x), hi = uint32_t(x >> 32);
+    const uint64_t wide = uint64_t(lo) * MLO;
+    const uint32_t plo = uint32_t(wide);
+    uint32_t phi = uint32_t(wide >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(lo), "r"(MHI));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(hi), "r"(MLO));
+    return (uint64_t(phi) << 32) | plo;
+}
+
 __device__ __forceinline__ uint64_t murmurMix(uint64_t k)
 {
-    const uint64_t M = 0xc6a4a7935bd1e995ull;
-    k *= M;
+    k = mulM(k);
     k ^= k >> 47;
-    k *= M;
+    k = mulM(k);
     return k;
+}
+
+// MurmurHash64A of one feature for one seed, given the seed-independent mixed blocks and tail.
+template<int MM> __device__ __forceinline__ uint64_t murmurFinish(uint64_t h, const uint64_t* mixed, uint32_t blocks, bool hasTail, uint64_t tail)
+{
+    if(MM > 0) {
+#pragma unroll
+        for(int b = 0; b < MM / 2; b++) { h ^= mixed[b]; h = mulM(h); }
+    } else {
+        for(uint32_t b = 0; b < blocks; b++) { h ^= mixed[b]; h = mulM(h); }
+    }
+    if(hasTail) { h ^= tail; h = mulM(h); }
+    h ^= h >> 47;
+    h = mulM(h);
+    h ^= h >> 47;
+    return h;
 }
 
 // Which oriented read does marker position p belong to, and is the feature starting at p valid
@@ -117,6 +145,7 @@ lowhashSweepKernel(const SweepArgs a)
 
     const uint64_t M = 0xc6a4a7935bd1e995ull;
     const uint32_t m = (MM > 0) ? uint32_t(MM) : a.m;
+    static_assert(kMaxFusedIterations <= 32, "the per-position hit mask has 32 bits");
     const uint64_t tileBase = uint64_t(blockIdx.x) * kSweepTile;
 
     if(threadIdx.x < kMaxFusedIterations) seedCount[threadIdx.x] = 0;
@@ -155,34 +184,31 @@ lowhashSweepKernel(const SweepArgs a)
         const bool hasTail = (m & 1u) != 0;
         const uint64_t tail = hasTail ? uint64_t(sk[local + m - 1]) : 0ull;
 
-        uint64_t seedTerm = (uint64_t(a.iterationBegin) * 37ull);
+        // Hot loop: hash for every seed, remember WHICH seeds gave a low hash in a bit mask (no divergent work here).
+        uint32_t hitMask = 0;
+        const uint32_t seedBase = a.iterationBegin * 37u;              // iteration * 37 fits 32 bits
 #pragma unroll 2
-        for(uint32_t s = 0; s < K; s++, seedTerm += 37ull) {
-            uint64_t h = seedTerm ^ lenTimesM;
-            if(MM > 0) {
-#pragma unroll
-                for(int b = 0; b < MM / 2; b++) { h ^= mixed[b]; h *= M; }
+        for(uint32_t s = 0; s < K; s++) {
+            const uint64_t h = murmurFinish<MM>(uint64_t(seedBase + 37u * s) ^ lenTimesM, mixed, blocks, hasTail, tail);
+            hitMask |= (h < threshold) ? (1u << s) : 0u;
+        }
+        // Rare path (about hashFraction of the hashes): recompute the few low hashes and queue them.
+        while(hitMask) {
+            const uint32_t s = uint32_t(__ffs(int(hitMask))) - 1u;
+            hitMask &= hitMask - 1u;
+            const uint64_t h = murmurFinish<MM>(uint64_t(seedBase + 37u * s) ^ lenTimesM, mixed, blocks, hasTail, tail);
+            const uint32_t q = atomicAdd(&queueCount, 1u);
+            if(q < (uint32_t)kSweepQueue) {
+                queueHash[q] = h;
+                queueMeta[q] = uint32_t(local) | (s << 16);
             } else {
-                for(uint32_t b = 0; b < blocks; b++) { h ^= mixed[b]; h *= M; }
-            }
-            if(hasTail) { h ^= tail; h *= M; }
-            h ^= h >> 47;
-            h *= M;
-            h ^= h >> 47;
-            if(h < threshold) {
-                const uint32_t q = atomicAdd(&queueCount, 1u);
-                if(q < (uint32_t)kSweepQueue) {
-                    queueHash[q] = h;
-                    queueMeta[q] = uint32_t(local) | (s << 16);
-                } else {
-                    // Queue full (pathological hashFraction): do the rare path inline.
-                    const uint32_t o = resolveFeature(a, p, m);
-                    if(o != 0xffffffffu) {
-                        const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
-                        if(gi < a.capacity) {
-                            a.keys[uint64_t(s) * a.capacity + gi] = ((h & a.bucketMask) << 32) | (h >> 32);
-                            a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
-                        }
+                // Queue full (pathological hashFraction): do the rare path inline.
+                const uint32_t o = resolveFeature(a, p, m);
+                if(o != 0xffffffffu) {
+                    const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
+                    if(gi < a.capacity) {
+                        a.keys[uint64_t(s) * a.capacity + gi] = ((h & a.bucketMask) << 32) | (h >> 32);
+                        a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
                     }
                 }
             }
