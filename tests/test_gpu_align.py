@@ -140,3 +140,26 @@ def test_alignment_table(ctx):
     assert np.array_equal(np.bincount(table, minlength=len(rec)), np.full(len(rec), 4))
     toc0, table0 = capi.compute_alignment_table(ctx, rec[:0], 200)
     assert toc0.sum() == 0 and len(table0) == 0
+
+
+@pytest.mark.parametrize("band_extend,max_band", [(40, 1000), (90, 1000), (150, 1000), (230, 1000), (350, 2000), (480, 2000),
+                                                  (700, 3000), (1500, 6000)])
+def test_all_band_classes(ctx, band_extend, max_band):
+    # bandExtend widens the stage-2 band so that every kernel class is exercised: the register-resident wavefront kernel
+    # with C = 2, 3, 4, 6, 8, 12, 16 sub-chunk widths, and the shared-memory scan kernel for bands wider than 1024.
+    d, cand = _dataset(150, 10, 45)
+    _compare(ctx, d, cand[:250], alignMethod=3, k=10, maxSkip=30, maxDrift=30, maxTrim=30, minAlignedMarkerCount=50,
+             minAlignedFraction=0.3, downsamplingFactor=0.1, bandExtend=band_extend, maxBand=max_band)
+
+
+def test_long_reads_wide_stage1(ctx):
+    # Ultra-long-like reads: stage 1 runs on ~700 downsampled markers per read (band classes C = 12/16 and the scan kernel).
+    p = synth.SynthParams(reads=24, k=10, genome_markers=9000, n50_bases=90000, min_bases=60000, seed=3, sigma=0.2)
+    d = synth.generate(p)
+    lp = B.LowHashParams(m=4, hashFraction=0.01, minHashIterationCount=10, minBucketSize=2, maxBucketSize=30, minFrequency=2)
+    cand, _, _ = B.oracle_lowhash0(d["toc"], d["data"], d["flags"], lp)
+    assert len(cand) > 20
+    _compare(ctx, d, cand[:60], alignMethod=3, k=10, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
+             minAlignedFraction=0.1, downsamplingFactor=0.15, bandExtend=10, maxBand=1000)
+    _compare(ctx, d, cand[:60], alignMethod=4, k=10, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
+             minAlignedFraction=0.1, maxBand=1000)
