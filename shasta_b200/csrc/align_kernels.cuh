@@ -298,7 +298,6 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     const uint32_t* bpA = b + (int64_t(jA) - 1);            // &b[jA - 1]
     const uint32_t* bpB = b + (int64_t(jB) - 1);
     const int32_t rowEndA = ny + hi - eA, rowEndB = ny + hi - eB;
-    const bool storesA = uint32_t(eA) < WpadJob, storesB = uint32_t(eB) < WpadJob;     // whole sub-chunks: WpadJob is a multiple of... see below
     const int32_t tLast = nx + 31;
     for(int32_t t2 = 0; t2 <= tLast; t2++, jA++, jB++, ap++, bpA++, bpB++) {
         const int32_t i = t2 - lane;
@@ -323,7 +322,6 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
             }
         }
     }
-    (void)storesA; (void)storesB;
     if(bestI != 0x7fffffff) bestJ -= hi;          // bestJ was tracked as j + hi
     // Warp reduction of the end cell: maximum score, then smallest i, then smallest j.
 #pragma unroll
@@ -414,27 +412,6 @@ __device__ inline uint32_t filterEqualSteps(uint2* __restrict__ steps, uint32_t 
     return count;
 }
 
-// Traceback (executed redundantly by all lanes; loads are warp-uniform). F(x, y) is called for every
-// diagonal step, last step first.
-template<class F> __device__ inline void tracebackPath(const uint32_t* __restrict__ trace, int32_t lo, int32_t hi,
-                                                       int32_t bestI, int32_t bestJ, F&& onDiagonal)
-{
-    const uint32_t Wpad = dpPaddedWidth(lo, hi);
-    int32_t i = bestI, j = bestJ;
-    int64_t cachedIndex = -1;
-    uint32_t word = 0;
-    while(i > 0 && j > 0) {
-        const int32_t e = j - i + hi;
-        const int64_t index = int64_t(i >> 4) * Wpad + e;
-        if(index != cachedIndex) { word = trace[index]; cachedIndex = index; }
-        const uint32_t code = (word >> (2 * (i & 15))) & 3u;
-        if(code == 1u) { onDiagonal(uint32_t(i - 1), uint32_t(j - 1)); i--; j--; }
-        else if(code == 2u) j--;
-        else if(code == 3u) i--;
-        else break;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Method 3, stage 1 (src/AssemblerAlign3.cpp:62-239): unbanded DP on the downsampled markers,
 // then the band for stage 2. One warp per candidate.
@@ -446,7 +423,7 @@ struct Method3Args {
     const uint64_t* dsToc; const uint32_t* dsKmer; const uint32_t* dsOrdinal;
     DpScores scores;
     int32_t bandExtend, maxBand;
-    uint32_t wMin, wMax;            // only jobs with wMin < Wpad <= wMax are processed by this launch
+    uint32_t wMin, wMax;            // wMax = widest padded band of this launch's class (sizes the scan kernel's shared memory)
 };
 
 template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
