@@ -119,12 +119,61 @@ struct AlignCache {
     DeviceBuffer<uint32_t> outRecords;
     DeviceBuffer<unsigned long long> outToc;
     DeviceBuffer<uint8_t> outData;
+    // side streams: the band classes of one batch are independent launches (disjoint jobs and scratch), so the few
+    // long jobs of the wide classes run beside the big narrow-band launch instead of after it
+    static constexpr int kSideStreams = 3;
+    cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t forkEv = nullptr, joinEv[kSideStreams] = {nullptr, nullptr, nullptr};
+    ~AlignCache()
+    {
+        for(int i = 0; i < kSideStreams; i++) { if(side[i]) cudaStreamDestroy(side[i]); if(joinEv[i]) cudaEventDestroy(joinEv[i]); }
+        if(forkEv) cudaEventDestroy(forkEv);
+    }
 };
 
 AlignCache& cache(shb_context* c)
 {
     if(!c->alignCache) c->alignCache = new AlignCache();
     return *static_cast<AlignCache*>(c->alignCache);
+}
+
+// Runs launch(k, count, offset, stream) for every non-empty band class: the widest classes first, on the side
+// streams, the remaining (largest) launches on the main stream; the main stream continues after all of them.
+template<class F> void forEachClassConcurrently(shb_context* c, const std::vector<uint64_t>& classCounts, F launch)
+{
+    AlignCache& ac = cache(c);
+    cudaStream_t st = c->stream;
+    if(!ac.forkEv) {
+        SHB_CUDA(cudaEventCreateWithFlags(&ac.forkEv, cudaEventDisableTiming));
+        for(int i = 0; i < AlignCache::kSideStreams; i++) {
+            SHB_CUDA(cudaStreamCreateWithFlags(&ac.side[i], cudaStreamNonBlocking));
+            SHB_CUDA(cudaEventCreateWithFlags(&ac.joinEv[i], cudaEventDisableTiming));
+        }
+    }
+    std::vector<uint64_t> offsets(kClassCount, 0);
+    int nonEmpty = 0, firstNonEmpty = -1;
+    for(int k = 0; k < kClassCount; k++) {
+        if(k) offsets[k] = offsets[k-1] + classCounts[k-1];
+        if(classCounts[k]) { nonEmpty++; if(firstNonEmpty < 0) firstNonEmpty = k; }
+    }
+    if(nonEmpty == 0) return;
+    bool used[AlignCache::kSideStreams] = {false, false, false};
+    if(nonEmpty > 1) {
+        SHB_CUDA(cudaEventRecord(ac.forkEv, st));
+        int slot = 0;
+        for(int k = kClassCount - 1; k > firstNonEmpty; k--) {
+            if(!classCounts[k]) continue;
+            const int i = slot++ % AlignCache::kSideStreams;
+            if(!used[i]) { SHB_CUDA(cudaStreamWaitEvent(ac.side[i], ac.forkEv, 0)); used[i] = true; }
+            launch(k, uint32_t(classCounts[k]), offsets[k], ac.side[i]);
+        }
+    }
+    launch(firstNonEmpty, uint32_t(classCounts[firstNonEmpty]), offsets[firstNonEmpty], st);
+    for(int i = 0; i < AlignCache::kSideStreams; i++) {
+        if(!used[i]) continue;
+        SHB_CUDA(cudaEventRecord(ac.joinEv[i], ac.side[i]));
+        SHB_CUDA(cudaStreamWaitEvent(st, ac.joinEv[i], 0));
+    }
 }
 
 void buildDownsampled(shb_context* c, uint32_t k, double factor)
@@ -346,19 +395,15 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     BandedArgs g;
     g.kmerIds = sequences; g.scores = scores;
     SHB_CUDA(cudaEventRecord(ev.a, st));
-    uint64_t offset = 0;
     (void)maxWidth;
-    for(int k = 0; k < kClassCount; k++) {
-        const uint32_t count = uint32_t(classCounts[k]);
-        if(count) {
-            const uint32_t warps = warpsForClass(kClasses[k]);
-            const size_t smem = smemForClass(kClasses[k], warps);
-            g.n = count; g.order = b.order + offset; g.wMin = 0; g.wMax = kClasses[k].wMax;
-            launchBanded(kClasses[k], ceilDiv(count, warps), warps * 32, smem, st, g, (const DpJob*)b.jobs.get(), b.trace.get(),
-                         b.ordinals.get(), b.counts.get());
-        }
-        offset += count;
-    }
+    forEachClassConcurrently(c, classCounts, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
+        const uint32_t warps = warpsForClass(kClasses[k]);
+        const size_t smem = smemForClass(kClasses[k], warps);
+        BandedArgs gk = g;
+        gk.n = count; gk.order = b.order + offset; gk.wMin = 0; gk.wMax = kClasses[k].wMax;
+        launchBanded(kClasses[k], ceilDiv(count, warps), warps * 32, smem, s, gk, (const DpJob*)b.jobs.get(), b.trace.get(),
+                     b.ordinals.get(), b.counts.get());
+    });
     SHB_CUDA(cudaEventRecord(ev.b, st));
 }
 
@@ -490,17 +535,13 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             std::vector<uint64_t> classCounts1;
             buildClassOrder(c, b, b.jobs1.get(), nb, classCounts1);
             SHB_CUDA(cudaEventRecord(dpEv1.a, st));
-            uint64_t offset1 = 0;
-            for(int k = 0; k < kClassCount; k++) {
-                const uint32_t count = uint32_t(classCounts1[k]);
-                if(count) {
-                    const uint32_t warps = warpsForClass(kClasses[k]);
-                    const size_t smem = smemForClass(kClasses[k], warps);
-                    g1.n = count; g1.order = b.order + offset1; g1.wMin = 0; g1.wMax = kClasses[k].wMax;
-                    launchStage1(kClasses[k], ceilDiv(count, warps), warps * 32, smem, st, g1, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
-                }
-                offset1 += count;
-            }
+            forEachClassConcurrently(c, classCounts1, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
+                const uint32_t warps = warpsForClass(kClasses[k]);
+                const size_t smem = smemForClass(kClasses[k], warps);
+                Method3Args gk = g1;
+                gk.n = count; gk.order = b.order + offset; gk.wMin = 0; gk.wMax = kClasses[k].wMax;
+                launchStage1(kClasses[k], ceilDiv(count, warps), warps * 32, smem, s, gk, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
+            });
             SHB_CUDA(cudaEventRecord(dpEv1.b, st));
             phases.lap(1, st);
             SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());

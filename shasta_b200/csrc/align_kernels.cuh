@@ -225,13 +225,11 @@ __host__ __device__ inline uint64_t dpTraceRows(uint32_t nx) { return uint64_t(n
 // One sub-chunk (C consecutive band offsets starting at e0) of column i. Straight-line code for the common interior
 // cell; cells outside the matrix are NOT masked: above the matrix they only ever combine "minus infinity" values
 // (kNegInf plus a bounded drift), below the matrix their values are never read by an in-matrix cell, and their trace
-// codes are never visited by the traceback. bestJ is tracked as j + hi (fixed up by the caller).
+// codes are never visited by the traceback.
 template<int C> __device__ __forceinline__ void systolicSubChunk(
-    int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t e0, int32_t i, uint32_t ai,
+    int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t i, uint32_t ai,
     int32_t below /* H(i, e0-1) */, int32_t top /* H(i-1, e0+C) */,
-    const uint32_t* __restrict__ bp /* &b[jFirst - 1], jFirst = e0 + i - hi */, int32_t jFirst,
-    int32_t rowEndBase /* ny + hi - e0: the column in which offset e0 reaches the last row */,
-    int32_t nx, int32_t ny, DpScores sc, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
+    const uint32_t* __restrict__ bp /* &b[jFirst - 1], jFirst = e0 + i - hi */, int32_t jFirst, int32_t ny, DpScores sc)
 {
     int32_t vertIn = below;
 #pragma unroll
@@ -239,38 +237,35 @@ template<int C> __device__ __forceinline__ void systolicSubChunk(
         // b[j-1]; the value only matters for interior cells, whose index is inside the row.
         uint32_t bv = 0xffffffffu;
         if(uint32_t(jFirst - 1 + c) < uint32_t(ny)) bv = __ldg(bp + c);
-        const int32_t diag = H[c] + ((ai == bv) ? sc.match : sc.mismatch);      // H(i-1, e)
-        const int32_t vert = vertIn + sc.gap;                                   // H(i, e-1)
-        const int32_t horz = ((c + 1 < C) ? H[c + 1] : top) + sc.gap;           // H(i-1, e+1)
-        const int32_t dv = max(diag, vert);
-        int32_t h = min(max(dv, horz), lim.cap[c]);
-        const uint32_t code = (horz > dv) ? 3u : ((vert > diag) ? 2u : 1u);
+        const int32_t diag = H[c] + ((ai == bv) ? sc.match : sc.mismatch);      // from H(i-1, e)
+        const int32_t horzIn = (c + 1 < C) ? H[c + 1] : top;                    // H(i-1, e+1); vertIn = H(i, e-1)
+        // max(diag, vert, horz) with the tie order diag > vert > horz, as one max, one add-max and two compares.
+        const int32_t gapIn = max(vertIn, horzIn);
+        int32_t h = __viaddmax_s32(gapIn, sc.gap, diag);
+        const uint32_t code = (h > diag) ? ((horzIn > vertIn) ? 3u : 2u) : 1u;
+        h = min(h, lim.cap[c]);
         h = (i == lim.first[c]) ? 0 : h;
         H[c] = h;
         vertIn = h;
         Tr[c] = (Tr[c] >> 2) | (code << 30);        // always holds the codes of the last 16 steps
     }
-    // End-cell candidates (rare): the cell of this sub-chunk that sits on the last row j == ny in this column ...
-    const int32_t cStar = rowEndBase - i;           // its index inside the sub-chunk
-    if(uint32_t(cStar) < uint32_t(C) && uint32_t(i) <= uint32_t(nx)) {
+}
+
+// End-cell candidates of one sub-chunk in column i (rare: only the lanes whose offsets touch the last row or the
+// last column get here). bestJ is tracked as j + hi (fixed up by the caller).
+template<int C> __device__ __forceinline__ void systolicEndCells(
+    const int32_t (&H)[C], const SubChunkLimits<C>& lim, int32_t e0, int32_t i, int32_t cStar /* offset index on row ny */,
+    int32_t nx, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
+{
 #pragma unroll
-        for(int c = 0; c < C; c++) {
-            if(c == cStar && lim.cap[c] == 0x7fffffff && i >= lim.first[c]) {
-                const int32_t h = H[c];
-                const int32_t jPlusHi = e0 + c + i;
-                if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && jPlusHi < bestJ)))) { bestScore = h; bestI = i; bestJ = jPlusHi; }
-            }
-        }
-    }
-    // ... and every in-matrix cell of the last column (ties: smaller j, i.e. smaller offset, first).
-    if(i == nx) {
-#pragma unroll
-        for(int c = 0; c < C; c++) {
-            if(lim.cap[c] == 0x7fffffff && lim.first[c] <= nx && c <= cStar) {        // c <= cStar  <=>  j <= ny
-                const int32_t h = H[c];
-                const int32_t jPlusHi = e0 + c + i;
-                if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && jPlusHi < bestJ)))) { bestScore = h; bestI = i; bestJ = jPlusHi; }
-            }
+    for(int c = 0; c < C; c++) {
+        // the cell on the last row j == ny of this column, and every in-matrix cell (j <= ny) of the last column
+        const bool lastRow = (c == cStar);
+        const bool lastColumn = (i == nx) && (c <= cStar) && (lim.first[c] <= nx);
+        if((lastRow || lastColumn) && lim.cap[c] == 0x7fffffff && i >= lim.first[c]) {
+            const int32_t h = H[c];
+            const int32_t jPlusHi = e0 + c + i;
+            if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && jPlusHi < bestJ)))) { bestScore = h; bestI = i; bestJ = jPlusHi; }
         }
     }
 }
@@ -293,33 +288,42 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     initSubChunkLimits<C>(limB, eB, W, hi);
     bestScore = kNegInf * 2; bestI = 0x7fffffff; bestJ = 0x7fffffff;
     // Column of this lane in step t2 is i = t2 - lane; first row of each sub-chunk in that column:
+    int32_t i = -lane;
     int32_t jA = eA - lane - hi, jB = eB - lane - hi;
     const uint32_t* ap = a + (int64_t(-lane) - 1);          // &a[i - 1]
     const uint32_t* bpA = b + (int64_t(jA) - 1);            // &b[jA - 1]
     const uint32_t* bpB = b + (int64_t(jB) - 1);
-    const int32_t rowEndA = ny + hi - eA, rowEndB = ny + hi - eB;
-    const int32_t tLast = nx + 31;
-    for(int32_t t2 = 0; t2 <= tLast; t2++, jA++, jB++, ap++, bpA++, bpB++) {
-        const int32_t i = t2 - lane;
-        uint32_t ai = 0xfffffffeu;
-        if(uint32_t(i - 1) < uint32_t(nx)) ai = __ldg(ap);
-        // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
-        int32_t below = __shfl_up_sync(0xffffffffu, HB[C - 1], 1);
-        if(lane == 0) below = kNegInf;
-        systolicSubChunk<C>(HA, TA, limA, eA, i, ai, below, HB[0], bpA, jA, rowEndA, nx, ny, sc, bestScore, bestI, bestJ);
-        // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
-        int32_t top = __shfl_down_sync(0xffffffffu, HA[0], 1);
-        if(lane == 31) top = kNegInf;
-        systolicSubChunk<C>(HB, TB, limB, eB, i, ai, HA[C - 1], top, bpB, jB, rowEndB, nx, ny, sc, bestScore, bestI, bestJ);
-        // Warp-uniform trace store of the last 16 steps.
-        if((t2 & 15) == 15 || t2 == tLast) {
-            const uint32_t shift = 2u * (15u - uint32_t(t2 & 15));
-            uint32_t* row = trace + uint64_t(uint32_t(t2) >> 4) * WpadJob;
-#pragma unroll
-            for(int c = 0; c < C; c++) {
-                if(uint32_t(eA + c) < WpadJob) row[eA + c] = TA[c] >> shift;
-                if(uint32_t(eB + c) < WpadJob) row[eB + c] = TB[c] >> shift;
+    const int32_t rowEndA = ny + hi - eA;                   // the column in which offset eA reaches the last row
+    // Steps run in blocks of 16 (one trace word per offset and block); the last block may run past step nx + 31, where
+    // every lane is beyond the last column: those cells feed nothing and their trace codes are never read.
+    constexpr int kUnroll = (C == 1) ? 16 : (C == 2) ? 8 : (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
+    const int32_t blocks = (nx + 47) >> 4;
+    uint32_t* row = trace;
+    for(int32_t blk = 0; blk < blocks; blk++, row += WpadJob) {
+#pragma unroll kUnroll
+        for(int s = 0; s < 16; s++, i++, jA++, jB++, ap++, bpA++, bpB++) {
+            uint32_t ai = 0xfffffffeu;
+            if(uint32_t(i - 1) < uint32_t(nx)) ai = __ldg(ap);
+            // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
+            int32_t below = __shfl_up_sync(0xffffffffu, HB[C - 1], 1);
+            if(lane == 0) below = kNegInf;
+            systolicSubChunk<C>(HA, TA, limA, i, ai, below, HB[0], bpA, jA, ny, sc);
+            // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
+            int32_t top = __shfl_down_sync(0xffffffffu, HA[0], 1);
+            if(lane == 31) top = kNegInf;
+            systolicSubChunk<C>(HB, TB, limB, i, ai, HA[C - 1], top, bpB, jB, ny, sc);
+            // End-cell bookkeeping for both sub-chunks: offsets eA + cStar (row ny) and, in column nx, all rows.
+            const int32_t cStar = rowEndA - i;
+            if((uint32_t(cStar) < uint32_t(2 * C) || i == nx) && uint32_t(i) <= uint32_t(nx)) {
+                systolicEndCells<C>(HA, limA, eA, i, cStar, nx, bestScore, bestI, bestJ);
+                systolicEndCells<C>(HB, limB, eB, i, cStar - C, nx, bestScore, bestI, bestJ);
             }
+        }
+        // Warp-uniform, coalesced trace store of the block's 16 steps.
+#pragma unroll
+        for(int c = 0; c < C; c++) {
+            if(uint32_t(eA + c) < WpadJob) row[eA + c] = TA[c];
+            if(uint32_t(eB + c) < WpadJob) row[eB + c] = TB[c];
         }
     }
     if(bestI != 0x7fffffff) bestJ -= hi;          // bestJ was tracked as j + hi
