@@ -95,9 +95,24 @@ constexpr int32_t kNegInf = -(1 << 29);
 constexpr int kDpMaxWarpsPerBlock = 4;
 
 __host__ __device__ inline uint32_t dpPaddedWidth(int32_t lo, int32_t hi) { return (uint32_t(hi - lo + 1) + 63u) & ~63u; }
-__host__ __device__ inline uint64_t dpTraceWords(uint32_t nx, int32_t lo, int32_t hi)
+// Columns of the matrix that hold at least one in-band cell: max(0, lo) <= i <= min(nx, ny + hi). The wavefront kernel
+// only visits these (a band that enters through the top edge or leaves through the bottom edge skips the rest).
+constexpr uint32_t kDpWavefrontMaxWidth = 1024;
+__host__ __device__ inline int32_t dpFirstColumn(int32_t lo) { return lo > 0 ? lo : 0; }
+__host__ __device__ inline int32_t dpLastColumn(uint32_t nx, uint32_t ny, int32_t hi)
 {
-    return (uint64_t(nx + 31u) / 16u + 2u) * dpPaddedWidth(lo, hi);      // rows of the by-step layout (+1 spare row)
+    const int64_t bottom = int64_t(ny) + hi;
+    return int32_t(bottom < int64_t(nx) ? bottom : int64_t(nx));
+}
+__host__ __device__ inline uint64_t dpTraceWords(uint32_t nx, uint32_t ny, int32_t lo, int32_t hi)
+{
+    const uint32_t Wpad = dpPaddedWidth(lo, hi);
+    uint64_t columns = nx;                                              // scan kernel: by-column layout over all columns
+    if(Wpad <= kDpWavefrontMaxWidth) {
+        const int64_t active = int64_t(dpLastColumn(nx, ny, hi)) - dpFirstColumn(lo);
+        columns = uint64_t(active > 0 ? active : 0);
+    }
+    return ((columns + 31u) / 16u + 2u) * Wpad;                         // rows of the by-step layout (+1 spare row)
 }
 
 // Warp-cooperative banded overlap DP. Band offset e = j - i + hi in [0, W). Lanes own e % 32.
@@ -220,7 +235,6 @@ template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimit
 // i = t2 - l in step t2, and every lane stores the codes of its last 16 steps in the same step (t2 % 16 == 15), so the
 // stores are warp-uniform and fully coalesced: word (t2 >> 4) * Wpad + e holds, at bits 2*(t2 % 16), the code of cell
 // (t2 - e / (2C), e). The traceback re-aligns two such words into a by-column word with one funnel shift.
-__host__ __device__ inline uint64_t dpTraceRows(uint32_t nx) { return uint64_t(nx + 31u) / 16u + 1u; }
 
 // One sub-chunk (C consecutive band offsets starting at e0) of column i. Straight-line code for the common interior
 // cell; cells outside the matrix are NOT masked: above the matrix they only ever combine "minus infinity" values
@@ -287,17 +301,19 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     initSubChunkLimits<C>(limA, eA, W, hi);
     initSubChunkLimits<C>(limB, eB, W, hi);
     bestScore = kNegInf * 2; bestI = 0x7fffffff; bestJ = 0x7fffffff;
-    // Column of this lane in step t2 is i = t2 - lane; first row of each sub-chunk in that column:
-    int32_t i = -lane;
-    int32_t jA = eA - lane - hi, jB = eB - lane - hi;
-    const uint32_t* ap = a + (int64_t(-lane) - 1);          // &a[i - 1]
+    // Only the columns iFirst..iLast hold in-band cells. Column of this lane in step t2 is i = iFirst + t2 - lane;
+    // first row of each sub-chunk in that column:
+    const int32_t iFirst = dpFirstColumn(lo), iLast = dpLastColumn(nxU, nyU, hi);
+    int32_t i = iFirst - lane;
+    int32_t jA = eA + i - hi, jB = eB + i - hi;
+    const uint32_t* ap = a + (int64_t(i) - 1);              // &a[i - 1]
     const uint32_t* bpA = b + (int64_t(jA) - 1);            // &b[jA - 1]
     const uint32_t* bpB = b + (int64_t(jB) - 1);
     const int32_t rowEndA = ny + hi - eA;                   // the column in which offset eA reaches the last row
-    // Steps run in blocks of 16 (one trace word per offset and block); the last block may run past step nx + 31, where
-    // every lane is beyond the last column: those cells feed nothing and their trace codes are never read.
+    // Steps run in blocks of 16 (one trace word per offset and block); the last block may run past the step in which
+    // lane 31 reaches column iLast: the cells beyond it feed nothing and their trace codes are never read.
     constexpr int kUnroll = (C == 1) ? 16 : (C == 2) ? 8 : (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
-    const int32_t blocks = (nx + 47) >> 4;
+    const int32_t blocks = (iLast - iFirst + 47) >> 4;
     uint32_t* row = trace;
     for(int32_t blk = 0; blk < blocks; blk++, row += WpadJob) {
 #pragma unroll kUnroll
@@ -345,8 +361,9 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
 // (x, y), last step first, into steps[]; returns how many. All control flow is warp-uniform.
 // pairWidth = 2C for traces written by the wavefront kernel (by-step layout, lane = e / pairWidth), 0 for the
 // by-column layout of the scan kernel.
+// iFirst = the column of step 0 (by-step layout; 0 for the by-column layout).
 __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, int32_t lo, int32_t hi,
-                                            int32_t bestI, int32_t bestJ, uint2* __restrict__ steps, int32_t pairWidth)
+                                            int32_t bestI, int32_t bestJ, uint2* __restrict__ steps, int32_t pairWidth, int32_t iFirst)
 {
     const int32_t lane = int32_t(threadIdx.x & 31u);
     const int32_t Wpad = int32_t(dpPaddedWidth(lo, hi));
@@ -366,15 +383,15 @@ __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, 
         const uint32_t w1 = trace[(row + 1) * uint32_t(Wpad) + uint32_t(e)];
         return __funnelshift_r(w0, w1, sh);
     };
-    int32_t block = i >> 4;
+    int32_t block = (i - iFirst) >> 4;
     int32_t eb = (j - i + hi) - 16;
     uint32_t cur = loadWindow(block, eb);
     int32_t ebNext = eb;
     uint32_t nxt = loadWindow(block - 1, ebNext);
     while(i > 0 && j > 0) {
         const int32_t e = j - i + hi;
-        if((i >> 4) != block) {
-            block = i >> 4;
+        if(((i - iFirst) >> 4) != block) {
+            block = (i - iFirst) >> 4;
             if(e - ebNext >= 0 && e - ebNext < 32) { cur = nxt; eb = ebNext; }
             else { eb = e - 16; cur = loadWindow(block, eb); }
             ebNext = e - 16;
@@ -384,7 +401,7 @@ __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, 
             cur = loadWindow(block, eb);
         }
         const uint32_t word = __shfl_sync(0xffffffffu, cur, e - eb);
-        const uint32_t code = (word >> (2 * (i & 15))) & 3u;
+        const uint32_t code = (word >> (2 * ((i - iFirst) & 15))) & 3u;
         if(code == 1u) {
             if(lane == 0) steps[n] = make_uint2(uint32_t(i - 1), uint32_t(j - 1));
             n++; i--; j--;
@@ -461,7 +478,7 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
     const uint32_t* ob = g.dsOrdinal + job.bOffset;
     // The stage-2 ordinal slots of this candidate (min(nx,ny) >= min(n0ds,n1ds)) double as scratch for the path.
     uint2* scratch = ordinals + jobs2[p].outOffset;
-    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, scratch, 2 * C);
+    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, scratch, 2 * C, C > 0 ? dpFirstColumn(job.lo) : 0);
     int32_t offsetMin = INT32_MAX, offsetMax = INT32_MIN;
     for(uint32_t k = lane; k < steps; k += 32) {
         const uint2 s = scratch[k];
@@ -533,7 +550,7 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
     __syncwarp();
     __threadfence_block();
     uint2* out = ordinals + job.outOffset;
-    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, out, 2 * C);
+    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, out, 2 * C, C > 0 ? dpFirstColumn(job.lo) : 0);
     const uint32_t count = filterEqualSteps(out, steps, a, b);
     if(lane == 0) counts[p] = count;
 }
@@ -759,7 +776,7 @@ static __global__ void method3SetupKernel(const uint32_t* __restrict__ candidate
     j2.lo = 0; j2.hi = 0; j2.traceOffset = 0; j2.outOffset = 0; j2.pad = 0;
     j2.state = (j1.state == kStateRun) ? kStateSkipped : kStateEmpty;       // stage 1 overwrites it when it runs
     jobs1[p] = j1; jobs2[p] = j2;
-    traceWords1[p] = (j1.state == kStateRun) ? dpTraceWords(j1.nx, j1.lo, j1.hi) : 0ull;
+    traceWords1[p] = (j1.state == kStateRun) ? dpTraceWords(j1.nx, j1.ny, j1.lo, j1.hi) : 0ull;
     outCount[p] = min(j2.nx, j2.ny);
 }
 
@@ -785,7 +802,8 @@ static __global__ void dpClassKeysKernel(const DpJob* __restrict__ jobs, uint32_
         const uint32_t Wpad = dpPaddedWidth(j.lo, j.hi);
         for(uint32_t k = 0; k < classCount; k++) if(Wpad <= classLimits[k]) { cls = k; break; }
     }
-    keys[p] = (uint64_t(cls) << 32) | uint64_t(0xffffffffu - j.nx);
+    const int32_t active = dpLastColumn(j.nx, j.ny, j.hi) - dpFirstColumn(j.lo);       // columns the kernel visits
+    keys[p] = (uint64_t(cls) << 32) | uint64_t(0xffffffffu - uint32_t(active > 0 ? active : 0));
     vals[p] = p;
 }
 
@@ -800,7 +818,7 @@ static __global__ void stage2TraceWordsKernel(const DpJob* __restrict__ jobs, ui
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n) return;
     const DpJob j = jobs[p];
-    traceWords[p] = (j.state == kStateRun) ? dpTraceWords(j.nx, j.lo, j.hi) : 0ull;
+    traceWords[p] = (j.state == kStateRun) ? dpTraceWords(j.nx, j.ny, j.lo, j.hi) : 0ull;
 }
 
 static __global__ void widenBytesKernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* __restrict__ out)
@@ -1086,7 +1104,7 @@ static __global__ void align4MakeJobsKernel(const uint32_t* __restrict__ candida
         j.hi = min(bandMax, int32_t(j.nx));
         j.state = misses ? kStateEmpty : kStateRun;
         jobs[first + c] = j;
-        traceWords[first + c] = misses ? 0ull : dpTraceWords(j.nx, j.lo, j.hi);
+        traceWords[first + c] = misses ? 0ull : dpTraceWords(j.nx, j.ny, j.lo, j.hi);
         outCount[first + c] = min(j.nx, j.ny);
     }
 }
