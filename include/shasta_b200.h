@@ -41,8 +41,11 @@ const char* shb_last_error(void);
 shb_status shb_context_create(int device, shb_context** ctx);
 void shb_context_destroy(shb_context* ctx);
 
-/* Free a host buffer returned by this library. */
+/* Free a host buffer returned by this library. Large buffers (>= 8 MiB) are kept on a free list and handed out
+ * again by later calls (page-locked from their second use on, so that results arrive by direct DMA);
+ * shb_trim_host_cache returns the cached buffers to the operating system. */
 void shb_free(void* hostPtr);
+void shb_trim_host_cache(void);
 
 /* ------------------------------------------------------------------------------------------
  * Marker upload.  Replaces Assembler::accessMarkers (src/AssemblerMarkers.cpp, Data/Markers.*) +

@@ -83,6 +83,8 @@ def lib():
         L.shb_context_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.shb_context_destroy.argtypes = [C.c_void_p]
         L.shb_free.argtypes = [C.c_void_p]
+        L.shb_trim_host_cache.argtypes = []
+        L.shb_trim_host_cache.restype = None
         L.shb_set_markers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.shb_set_markers_device.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.shb_lowhash0.argtypes = [C.c_void_p, C.POINTER(LowHashParams), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
@@ -213,6 +215,11 @@ class Context:
         out = _records_to_array(cand, n.value)
         lib().shb_free(cand)
         return out, stats, res
+
+
+def trim_host_cache():
+    """Return the recycled host result buffers to the operating system (shb_trim_host_cache)."""
+    lib().shb_trim_host_cache()
 
 
 class DeviceMarkers:

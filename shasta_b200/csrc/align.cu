@@ -3,6 +3,7 @@
 // Method 4: Align4 front end (cells/components) -> one banded DP per component -> best -> epilogue.
 #include "context.cuh"
 #include "align_kernels.cuh"
+#include "hostpool.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -288,18 +289,6 @@ struct PhaseClock {
     }
 };
 
-// Large result buffers: 2 MiB aligned with transparent huge pages requested, so that the first-touch page faults of the
-// copy below do not dominate (a fresh 4 KiB-page buffer is filled at ~4 GB/s). Freed with free() / shb_free.
-void* allocHostResult(uint64_t bytes)
-{
-    if(bytes < (8ull << 20)) return malloc(bytes ? bytes : 1);
-    void* p = nullptr;
-    const uint64_t rounded = (bytes + (2ull << 20) - 1) & ~((2ull << 20) - 1);
-    if(posix_memalign(&p, 2ull << 20, rounded) != 0) return nullptr;
-    madvise(p, rounded, MADV_HUGEPAGE);
-    return p;
-}
-
 void parallelMemcpy(uint8_t* dst, const uint8_t* src, uint64_t n)
 {
     constexpr int kThreads = 4;
@@ -319,6 +308,10 @@ void parallelMemcpy(uint8_t* dst, const uint8_t* src, uint64_t n)
 void copyToHostPipelined(shb_context* c, void* dstHost, const void* srcDevice, uint64_t bytes)
 {
     if(bytes == 0) return;
+    if(HostPool::instance().isPageLocked(dstHost)) {        // recycled, page-locked result block: direct DMA
+        SHB_CUDA(cudaMemcpyAsync(dstHost, srcDevice, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return;
+    }
     constexpr uint64_t kChunk = 32ull << 20;
     if(!c->pinnedStage[0]) {
         SHB_CUDA(cudaHostAlloc(&c->pinnedStage[0], kChunk, cudaHostAllocDefault));
@@ -544,6 +537,21 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             });
             SHB_CUDA(cudaEventRecord(dpEv1.b, st));
             phases.lap(1, st);
+            if(phases.on && begin == 0) {        // SHB_TRACE: band-width and active-column statistics of the first batch
+                std::vector<DpJob> h(nb);
+                SHB_CUDA(cudaMemcpy(h.data(), b.jobs.get(), sizeof(DpJob) * nb, cudaMemcpyDeviceToHost));
+                uint64_t hist[12] = {0}, run = 0, cols = 0, fullCols = 0;
+                for(const DpJob& j : h) {
+                    if(j.state != kStateRun) continue;
+                    run++;
+                    const uint32_t w = uint32_t(j.hi - j.lo + 1);
+                    hist[std::min<uint32_t>(11, (w + 7) / 8)]++;
+                    cols += uint64_t(dpLastColumn(j.nx, j.ny, j.hi) - dpFirstColumn(j.lo)); fullCols += j.nx;
+                }
+                fprintf(stderr, "[shb] stage-2 jobs %llu of %u; band width histogram (bins of 8 offsets, last = wider):", (unsigned long long)run, nb);
+                for(int k = 0; k < 12; k++) fprintf(stderr, " %llu", (unsigned long long)hist[k]);
+                fprintf(stderr, "; active columns %.1f of %.1f per job\n", double(cols) / double(run ? run : 1), double(fullCols) / double(run ? run : 1));
+            }
             SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());
             runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
             phases.lap(2, st);
@@ -637,6 +645,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         copyToHostPipelined(c, recOut, outRecords.get(), 64 * count);
         copyToHostPipelined(c, tocOut, outToc.get(), 8 * count);
         copyToHostPipelined(c, dataOut, outData.get(), outBytes);
+        SHB_CUDA(cudaStreamSynchronize(st));
     }
     const unsigned long long skipped = readBack<unsigned long long>(skippedDev, st);
     phases.lap(5, st);

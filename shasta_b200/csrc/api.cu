@@ -1,6 +1,7 @@
 // C ABI (include/shasta_b200.h): argument checking, exception -> status translation, marker upload.
 #include "context.cuh"
 #include "lowhash_kernels.cuh"
+#include "hostpool.cuh"
 
 #include <cstring>
 #include <string>
@@ -112,7 +113,8 @@ void shb_context_destroy(shb_context* c)
     delete c;
 }
 
-void shb_free(void* p) { free(p); }
+void shb_free(void* p) { shb::HostPool::instance().release(p); }
+void shb_trim_host_cache(void) { shb::HostPool::instance().trim(); }
 
 shb_status shb_set_markers(shb_context* c, uint64_t readCountTotal, uint64_t readBegin, uint64_t readEnd,
                            const uint64_t* toc, const uint8_t* markerData7, const uint8_t* readFlags,

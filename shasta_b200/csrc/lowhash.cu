@@ -3,6 +3,7 @@
 // see DESIGN.md for the data layout and the per-kernel roofline.
 #include "context.cuh"
 #include "lowhash_kernels.cuh"
+#include "hostpool.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -320,7 +321,7 @@ void lowhashSetPairs(shb_context* c, const uint64_t* keys, const uint32_t* count
     S.acc.count = n;
 }
 
-// Final merge + emission, src/LowHash0.cpp:204-214. Returns a malloc'ed host buffer of 12-byte records.
+// Final merge + emission, src/LowHash0.cpp:204-214. Returns a host buffer (shb_free) of 12-byte records.
 void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountOut)
 {
     LowHashState& S = lowhashState(c);
@@ -329,7 +330,7 @@ void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountO
     cudaStream_t st = c->stream;
     mergeAccumulator(c, S.acc, S.readBits);
     const uint64_t nOut = countHighFrequency(c, S.acc, S.p.minFrequency, true);
-    void* host = malloc(nOut ? nOut * 12 : 1);
+    void* host = allocHostResult(nOut * 12);
     SHB_REQUIRE(host != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment candidates.");
     if(nOut) {
         c->candidatesDev.reserve(3 * nOut);
