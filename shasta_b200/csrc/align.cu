@@ -67,6 +67,20 @@ template<class... Args> void launchStage1(const DpClass& k, uint32_t blocks, uin
         SHB_LAUNCH(method3Stage1Kernel<0>, blocks, threads, smem, st, args...); break;
     }
 }
+// Stage 1 of method 3 for downsampled reads of at most 32*R markers (rows per lane R).
+const int kForwardRows[] = {2, 4, 6, 8, 12, 16};
+constexpr int kForwardClassCount = 6;        // row limits 64 .. 512 = kClasses[0..5].wMax
+template<class... Args> void launchStage1Forward(int rows, uint32_t blocks, uint32_t threads, cudaStream_t st, Args... args)
+{
+    switch(rows) {
+    case 2: SHB_LAUNCH(method3Stage1ForwardKernel<2>, blocks, threads, 0, st, args...); break;
+    case 4: SHB_LAUNCH(method3Stage1ForwardKernel<4>, blocks, threads, 0, st, args...); break;
+    case 6: SHB_LAUNCH(method3Stage1ForwardKernel<6>, blocks, threads, 0, st, args...); break;
+    case 8: SHB_LAUNCH(method3Stage1ForwardKernel<8>, blocks, threads, 0, st, args...); break;
+    case 12: SHB_LAUNCH(method3Stage1ForwardKernel<12>, blocks, threads, 0, st, args...); break;
+    default: SHB_LAUNCH(method3Stage1ForwardKernel<16>, blocks, threads, 0, st, args...); break;
+    }
+}
 template<class... Args> void launchBanded(const DpClass& k, uint32_t blocks, uint32_t threads, size_t smem, cudaStream_t st, Args... args)
 {
     switch(k.c) {
@@ -151,9 +165,10 @@ template<class F> void forEachClassConcurrently(shb_context* c, const std::vecto
             SHB_CUDA(cudaEventCreateWithFlags(&ac.joinEv[i], cudaEventDisableTiming));
         }
     }
-    std::vector<uint64_t> offsets(kClassCount, 0);
+    const int classCount = int(classCounts.size());
+    std::vector<uint64_t> offsets(classCounts.size(), 0);
     int nonEmpty = 0, firstNonEmpty = -1;
-    for(int k = 0; k < kClassCount; k++) {
+    for(int k = 0; k < classCount; k++) {
         if(k) offsets[k] = offsets[k-1] + classCounts[k-1];
         if(classCounts[k]) { nonEmpty++; if(firstNonEmpty < 0) firstNonEmpty = k; }
     }
@@ -162,7 +177,7 @@ template<class F> void forEachClassConcurrently(shb_context* c, const std::vecto
     if(nonEmpty > 1) {
         SHB_CUDA(cudaEventRecord(ac.forkEv, st));
         int slot = 0;
-        for(int k = kClassCount - 1; k > firstNonEmpty; k--) {
+        for(int k = classCount - 1; k > firstNonEmpty; k--) {
             if(!classCounts[k]) continue;
             const int i = slot++ % AlignCache::kSideStreams;
             if(!used[i]) { SHB_CUDA(cudaStreamWaitEvent(ac.side[i], ac.forkEv, 0)); used[i] = true; }
@@ -337,10 +352,11 @@ void copyToHostPipelined(shb_context* c, void* dstHost, const void* srcDevice, u
 
 // Groups the runnable jobs by band class (longest first inside a class). Returns per-class counts; b.order holds the
 // job indices, class after class.
-void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs, std::vector<uint64_t>& classCounts)
+void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs, std::vector<uint64_t>& classCounts,
+                     uint32_t forwardClasses = 0)
 {
     cudaStream_t st = c->stream;
-    classCounts.assign(kClassCount, 0);
+    classCounts.assign(kClassCount + forwardClasses, 0);
     if(nJobs == 0) return;
     if(!b.classLimits.get()) {
         b.classLimits.reserve(kClassCount);
@@ -351,7 +367,7 @@ void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs
     }
     b.orderKeysA.reserve(nJobs); b.orderKeysB.reserve(nJobs); b.orderValsA.reserve(nJobs); b.orderValsB.reserve(nJobs);
     SHB_LAUNCH(dpClassKeysKernel, ceilDiv(nJobs, 256), 256, 0, st, jobs, nJobs, (const uint32_t*)b.classLimits.get(), uint32_t(kClassCount),
-               b.orderKeysA.get(), b.orderValsA.get());
+               forwardClasses, b.orderKeysA.get(), b.orderValsA.get());
     const int ranges[1][2] = {{0, 40}};
     const bool inB = radixSort<true>(b.orderKeysA.get(), b.orderKeysB.get(), b.orderValsA.get(), b.orderValsB.get(), nJobs, ranges, 1, c->sortWs, st);
     b.order = inB ? b.orderValsB.get() : b.orderValsA.get();
@@ -362,7 +378,7 @@ void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs
     unsigned long long h[256];
     SHB_CUDA(cudaMemcpyAsync(h, dCounts, sizeof(h), cudaMemcpyDeviceToHost, st));
     SHB_CUDA(cudaStreamSynchronize(st));
-    for(int k = 0; k < kClassCount; k++) classCounts[k] = h[k];
+    for(size_t k = 0; k < classCounts.size(); k++) classCounts[k] = h[k];
 }
 
 // Scratch offsets + the banded DP + traceback for nJobs jobs whose lo/hi/state are set.
@@ -472,7 +488,8 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     DeviceBuffer<uint8_t>& outData = ac.outData;
     uint64_t outCount = 0, outBytes = 0;
     unsigned long long* skippedDev = c->scalars.get() + 56;
-    SHB_CUDA(cudaMemsetAsync(skippedDev, 0, sizeof(unsigned long long), st));
+    unsigned long long* forwardCellsDev = c->scalars.get() + 57;          // cells of the trace-free stage-1 jobs
+    SHB_CUDA(cudaMemsetAsync(skippedDev, 0, 2 * sizeof(unsigned long long), st));
     uint64_t dpCells = 0;
     const std::vector<uint64_t>& toc = c->tocHost;
 
@@ -508,7 +525,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             nJobs = nb;
             b.jobs1.reserve(nb); b.jobs.reserve(nb); b.tw.reserve(nb); b.twOff.reserve(nb); b.outCnt.reserve(nb);
             SHB_LAUNCH(method3SetupKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb,
-                       (const uint64_t*)c->toc.get(), (const uint64_t*)ac.dsToc.get(), b.jobs1.get(), b.jobs.get(), b.tw.get(), b.outCnt.get());
+                       (const uint64_t*)c->toc.get(), (const uint64_t*)ac.dsToc.get(), b.jobs1.get(), b.jobs.get(), b.tw.get(), b.outCnt.get(), forwardCellsDev);
             exclusiveScan<unsigned long long>(b.tw.get(), b.twOff.get(), nb, total64, b.scanWs64.get(), st);
             const unsigned long long traceWords1 = readBack<unsigned long long>(total64, st);
             b.trace.reserve(traceWords1 + 1);
@@ -526,14 +543,22 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             g1.toc = c->toc.get(); g1.dsToc = ac.dsToc.get(); g1.dsKmer = ac.dsKmer.get(); g1.dsOrdinal = ac.dsOrdinal.get();
             g1.scores = scores; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
             std::vector<uint64_t> classCounts1;
-            buildClassOrder(c, b, b.jobs1.get(), nb, classCounts1);
+            buildClassOrder(c, b, b.jobs1.get(), nb, classCounts1, kForwardClassCount);
             SHB_CUDA(cudaEventRecord(dpEv1.a, st));
             forEachClassConcurrently(c, classCounts1, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
-                const uint32_t warps = warpsForClass(kClasses[k]);
-                const size_t smem = smemForClass(kClasses[k], warps);
                 Method3Args gk = g1;
-                gk.n = count; gk.order = b.order + offset; gk.wMin = 0; gk.wMax = kClasses[k].wMax;
-                launchStage1(kClasses[k], ceilDiv(count, warps), warps * 32, smem, s, gk, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
+                gk.n = count; gk.order = b.order + offset; gk.wMin = 0;
+                if(k < kForwardClassCount) {
+                    gk.wMax = 0;
+                    launchStage1Forward(kForwardRows[k], ceilDiv(count, kDpMaxWarpsPerBlock), kDpMaxWarpsPerBlock * 32, s, gk,
+                                        (const DpJob*)b.jobs1.get(), b.jobs.get());
+                    return;
+                }
+                const DpClass& cls = kClasses[k - kForwardClassCount];      // too long for the forward kernel: DP with a trace
+                const uint32_t warps = warpsForClass(cls);
+                const size_t smem = smemForClass(cls, warps);
+                gk.wMax = cls.wMax;
+                launchStage1(cls, ceilDiv(count, warps), warps * 32, smem, s, gk, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
             });
             SHB_CUDA(cudaEventRecord(dpEv1.b, st));
             phases.lap(1, st);
@@ -648,6 +673,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         SHB_CUDA(cudaStreamSynchronize(st));
     }
     const unsigned long long skipped = readBack<unsigned long long>(skippedDev, st);
+    dpCells += readBack<unsigned long long>(forwardCellsDev, st);
     phases.lap(5, st);
     {
         static const char* const names[] = {"prepare", "setup+stage1", "stage2", "epilogue", "compact+write", "copy_to_host"};

@@ -512,6 +512,133 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
     }
 }
 
+// Method 3, stage 1 without a trace: the unbanded DP on the downsampled markers only has to deliver the smallest and
+// largest ordinal offset over the matching diagonal steps of the optimal path (src/AssemblerAlign3.cpp:193-239), so
+// every cell carries that pair along with its score and inherits it from the predecessor the recurrence picks: the
+// same information a traceback from that cell would collect, with no trace to write or walk.
+// Layout: lane l owns the R consecutive rows j = R*l + 1 .. R*l + R of b (its k-mers and ordinals stay in registers),
+// and in step t works on column i = t - l + 1; the only inter-lane traffic is lane l-1's last row (score and pair) of
+// the same column, one step earlier. Rows beyond ny and columns outside 1..nx are dead: nothing live reads them.
+// Covers ny <= 32*R (R <= 16); longer downsampled reads take method3Stage1Kernel. Same recurrence, tie-break and
+// end-cell rules as bandedOverlapDp.
+constexpr int32_t kNoDiagonalStep = 0x7fffffff;         // offsetMin of a path without diagonal steps
+constexpr int32_t kNoMatchingStep = 0x7ffffffe;         // ... with diagonal steps, none of them on equal k-mers
+constexpr uint32_t kStage1ForwardMaxRows = 512;
+
+template<int R> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
+method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob* __restrict__ jobs2)
+{
+    const int32_t lane = int32_t(threadIdx.x & 31u);
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if(slot >= g.n) return;
+    const uint32_t p = g.order[slot];
+    const DpJob job = jobs1[p];
+    if(job.state != kStateRun) return;
+    const uint32_t* __restrict__ a = g.dsKmer + job.aOffset;
+    const uint32_t* __restrict__ oa = g.dsOrdinal + job.aOffset;
+    const int32_t nx = int32_t(job.nx), ny = int32_t(job.ny);
+    const DpScores sc = g.scores;
+
+    // This lane's rows of b.
+    uint32_t bk[R]; int32_t bo[R];
+    int32_t H[R], Mn[R], Mx[R];                 // column i-1 (then i) of the own rows; column 0 is the boundary
+#pragma unroll
+    for(int r = 0; r < R; r++) {
+        const int32_t j = R * lane + r + 1;
+        bk[r] = 0xffffffffu; bo[r] = 0;
+        if(j <= ny) { bk[r] = __ldg(g.dsKmer + job.bOffset + (j - 1)); bo[r] = int32_t(__ldg(g.dsOrdinal + job.bOffset + (j - 1))); }
+        H[r] = 0; Mn[r] = kNoDiagonalStep; Mx[r] = INT32_MIN;
+    }
+    const int32_t lastLane = (ny - 1) / R, rLast = (ny - 1) % R;        // where row ny lives
+    int32_t upH = 0, upMn = kNoDiagonalStep, upMx = INT32_MIN;          // row R*lane of the previous column
+    int32_t bestScore = 0, bestI = 0x7fffffff, bestJ = 0x7fffffff, bestMn = kNoDiagonalStep, bestMx = INT32_MIN;
+
+    const int32_t steps = nx + lastLane;                                // lanes beyond lastLane only hold dead rows
+#pragma unroll 2
+    for(int32_t t = 0; t < steps; t++) {
+        // Row R*lane of the current column: lane-1's last row, computed one step ago (row 0 for lane 0).
+        int32_t inH = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
+        int32_t inMn = __shfl_up_sync(0xffffffffu, Mn[R - 1], 1);
+        int32_t inMx = __shfl_up_sync(0xffffffffu, Mx[R - 1], 1);
+        if(lane == 0) { inH = 0; inMn = kNoDiagonalStep; inMx = INT32_MIN; }
+        const int32_t i = t - lane + 1;
+        if(uint32_t(i - 1) < uint32_t(nx)) {
+            const uint32_t ai = __ldg(a + (i - 1));
+            const int32_t ao = int32_t(__ldg(oa + (i - 1)));
+            int32_t dH = upH, dMn = upMn, dMx = upMx;                   // (i-1, j-1)
+            int32_t vH = inH, vMn = inMn, vMx = inMx;                   // (i, j-1)
+#pragma unroll
+            for(int r = 0; r < R; r++) {
+                const int32_t hH = H[r], hMn = Mn[r], hMx = Mx[r];      // (i-1, j)
+                const bool eq = (ai == bk[r]);
+                const int32_t diag = dH + (eq ? sc.match : sc.mismatch);
+                const int32_t gapIn = max(vH, hH);
+                const int32_t h = __viaddmax_s32(gapIn, sc.gap, diag);  // diag > vert > horz on ties
+                const bool viaGap = h > diag, viaHorz = hH > vH;
+                const int32_t off = ao - bo[r];
+                const int32_t stepMn = min(dMn, eq ? off : kNoMatchingStep);
+                const int32_t stepMx = max(dMx, eq ? off : INT32_MIN);
+                const int32_t gapMn = viaHorz ? hMn : vMn, gapMx = viaHorz ? hMx : vMx;
+                const int32_t mn = viaGap ? gapMn : stepMn, mx = viaGap ? gapMx : stepMx;
+                dH = hH; dMn = hMn; dMx = hMx;
+                vH = h; vMn = mn; vMx = mx;
+                H[r] = h; Mn[r] = mn; Mx[r] = mx;
+            }
+            // End-cell candidates: row ny in every column, then every row of column nx (column-major order, first
+            // strict maximum; the boundary cells score 0 and come first, so only positive scores can win).
+            if(lane == lastLane) {
+                int32_t h = 0, mn = 0, mx = 0;
+                switch(rLast) {                  // warp-uniform; a jump instead of R selects per value
+#define SHB_PICK_ROW(k) case k: if constexpr(k < R) { h = H[k]; mn = Mn[k]; mx = Mx[k]; } break;
+                SHB_PICK_ROW(0) SHB_PICK_ROW(1) SHB_PICK_ROW(2) SHB_PICK_ROW(3) SHB_PICK_ROW(4) SHB_PICK_ROW(5) SHB_PICK_ROW(6) SHB_PICK_ROW(7)
+                SHB_PICK_ROW(8) SHB_PICK_ROW(9) SHB_PICK_ROW(10) SHB_PICK_ROW(11) SHB_PICK_ROW(12) SHB_PICK_ROW(13) SHB_PICK_ROW(14) SHB_PICK_ROW(15)
+#undef SHB_PICK_ROW
+                default: break;
+                }
+                if(h > bestScore) { bestScore = h; bestI = i; bestJ = ny; bestMn = mn; bestMx = mx; }
+            }
+            if(i == nx) {
+#pragma unroll
+                for(int r = 0; r < R; r++) {
+                    const int32_t j = R * lane + r + 1;
+                    if(j <= ny && H[r] > bestScore) { bestScore = H[r]; bestI = i; bestJ = j; bestMn = Mn[r]; bestMx = Mx[r]; }
+                }
+            }
+        }
+        upH = inH; upMn = inMn; upMx = inMx;
+    }
+    // Maximum score, then smallest i, then smallest j.
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1) {
+        const int32_t s2 = __shfl_xor_sync(0xffffffffu, bestScore, d);
+        const int32_t i2 = __shfl_xor_sync(0xffffffffu, bestI, d);
+        const int32_t j2 = __shfl_xor_sync(0xffffffffu, bestJ, d);
+        const int32_t mn2 = __shfl_xor_sync(0xffffffffu, bestMn, d);
+        const int32_t mx2 = __shfl_xor_sync(0xffffffffu, bestMx, d);
+        if(s2 > bestScore || (s2 == bestScore && (i2 < bestI || (i2 == bestI && j2 < bestJ)))) {
+            bestScore = s2; bestI = i2; bestJ = j2; bestMn = mn2; bestMx = mx2;
+        }
+    }
+    if(lane == 0) {
+        DpJob j2 = jobs2[p];
+        if(bestI == 0x7fffffff || bestMn == kNoDiagonalStep) j2.state = kStateEmpty;        // :185-191
+        else {
+            const int32_t offsetMin = (bestMn == kNoMatchingStep) ? INT32_MAX : bestMn, offsetMax = bestMx;
+            // 32-bit wrap-around like the compiled reference (:222-239)
+            const int32_t bandMin = int32_t(uint32_t(offsetMin) - uint32_t(g.bandExtend));
+            const int32_t bandMax = int32_t(uint32_t(offsetMax) + uint32_t(g.bandExtend));
+            if(int32_t(uint32_t(bandMax) - uint32_t(bandMin)) > g.maxBand) j2.state = kStateEmpty;
+            else if(bandMin > bandMax || bandMax < -int32_t(j2.ny) || bandMin > int32_t(j2.nx)) j2.state = kStateSkipped;  // SeqAn MinValue -> throw
+            else {
+                j2.lo = max(bandMin, -int32_t(j2.ny));
+                j2.hi = min(bandMax, int32_t(j2.nx));
+                j2.state = kStateRun;
+            }
+        }
+        jobs2[p] = j2;
+    }
+}
+
 // Stage 2 / generic banded alignment on full marker rows: DP, traceback, and the equal-kmer diagonal
 // steps written LAST STEP FIRST to ordinals[outOffset ...]; counts[p] receives how many.
 struct BandedArgs {
@@ -758,7 +885,8 @@ namespace shb {
 static __global__ void method3SetupKernel(const uint32_t* __restrict__ candidates, uint32_t n,
                                           const uint64_t* __restrict__ toc, const uint64_t* __restrict__ dsToc,
                                           DpJob* __restrict__ jobs1, DpJob* __restrict__ jobs2,
-                                          unsigned long long* __restrict__ traceWords1, unsigned long long* __restrict__ outCount)
+                                          unsigned long long* __restrict__ traceWords1, unsigned long long* __restrict__ outCount,
+                                          unsigned long long* __restrict__ forwardCells)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n) return;
@@ -776,7 +904,10 @@ static __global__ void method3SetupKernel(const uint32_t* __restrict__ candidate
     j2.lo = 0; j2.hi = 0; j2.traceOffset = 0; j2.outOffset = 0; j2.pad = 0;
     j2.state = (j1.state == kStateRun) ? kStateSkipped : kStateEmpty;       // stage 1 overwrites it when it runs
     jobs1[p] = j1; jobs2[p] = j2;
-    traceWords1[p] = (j1.state == kStateRun) ? dpTraceWords(j1.nx, j1.ny, j1.lo, j1.hi) : 0ull;
+    // Only the jobs that are too long for the forward kernel need a trace.
+    const bool forward = j1.ny <= kStage1ForwardMaxRows;
+    traceWords1[p] = (j1.state == kStateRun && !forward) ? dpTraceWords(j1.nx, j1.ny, j1.lo, j1.hi) : 0ull;
+    if(j1.state == kStateRun && forward) atomicAdd(forwardCells, (unsigned long long)j1.nx * j1.ny);
     outCount[p] = min(j2.nx, j2.ny);
 }
 
@@ -791,16 +922,22 @@ static __global__ void setTraceOffsetsKernel(DpJob* __restrict__ jobs, uint32_t 
 
 // Sort key of a DP job: band class in bits 32.., then longest sequence first (load balance inside a launch).
 // classLimits[k] = widest padded band of class k; jobs that do not run get class 255.
+// forwardClasses > 0 (method 3, stage 1): jobs of at most classLimits[forwardClasses-1] rows go to the forward kernel,
+// class k = first k with ny <= classLimits[k]; the others keep their band class, shifted up by forwardClasses.
 static __global__ void dpClassKeysKernel(const DpJob* __restrict__ jobs, uint32_t n, const uint32_t* __restrict__ classLimits,
-                                         uint32_t classCount, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+                                         uint32_t classCount, uint32_t forwardClasses, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n) return;
     const DpJob j = jobs[p];
     uint32_t cls = 255;
     if(j.state == kStateRun) {
-        const uint32_t Wpad = dpPaddedWidth(j.lo, j.hi);
-        for(uint32_t k = 0; k < classCount; k++) if(Wpad <= classLimits[k]) { cls = k; break; }
+        if(forwardClasses && j.ny <= classLimits[forwardClasses - 1]) {
+            for(uint32_t k = 0; k < forwardClasses; k++) if(j.ny <= classLimits[k]) { cls = k; break; }
+        } else {
+            const uint32_t Wpad = dpPaddedWidth(j.lo, j.hi);
+            for(uint32_t k = 0; k < classCount; k++) if(Wpad <= classLimits[k]) { cls = forwardClasses + k; break; }
+        }
     }
     const int32_t active = dpLastColumn(j.nx, j.ny, j.hi) - dpFirstColumn(j.lo);       // columns the kernel visits
     keys[p] = (uint64_t(cls) << 32) | uint64_t(0xffffffffu - uint32_t(active > 0 ? active : 0));
