@@ -239,26 +239,23 @@ template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimit
 // One sub-chunk (C consecutive band offsets starting at e0) of column i. Straight-line code for the common interior
 // cell; cells outside the matrix are NOT masked: above the matrix they only ever combine "minus infinity" values
 // (kNegInf plus a bounded drift), below the matrix their values are never read by an in-matrix cell, and their trace
-// codes are never visited by the traceback.
-template<int C> __device__ __forceinline__ void systolicSubChunk(
+// codes are never visited by the traceback. bw[] = b[j-1] for the C offsets (sentinel outside the row).
+// Boundary = false leaves out the test for the boundary cell (i == 0 or j == 0): for columns past max(0, hi).
+template<int C, bool Boundary> __device__ __forceinline__ void systolicSubChunk(
     int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t i, uint32_t ai,
-    int32_t below /* H(i, e0-1) */, int32_t top /* H(i-1, e0+C) */,
-    const uint32_t* __restrict__ bp /* &b[jFirst - 1], jFirst = e0 + i - hi */, int32_t jFirst, int32_t ny, DpScores sc)
+    int32_t below /* H(i, e0-1) */, int32_t top /* H(i-1, e0+C) */, const uint32_t* bw, DpScores sc)
 {
     int32_t vertIn = below;
 #pragma unroll
     for(int c = 0; c < C; c++) {
-        // b[j-1]; the value only matters for interior cells, whose index is inside the row.
-        uint32_t bv = 0xffffffffu;
-        if(uint32_t(jFirst - 1 + c) < uint32_t(ny)) bv = __ldg(bp + c);
-        const int32_t diag = H[c] + ((ai == bv) ? sc.match : sc.mismatch);      // from H(i-1, e)
+        const int32_t diag = H[c] + ((ai == bw[c]) ? sc.match : sc.mismatch);   // from H(i-1, e)
         const int32_t horzIn = (c + 1 < C) ? H[c + 1] : top;                    // H(i-1, e+1); vertIn = H(i, e-1)
         // max(diag, vert, horz) with the tie order diag > vert > horz, as one max, one add-max and two compares.
         const int32_t gapIn = max(vertIn, horzIn);
         int32_t h = __viaddmax_s32(gapIn, sc.gap, diag);
         const uint32_t code = (h > diag) ? ((horzIn > vertIn) ? 3u : 2u) : 1u;
         h = min(h, lim.cap[c]);
-        h = (i == lim.first[c]) ? 0 : h;
+        if(Boundary) h = (i == lim.first[c]) ? 0 : h;
         H[c] = h;
         vertIn = h;
         Tr[c] = (Tr[c] >> 2) | (code << 30);        // always holds the codes of the last 16 steps
@@ -284,6 +281,54 @@ template<int C> __device__ __forceinline__ void systolicEndCells(
     }
 }
 
+// State of one job's wavefront, all in registers.
+template<int C> struct SystolicState {
+    int32_t HA[C], HB[C];
+    uint32_t TA[C], TB[C];
+    SubChunkLimits<C> limA, limB;
+    uint32_t bw[2 * C];             // b[j-1] of the lane's 2C offsets in the current column (sliding window)
+    int32_t i;                      // column of this lane in the current step
+    const uint32_t* ap;             // &a[i - 1]
+    const uint32_t* bNext;          // &b[jA - 1 + 2C]: the element that enters the window in the next step
+    int32_t jNext;                  // its index (jA - 1 + 2C), for the range test
+    int32_t bestScore, bestI, bestJ;
+};
+
+// 16 steps. Checked = false: no boundary cell and no end cell can occur in these steps for any lane.
+template<int C, bool Checked> __device__ __forceinline__ void systolicBlock(
+    SystolicState<C>& s, int32_t lane, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc)
+{
+    constexpr int kUnroll = (C == 1) ? 16 : (C == 2) ? 8 : (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
+#pragma unroll kUnroll
+    for(int step = 0; step < 16; step++) {
+        uint32_t ai = 0xfffffffeu;
+        if(uint32_t(s.i - 1) < uint32_t(nx)) ai = __ldg(s.ap);
+        uint32_t bIn = 0xffffffffu;                     // enters the window after this step
+        if(uint32_t(s.jNext) < uint32_t(ny)) bIn = __ldg(s.bNext);
+        // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
+        int32_t below = __shfl_up_sync(0xffffffffu, s.HB[C - 1], 1);
+        if(lane == 0) below = kNegInf;
+        systolicSubChunk<C, Checked>(s.HA, s.TA, s.limA, s.i, ai, below, s.HB[0], s.bw, sc);
+        // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
+        int32_t top = __shfl_down_sync(0xffffffffu, s.HA[0], 1);
+        if(lane == 31) top = kNegInf;
+        systolicSubChunk<C, Checked>(s.HB, s.TB, s.limB, s.i, ai, s.HA[C - 1], top, s.bw + C, sc);
+        if(Checked) {
+            // End-cell bookkeeping for both sub-chunks: offsets eA + cStar (row ny) and, in column nx, all rows.
+            const int32_t cStar = rowEndA - s.i;
+            if((uint32_t(cStar) < uint32_t(2 * C) || s.i == nx) && uint32_t(s.i) <= uint32_t(nx)) {
+                systolicEndCells<C>(s.HA, s.limA, eA, s.i, cStar, nx, s.bestScore, s.bestI, s.bestJ);
+                systolicEndCells<C>(s.HB, s.limB, eB, s.i, cStar - C, nx, s.bestScore, s.bestI, s.bestJ);
+            }
+        }
+        // Next column: every offset moves one row down.
+#pragma unroll
+        for(int k = 0; k + 1 < 2 * C; k++) s.bw[k] = s.bw[k + 1];
+        s.bw[2 * C - 1] = bIn;
+        s.i++; s.ap++; s.bNext++; s.jNext++;
+    }
+}
+
 template<int C> __device__ inline void bandedOverlapDpSystolic(
     const uint32_t* __restrict__ a, uint32_t nxU, const uint32_t* __restrict__ b, uint32_t nyU, int32_t lo, int32_t hi, DpScores sc,
     uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
@@ -292,56 +337,49 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     const int32_t nx = int32_t(nxU), ny = int32_t(nyU);
     const int32_t W = hi - lo + 1;
     const uint32_t WpadJob = dpPaddedWidth(lo, hi);
-    int32_t HA[C], HB[C];
-    uint32_t TA[C], TB[C];
-    SubChunkLimits<C> limA, limB;
+    SystolicState<C> s;
     const int32_t eA = (2 * lane) * C, eB = (2 * lane + 1) * C;
 #pragma unroll
-    for(int c = 0; c < C; c++) { HA[c] = kNegInf; HB[c] = kNegInf; TA[c] = 0; TB[c] = 0; }
-    initSubChunkLimits<C>(limA, eA, W, hi);
-    initSubChunkLimits<C>(limB, eB, W, hi);
-    bestScore = kNegInf * 2; bestI = 0x7fffffff; bestJ = 0x7fffffff;
+    for(int c = 0; c < C; c++) { s.HA[c] = kNegInf; s.HB[c] = kNegInf; s.TA[c] = 0; s.TB[c] = 0; }
+    initSubChunkLimits<C>(s.limA, eA, W, hi);
+    initSubChunkLimits<C>(s.limB, eB, W, hi);
+    s.bestScore = kNegInf * 2; s.bestI = 0x7fffffff; s.bestJ = 0x7fffffff;
     // Only the columns iFirst..iLast hold in-band cells. Column of this lane in step t2 is i = iFirst + t2 - lane;
-    // first row of each sub-chunk in that column:
+    // the row of its first offset in that column is jA = eA + i - hi.
     const int32_t iFirst = dpFirstColumn(lo), iLast = dpLastColumn(nxU, nyU, hi);
-    int32_t i = iFirst - lane;
-    int32_t jA = eA + i - hi, jB = eB + i - hi;
-    const uint32_t* ap = a + (int64_t(i) - 1);              // &a[i - 1]
-    const uint32_t* bpA = b + (int64_t(jA) - 1);            // &b[jA - 1]
-    const uint32_t* bpB = b + (int64_t(jB) - 1);
+    s.i = iFirst - lane;
+    const int32_t jA = eA + s.i - hi;
+    s.ap = a + (int64_t(s.i) - 1);
+#pragma unroll
+    for(int k = 0; k < 2 * C; k++) {
+        const int32_t idx = jA - 1 + k;
+        s.bw[k] = 0xffffffffu;
+        if(uint32_t(idx) < uint32_t(ny)) s.bw[k] = __ldg(b + idx);
+    }
+    s.jNext = jA - 1 + 2 * C;
+    s.bNext = b + int64_t(s.jNext);
     const int32_t rowEndA = ny + hi - eA;                   // the column in which offset eA reaches the last row
     // Steps run in blocks of 16 (one trace word per offset and block); the last block may run past the step in which
     // lane 31 reaches column iLast: the cells beyond it feed nothing and their trace codes are never read.
-    constexpr int kUnroll = (C == 1) ? 16 : (C == 2) ? 8 : (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
     const int32_t blocks = (iLast - iFirst + 47) >> 4;
+    // Boundary cells only occur in columns <= max(0, hi), which lane 31 leaves after step max(0, hi) - iFirst + 31.
+    // End cells (row ny, column nx) first occur in step min(nx - iFirst, ny + hi - iFirst - 64C + 32): lane 0 reaching
+    // column nx, or lane 31's last offset reaching row ny. The blocks in between run without either test.
+    const int32_t headBlocks = ((max(0, hi) - iFirst + 31) >> 4) + 1;
+    const int32_t firstEndStep = min(nx - iFirst, ny + hi - iFirst - 64 * C + 32);
+    const int32_t tailBlock = max(0, firstEndStep) >> 4;
     uint32_t* row = trace;
     for(int32_t blk = 0; blk < blocks; blk++, row += WpadJob) {
-#pragma unroll kUnroll
-        for(int s = 0; s < 16; s++, i++, jA++, jB++, ap++, bpA++, bpB++) {
-            uint32_t ai = 0xfffffffeu;
-            if(uint32_t(i - 1) < uint32_t(nx)) ai = __ldg(ap);
-            // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
-            int32_t below = __shfl_up_sync(0xffffffffu, HB[C - 1], 1);
-            if(lane == 0) below = kNegInf;
-            systolicSubChunk<C>(HA, TA, limA, i, ai, below, HB[0], bpA, jA, ny, sc);
-            // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
-            int32_t top = __shfl_down_sync(0xffffffffu, HA[0], 1);
-            if(lane == 31) top = kNegInf;
-            systolicSubChunk<C>(HB, TB, limB, i, ai, HA[C - 1], top, bpB, jB, ny, sc);
-            // End-cell bookkeeping for both sub-chunks: offsets eA + cStar (row ny) and, in column nx, all rows.
-            const int32_t cStar = rowEndA - i;
-            if((uint32_t(cStar) < uint32_t(2 * C) || i == nx) && uint32_t(i) <= uint32_t(nx)) {
-                systolicEndCells<C>(HA, limA, eA, i, cStar, nx, bestScore, bestI, bestJ);
-                systolicEndCells<C>(HB, limB, eB, i, cStar - C, nx, bestScore, bestI, bestJ);
-            }
-        }
+        if(blk < headBlocks || blk >= tailBlock) systolicBlock<C, true>(s, lane, eA, eB, rowEndA, nx, ny, sc);
+        else systolicBlock<C, false>(s, lane, eA, eB, rowEndA, nx, ny, sc);
         // Warp-uniform, coalesced trace store of the block's 16 steps.
 #pragma unroll
         for(int c = 0; c < C; c++) {
-            if(uint32_t(eA + c) < WpadJob) row[eA + c] = TA[c];
-            if(uint32_t(eB + c) < WpadJob) row[eB + c] = TB[c];
+            if(uint32_t(eA + c) < WpadJob) row[eA + c] = s.TA[c];
+            if(uint32_t(eB + c) < WpadJob) row[eB + c] = s.TB[c];
         }
     }
+    bestScore = s.bestScore; bestI = s.bestI; bestJ = s.bestJ;
     if(bestI != 0x7fffffff) bestJ -= hi;          // bestJ was tracked as j + hi
     // Warp reduction of the end cell: maximum score, then smallest i, then smallest j.
 #pragma unroll
@@ -649,7 +687,7 @@ struct BandedArgs {
     uint32_t wMin, wMax;
 };
 
-template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
+template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32, (C == 1) ? 7 : 1)
 bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __restrict__ trace,
                   uint2* __restrict__ ordinals, uint32_t* __restrict__ counts)
 {
