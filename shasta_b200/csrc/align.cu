@@ -368,13 +368,13 @@ void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs
     b.orderKeysA.reserve(nJobs); b.orderKeysB.reserve(nJobs); b.orderValsA.reserve(nJobs); b.orderValsB.reserve(nJobs);
     SHB_LAUNCH(dpClassKeysKernel, ceilDiv(nJobs, 256), 256, 0, st, jobs, nJobs, (const uint32_t*)b.classLimits.get(), uint32_t(kClassCount),
                forwardClasses, b.orderKeysA.get(), b.orderValsA.get());
-    const int ranges[1][2] = {{0, 40}};
+    const int ranges[1][2] = {{0, kDpLengthKeyBits + kDpClassKeyBits}};
     const bool inB = radixSort<true>(b.orderKeysA.get(), b.orderKeysB.get(), b.orderValsA.get(), b.orderValsB.get(), nJobs, ranges, 1, c->sortWs, st);
     b.order = inB ? b.orderValsB.get() : b.orderValsA.get();
     // scalars: 512 entries, allocated once at context creation
     unsigned long long* dCounts = c->scalars.get() + 64;
     SHB_CUDA(cudaMemsetAsync(dCounts, 0, 256 * sizeof(unsigned long long), st));
-    SHB_LAUNCH(digitCountKernel, ceilDiv(nJobs, 256), 256, 0, st, (const uint64_t*)(inB ? b.orderKeysB.get() : b.orderKeysA.get()), nJobs, 32, 0xffu, dCounts);
+    SHB_LAUNCH(digitCountKernel, ceilDiv(nJobs, 256), 256, 0, st, (const uint64_t*)(inB ? b.orderKeysB.get() : b.orderKeysA.get()), nJobs, kDpLengthKeyBits, kDpClassNone, dCounts);
     unsigned long long h[256];
     SHB_CUDA(cudaMemcpyAsync(h, dCounts, sizeof(h), cudaMemcpyDeviceToHost, st));
     SHB_CUDA(cudaStreamSynchronize(st));

@@ -439,13 +439,22 @@ __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, 
             cur = loadWindow(block, eb);
         }
         const uint32_t word = __shfl_sync(0xffffffffu, cur, e - eb);
-        const uint32_t code = (word >> (2 * ((i - iFirst) & 15))) & 3u;
-        if(code == 1u) {
-            if(lane == 0) steps[n] = make_uint2(uint32_t(i - 1), uint32_t(j - 1));
-            n++; i--; j--;
-        } else if(code == 2u) j--;
-        else if(code == 3u) i--;
-        else break;
+        // Diagonal steps stay on the same offset, so a run of them is a run of "01" codes going down this word:
+        // take the whole run at once (one lane per step writes it) instead of one step per iteration.
+        const int32_t q = (i - iFirst) & 15;
+        const uint32_t x = word ^ 0x55555555u;
+        const uint32_t notDiag = (x | (x >> 1)) & 0x55555555u & ((2u << (2 * q)) - 1u);       // bit 2p: column p of the block, p <= q
+        int32_t run = notDiag ? q - ((31 - __clz(notDiag)) >> 1) : q + 1;
+        run = min(run, min(i, j));
+        if(run > 0) {
+            if(lane < run) steps[n + uint32_t(lane)] = make_uint2(uint32_t(i - 1 - lane), uint32_t(j - 1 - lane));
+            n += uint32_t(run); i -= run; j -= run;
+        } else {
+            const uint32_t code = (word >> (2 * q)) & 3u;
+            if(code == 2u) j--;
+            else if(code == 3u) i--;
+            else break;
+        }
     }
     __syncwarp();
     return n;
@@ -687,7 +696,10 @@ struct BandedArgs {
     uint32_t wMin, wMax;
 };
 
-template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32, (C == 1) ? 7 : 1)
+// Resident blocks per SM the register allocation aims for (the narrow classes are issue-bound and want the warps).
+constexpr int dpMinBlocks(int C) { return C == 1 ? 7 : C == 2 ? 6 : C == 3 ? 5 : C == 4 ? 4 : C <= 8 ? 2 : 1; }
+
+template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32, dpMinBlocks(C))
 bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __restrict__ trace,
                   uint2* __restrict__ ordinals, uint32_t* __restrict__ counts)
 {
@@ -958,8 +970,11 @@ static __global__ void setTraceOffsetsKernel(DpJob* __restrict__ jobs, uint32_t 
     if(outOffsets) jobs[p].outOffset = outOffsets[p];
 }
 
-// Sort key of a DP job: band class in bits 32.., then longest sequence first (load balance inside a launch).
-// classLimits[k] = widest padded band of class k; jobs that do not run get class 255.
+constexpr int kDpLengthKeyBits = 11, kDpClassKeyBits = 5;
+constexpr uint32_t kDpLengthKeyMax = (1u << kDpLengthKeyBits) - 1u, kDpClassNone = (1u << kDpClassKeyBits) - 1u;
+
+// Sort key of a DP job: band class, then longest sequence first (load balance inside a launch).
+// classLimits[k] = widest padded band of class k; jobs that do not run get class kDpClassNone.
 // forwardClasses > 0 (method 3, stage 1): jobs of at most classLimits[forwardClasses-1] rows go to the forward kernel,
 // class k = first k with ny <= classLimits[k]; the others keep their band class, shifted up by forwardClasses.
 static __global__ void dpClassKeysKernel(const DpJob* __restrict__ jobs, uint32_t n, const uint32_t* __restrict__ classLimits,
@@ -977,8 +992,10 @@ static __global__ void dpClassKeysKernel(const DpJob* __restrict__ jobs, uint32_
             for(uint32_t k = 0; k < classCount; k++) if(Wpad <= classLimits[k]) { cls = forwardClasses + k; break; }
         }
     }
-    const int32_t active = dpLastColumn(j.nx, j.ny, j.hi) - dpFirstColumn(j.lo);       // columns the kernel visits
-    keys[p] = (uint64_t(cls) << 32) | uint64_t(0xffffffffu - uint32_t(active > 0 ? active : 0));
+    // 16-bit key (two radix passes): class, then the number of columns the kernel visits in units of 16, longest first.
+    const int32_t active = dpLastColumn(j.nx, j.ny, j.hi) - dpFirstColumn(j.lo);
+    const uint32_t length = min(uint32_t(active > 0 ? active : 0) >> 4, kDpLengthKeyMax);
+    keys[p] = (uint64_t(min(cls, kDpClassNone)) << kDpLengthKeyBits) | uint64_t(kDpLengthKeyMax - length);
     vals[p] = p;
 }
 
