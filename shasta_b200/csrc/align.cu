@@ -105,6 +105,8 @@ struct Batch {
     DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, bytes64, bytesOff, scanWs64, ctoc;
     DeviceBuffer<uint32_t> trace;
     DeviceBuffer<uint2> ordinals;
+    DeviceBuffer<int2> endCells;
+    DeviceBuffer<uint32_t> stepCounts;
     DeviceBuffer<uint8_t> cdata;
     // method 4
     DeviceBuffer<unsigned long long> cellCnt, cellOff;
@@ -139,8 +141,16 @@ struct AlignCache {
     static constexpr int kSideStreams = 3;
     cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t forkEv = nullptr, joinEv[kSideStreams] = {nullptr, nullptr, nullptr};
+    // high-priority stream for the short latency-bound kernels (traceback, filter) that follow each DP chunk: their
+    // blocks are scheduled ahead of the pending blocks of the other chunks' DP kernels
+    cudaStream_t hiStream = nullptr;
+    cudaEvent_t hiJoinEv = nullptr;
+    std::vector<cudaEvent_t> unitEvents;
     ~AlignCache()
     {
+        if(hiStream) cudaStreamDestroy(hiStream);
+        if(hiJoinEv) cudaEventDestroy(hiJoinEv);
+        for(cudaEvent_t e : unitEvents) cudaEventDestroy(e);
         for(int i = 0; i < kSideStreams; i++) { if(side[i]) cudaStreamDestroy(side[i]); if(joinEv[i]) cudaEventDestroy(joinEv[i]); }
         if(forkEv) cudaEventDestroy(forkEv);
     }
@@ -152,9 +162,12 @@ AlignCache& cache(shb_context* c)
     return *static_cast<AlignCache*>(c->alignCache);
 }
 
-// Runs launch(k, count, offset, stream) for every non-empty band class: the widest classes first, on the side
-// streams, the remaining (largest) launches on the main stream; the main stream continues after all of them.
-template<class F> void forEachClassConcurrently(shb_context* c, const std::vector<uint64_t>& classCounts, F launch)
+// Runs launch(k, count, offset, stream) for every non-empty band class, cut into chunks of at most chunkMax jobs:
+// the widest classes first, round-robin over the side streams and the main stream, so that independent launches
+// (disjoint jobs and scratch) overlap: the few long jobs of the wide classes run beside the big narrow-band launch,
+// and the latency-bound traceback of one chunk runs beside the issue-bound DP of the next. The main stream continues
+// after all of them.
+template<class F> void forEachClassConcurrently(shb_context* c, const std::vector<uint64_t>& classCounts, uint32_t chunkMax, F launch)
 {
     AlignCache& ac = cache(c);
     cudaStream_t st = c->stream;
@@ -165,26 +178,31 @@ template<class F> void forEachClassConcurrently(shb_context* c, const std::vecto
             SHB_CUDA(cudaEventCreateWithFlags(&ac.joinEv[i], cudaEventDisableTiming));
         }
     }
+    struct Unit { int k; uint32_t count; uint64_t offset; };
+    std::vector<Unit> units;
     const int classCount = int(classCounts.size());
     std::vector<uint64_t> offsets(classCounts.size(), 0);
-    int nonEmpty = 0, firstNonEmpty = -1;
-    for(int k = 0; k < classCount; k++) {
-        if(k) offsets[k] = offsets[k-1] + classCounts[k-1];
-        if(classCounts[k]) { nonEmpty++; if(firstNonEmpty < 0) firstNonEmpty = k; }
+    for(int k = 1; k < classCount; k++) offsets[k] = offsets[k-1] + classCounts[k-1];
+    for(int k = classCount - 1; k >= 0; k--) {
+        const uint64_t count = classCounts[k];
+        if(!count) continue;
+        const uint64_t chunks = (count + chunkMax - 1) / chunkMax, per = (count + chunks - 1) / chunks;
+        for(uint64_t begin = 0; begin < count; begin += per) units.push_back({k, uint32_t(std::min(per, count - begin)), offsets[k] + begin});
     }
-    if(nonEmpty == 0) return;
+    if(units.empty()) return;
+    constexpr int kStreams = AlignCache::kSideStreams + 1;      // the last one is the main stream
     bool used[AlignCache::kSideStreams] = {false, false, false};
-    if(nonEmpty > 1) {
-        SHB_CUDA(cudaEventRecord(ac.forkEv, st));
-        int slot = 0;
-        for(int k = classCount - 1; k > firstNonEmpty; k--) {
-            if(!classCounts[k]) continue;
-            const int i = slot++ % AlignCache::kSideStreams;
-            if(!used[i]) { SHB_CUDA(cudaStreamWaitEvent(ac.side[i], ac.forkEv, 0)); used[i] = true; }
-            launch(k, uint32_t(classCounts[k]), offsets[k], ac.side[i]);
+    if(units.size() > 1) SHB_CUDA(cudaEventRecord(ac.forkEv, st));
+    for(size_t u = 0; u < units.size(); u++) {
+        // the last unit always goes to the main stream
+        const int i = (u + 1 == units.size()) ? kStreams - 1 : int(u % kStreams);
+        cudaStream_t s = st;
+        if(i < AlignCache::kSideStreams) {
+            s = ac.side[i];
+            if(!used[i]) { SHB_CUDA(cudaStreamWaitEvent(s, ac.forkEv, 0)); used[i] = true; }
         }
+        launch(units[u].k, units[u].count, units[u].offset, s);
     }
-    launch(firstNonEmpty, uint32_t(classCounts[firstNonEmpty]), offsets[firstNonEmpty], st);
     for(int i = 0; i < AlignCache::kSideStreams; i++) {
         if(!used[i]) continue;
         SHB_CUDA(cudaEventRecord(ac.joinEv[i], ac.side[i]));
@@ -281,6 +299,9 @@ void buildSortedMarkers(shb_context* c, uint32_t k)
 }
 
 struct DpTotals { unsigned long long traceWords = 0; double ms = 0.; };
+
+// SHB_TRACE only: wall time of the stage-2 sub-phases (each bracketed by stream synchronisation), summed per call.
+double g_tracePhaseMs[4] = {0., 0., 0., 0.};
 
 // Host-side phase timing, printed to stderr when SHB_TRACE is set (diagnostics only).
 struct PhaseClock {
@@ -386,9 +407,18 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
                    Events& ev, DpTotals& totals)
 {
     cudaStream_t st = c->stream;
+    static const bool traceOn = getenv("SHB_TRACE") != nullptr;
+    auto lap = [&](int k, std::chrono::steady_clock::time_point& t0) {
+        if(!traceOn) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        g_tracePhaseMs[k] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+    };
+    auto t0 = std::chrono::steady_clock::now();
     unsigned long long* total64 = c->scalars.get() + 48;
     b.scanWs64.reserve(scanWorkspaceElements(nJobs));
-    b.twOff.reserve(nJobs); b.outOff.reserve(nJobs); b.counts.reserve(nJobs);
+    b.twOff.reserve(nJobs); b.outOff.reserve(nJobs); b.counts.reserve(nJobs); b.endCells.reserve(nJobs); b.stepCounts.reserve(nJobs);
     exclusiveScan<unsigned long long>(b.tw.get(), b.twOff.get(), nJobs, total64, b.scanWs64.get(), st);
     const unsigned long long traceWords = readBack<unsigned long long>(total64, st);
     exclusiveScan<unsigned long long>(b.outCnt.get(), b.outOff.get(), nJobs, total64, b.scanWs64.get(), st);
@@ -403,16 +433,43 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     buildClassOrder(c, b, b.jobs.get(), nJobs, classCounts);
     BandedArgs g;
     g.kmerIds = sequences; g.scores = scores;
+    lap(3, t0);
     SHB_CUDA(cudaEventRecord(ev.a, st));
     (void)maxWidth;
-    forEachClassConcurrently(c, classCounts, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
+    // Per chunk: DP (warp per job) on its stream, then traceback (thread per job) and equal-k-mer filter (warp per job)
+    // on the high-priority stream.
+    AlignCache& ac = cache(c);
+    if(!ac.hiStream) {
+        int least = 0, greatest = 0;
+        SHB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SHB_CUDA(cudaStreamCreateWithPriority(&ac.hiStream, cudaStreamNonBlocking, greatest));
+        SHB_CUDA(cudaEventCreateWithFlags(&ac.hiJoinEv, cudaEventDisableTiming));
+    }
+    size_t unit = 0;
+    forEachClassConcurrently(c, classCounts, 32768, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
         const uint32_t warps = warpsForClass(kClasses[k]);
         const size_t smem = smemForClass(kClasses[k], warps);
         BandedArgs gk = g;
         gk.n = count; gk.order = b.order + offset; gk.wMin = 0; gk.wMax = kClasses[k].wMax;
-        launchBanded(kClasses[k], ceilDiv(count, warps), warps * 32, smem, s, gk, (const DpJob*)b.jobs.get(), b.trace.get(),
-                     b.ordinals.get(), b.counts.get());
+        launchBanded(kClasses[k], ceilDiv(count, warps), warps * 32, smem, s, gk, (const DpJob*)b.jobs.get(), b.trace.get(), b.endCells.get());
+        if(unit == ac.unitEvents.size()) {
+            cudaEvent_t e = nullptr;
+            SHB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ac.unitEvents.push_back(e);
+        }
+        SHB_CUDA(cudaEventRecord(ac.unitEvents[unit], s));
+        SHB_CUDA(cudaStreamWaitEvent(ac.hiStream, ac.unitEvents[unit], 0));
+        unit++;
+        SHB_LAUNCH(tracebackKernel, ceilDiv(count, 128), 128, 0, ac.hiStream, count, gk.order, (const DpJob*)b.jobs.get(),
+                   (const int2*)b.endCells.get(), (const uint32_t*)b.trace.get(), b.ordinals.get(), b.stepCounts.get());
+        SHB_LAUNCH(filterStepsKernel, ceilDiv(count, 4), 128, 0, ac.hiStream, count, gk.order, (const DpJob*)b.jobs.get(), sequences,
+                   b.ordinals.get(), (const uint32_t*)b.stepCounts.get(), b.counts.get());
     });
+    if(unit) {
+        SHB_CUDA(cudaEventRecord(ac.hiJoinEv, ac.hiStream));
+        SHB_CUDA(cudaStreamWaitEvent(st, ac.hiJoinEv, 0));
+    }
+    lap(2, t0);
     SHB_CUDA(cudaEventRecord(ev.b, st));
 }
 
@@ -545,7 +602,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             std::vector<uint64_t> classCounts1;
             buildClassOrder(c, b, b.jobs1.get(), nb, classCounts1, kForwardClassCount);
             SHB_CUDA(cudaEventRecord(dpEv1.a, st));
-            forEachClassConcurrently(c, classCounts1, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
+            forEachClassConcurrently(c, classCounts1, 0xffffffffu, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
                 Method3Args gk = g1;
                 gk.n = count; gk.order = b.order + offset; gk.wMin = 0;
                 if(k < kForwardClassCount) {
@@ -678,6 +735,10 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     {
         static const char* const names[] = {"prepare", "setup+stage1", "stage2", "epilogue", "compact+write", "copy_to_host"};
         phases.report(names, 6);
+        if(phases.on) {
+            fprintf(stderr, "[shb] stage-2 detail (ms): dp+traceback+filter=%.1f setup=%.1f\n", g_tracePhaseMs[2], g_tracePhaseMs[3]);
+            for(double& v : g_tracePhaseMs) v = 0.;
+        }
     }
     tocOut[count] = outBytes;
     if(count == 0) tocOut[0] = 0;

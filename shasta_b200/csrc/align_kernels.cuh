@@ -686,8 +686,11 @@ method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob
     }
 }
 
-// Stage 2 / generic banded alignment on full marker rows: DP, traceback, and the equal-kmer diagonal
-// steps written LAST STEP FIRST to ordinals[outOffset ...]; counts[p] receives how many.
+// Stage 2 / generic banded alignment on full marker rows, in three launches:
+//   bandedAlignKernel<C>   one warp per job: the DP; writes the trace and the end cell;
+//   tracebackKernel        one THREAD per job: walks the trace (a serial, latency-bound pointer chase that a warp could
+//                          only execute redundantly on its 32 lanes) and writes every diagonal step, last step first;
+//   filterStepsKernel      one warp per job: keeps the steps on equal k-mers; counts[p] receives how many.
 struct BandedArgs {
     uint32_t n;
     const uint32_t* order;          // job indices of this launch's band class, longest first; n = how many
@@ -700,8 +703,7 @@ struct BandedArgs {
 constexpr int dpMinBlocks(int C) { return C == 1 ? 7 : C == 2 ? 6 : C == 3 ? 5 : C == 4 ? 4 : C <= 8 ? 2 : 1; }
 
 template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32, dpMinBlocks(C))
-bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __restrict__ trace,
-                  uint2* __restrict__ ordinals, uint32_t* __restrict__ counts)
+bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __restrict__ trace, int2* __restrict__ endCells)
 {
     extern __shared__ int32_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -709,7 +711,7 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
     if(slot >= g.n) return;
     const uint32_t p = g.order[slot];
     const DpJob job = jobs[p];
-    if(job.state != kStateRun) return;          // counts[] is zeroed by the host
+    if(job.state != kStateRun) return;
     const uint32_t* a = g.kmerIds + job.aOffset;
     const uint32_t* b = g.kmerIds + job.bOffset;
     int32_t bestScore, bestI, bestJ;
@@ -724,12 +726,69 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
         bandedOverlapDp(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, hPrev, hCur, traceAcc, trace + job.traceOffset,
                         bestScore, bestI, bestJ);
     }
-    __syncwarp();
-    __threadfence_block();
-    uint2* out = ordinals + job.outOffset;
-    const uint32_t steps = tracebackCollect(trace + job.traceOffset, job.lo, job.hi, bestI, bestJ, out, 2 * C, C > 0 ? dpFirstColumn(job.lo) : 0);
-    const uint32_t count = filterEqualSteps(out, steps, a, b);
-    if(lane == 0) counts[p] = count;
+    if(lane == 0) endCells[p] = make_int2(bestI, bestJ);
+}
+
+// Offsets per sub-chunk of the wavefront kernel that handles a padded band width (0: the scan kernel, by-column trace).
+__host__ __device__ inline uint32_t dpWavefrontC(uint32_t Wpad)
+{
+    return Wpad <= 256 ? Wpad / 64 : Wpad <= 384 ? 6 : Wpad <= 512 ? 8 : Wpad <= 768 ? 12 : Wpad <= kDpWavefrontMaxWidth ? 16 : 0;
+}
+
+static __global__ void __launch_bounds__(128)
+tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __restrict__ jobs, const int2* __restrict__ endCells,
+                const uint32_t* __restrict__ trace, uint2* __restrict__ ordinals, uint32_t* __restrict__ stepCounts)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if(slot >= n) return;
+    const uint32_t p = order[slot];             // neighbouring threads: same band class, similar length
+    const DpJob job = jobs[p];
+    const int2 end = endCells[p];
+    int32_t i = end.x, j = end.y;
+    uint32_t count = 0;
+    if(job.state == kStateRun && i > 0 && j > 0) {
+        const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
+        const uint32_t C = dpWavefrontC(Wpad);
+        // By-step layout: the code of cell (i, e) sits in step t = (i - iFirst) + e / (2C); by-column layout: t = i.
+        const int32_t iFirst = C ? dpFirstColumn(job.lo) : 0;
+        const uint32_t reciprocal = C ? (65536u + 2u * C - 1u) / (2u * C) : 0u;      // e / (2C) == (e * reciprocal) >> 16 for e < 1024
+        const uint32_t* __restrict__ tr = trace + job.traceOffset;
+        uint2* __restrict__ out = ordinals + job.outOffset;
+        const int32_t hi = job.hi;
+        while(i > 0 && j > 0) {
+            const uint32_t e = uint32_t(j - i + hi);
+            const uint32_t t = uint32_t(i - iFirst) + ((e * reciprocal) >> 16);
+            const uint32_t word = tr[uint64_t(t >> 4) * Wpad + e];
+            // Diagonal steps stay on the same offset: a run of them is a run of "01" codes going down this word.
+            const uint32_t q = t & 15u;
+            const uint32_t x = word ^ 0x55555555u;
+            const uint32_t notDiag = (x | (x >> 1)) & 0x55555555u & ((2u << (2u * q)) - 1u);      // bit 2s: step s of the word, s <= q
+            int32_t run = notDiag ? int32_t(q) - ((31 - __clz(notDiag)) >> 1) : int32_t(q) + 1;
+            run = min(run, min(i, j));
+            if(run > 0) {
+                for(int32_t k = 0; k < run; k++) out[count + uint32_t(k)] = make_uint2(uint32_t(i - 1 - k), uint32_t(j - 1 - k));
+                count += uint32_t(run); i -= run; j -= run;
+            } else {
+                const uint32_t code = (word >> (2u * q)) & 3u;
+                if(code == 2u) j--;
+                else if(code == 3u) i--;
+                else break;
+            }
+        }
+    }
+    stepCounts[p] = count;
+}
+
+static __global__ void __launch_bounds__(128)
+filterStepsKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __restrict__ jobs, const uint32_t* __restrict__ kmerIds,
+                  uint2* __restrict__ ordinals, const uint32_t* __restrict__ stepCounts, uint32_t* __restrict__ counts)
+{
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if(slot >= n) return;
+    const uint32_t p = order[slot];
+    const DpJob job = jobs[p];
+    const uint32_t count = filterEqualSteps(ordinals + job.outOffset, stepCounts[p], kmerIds + job.aOffset, kmerIds + job.bOffset);
+    if((threadIdx.x & 31u) == 0) counts[p] = count;
 }
 
 // ---------------------------------------------------------------------------------------------
