@@ -104,7 +104,7 @@ struct Batch {
     DeviceBuffer<DpJob> jobs1, jobs;
     DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, bytes64, bytesOff, scanWs64, ctoc;
     DeviceBuffer<uint32_t> trace;
-    DeviceBuffer<uint2> ordinals;
+    DeviceBuffer<uint2> ordinals, runs;
     DeviceBuffer<int2> endCells;
     DeviceBuffer<uint32_t> stepCounts;
     DeviceBuffer<uint8_t> cdata;
@@ -130,6 +130,7 @@ struct AlignCache {
     // method 4: markers sorted by k-mer id within each oriented read
     DeviceBuffer<uint32_t> sortedKmer, sortedOrdinal;
     uint64_t sortedGeneration = ~0ull;
+    uint64_t lengthCheckGeneration = ~0ull;
     // per-batch scratch and the device-side result accumulation: kept across calls so that a steady-state call does
     // not allocate or free device memory
     Batch batch;
@@ -143,13 +144,13 @@ struct AlignCache {
     cudaEvent_t forkEv = nullptr, joinEv[kSideStreams] = {nullptr, nullptr, nullptr};
     // high-priority stream for the short latency-bound kernels (traceback, filter) that follow each DP chunk: their
     // blocks are scheduled ahead of the pending blocks of the other chunks' DP kernels
-    cudaStream_t hiStream = nullptr;
-    cudaEvent_t hiJoinEv = nullptr;
+    static constexpr int kHiStreams = 4;
+    cudaStream_t hiStream[kHiStreams] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t hiJoinEv[kHiStreams] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> unitEvents;
     ~AlignCache()
     {
-        if(hiStream) cudaStreamDestroy(hiStream);
-        if(hiJoinEv) cudaEventDestroy(hiJoinEv);
+        for(int i = 0; i < kHiStreams; i++) { if(hiStream[i]) cudaStreamDestroy(hiStream[i]); if(hiJoinEv[i]) cudaEventDestroy(hiJoinEv[i]); }
         for(cudaEvent_t e : unitEvents) cudaEventDestroy(e);
         for(int i = 0; i < kSideStreams; i++) { if(side[i]) cudaStreamDestroy(side[i]); if(joinEv[i]) cudaEventDestroy(joinEv[i]); }
         if(forkEv) cudaEventDestroy(forkEv);
@@ -425,6 +426,7 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     const unsigned long long ordinalSlots = readBack<unsigned long long>(total64, st);
     b.trace.reserve(traceWords + 1);
     b.ordinals.reserve(ordinalSlots + 1);
+    b.runs.reserve(ordinalSlots + 1);
     totals.traceWords += traceWords;
     SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nJobs, 256), 256, 0, st, b.jobs.get(), nJobs, (const unsigned long long*)b.twOff.get(),
                (const unsigned long long*)b.outOff.get());
@@ -439,11 +441,13 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     // Per chunk: DP (warp per job) on its stream, then traceback (thread per job) and equal-k-mer filter (warp per job)
     // on the high-priority stream.
     AlignCache& ac = cache(c);
-    if(!ac.hiStream) {
+    if(!ac.hiStream[0]) {
         int least = 0, greatest = 0;
         SHB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        SHB_CUDA(cudaStreamCreateWithPriority(&ac.hiStream, cudaStreamNonBlocking, greatest));
-        SHB_CUDA(cudaEventCreateWithFlags(&ac.hiJoinEv, cudaEventDisableTiming));
+        for(int i = 0; i < AlignCache::kHiStreams; i++) {
+            SHB_CUDA(cudaStreamCreateWithPriority(&ac.hiStream[i], cudaStreamNonBlocking, greatest));
+            SHB_CUDA(cudaEventCreateWithFlags(&ac.hiJoinEv[i], cudaEventDisableTiming));
+        }
     }
     size_t unit = 0;
     forEachClassConcurrently(c, classCounts, 32768, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
@@ -458,16 +462,17 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
             ac.unitEvents.push_back(e);
         }
         SHB_CUDA(cudaEventRecord(ac.unitEvents[unit], s));
-        SHB_CUDA(cudaStreamWaitEvent(ac.hiStream, ac.unitEvents[unit], 0));
+        cudaStream_t hs = ac.hiStream[unit % AlignCache::kHiStreams];
+        SHB_CUDA(cudaStreamWaitEvent(hs, ac.unitEvents[unit], 0));
         unit++;
-        SHB_LAUNCH(tracebackKernel, ceilDiv(count, 128), 128, 0, ac.hiStream, count, gk.order, (const DpJob*)b.jobs.get(),
-                   (const int2*)b.endCells.get(), (const uint32_t*)b.trace.get(), b.ordinals.get(), b.stepCounts.get());
-        SHB_LAUNCH(filterStepsKernel, ceilDiv(count, 4), 128, 0, ac.hiStream, count, gk.order, (const DpJob*)b.jobs.get(), sequences,
-                   b.ordinals.get(), (const uint32_t*)b.stepCounts.get(), b.counts.get());
+        SHB_LAUNCH(tracebackKernel, ceilDiv(count, 128), 128, 0, hs, count, gk.order, (const DpJob*)b.jobs.get(),
+                   (const int2*)b.endCells.get(), (const uint32_t*)b.trace.get(), b.runs.get(), b.stepCounts.get());
+        SHB_LAUNCH(filterStepsKernel, ceilDiv(count, 4), 128, 0, hs, count, gk.order, (const DpJob*)b.jobs.get(), sequences,
+                   (const uint2*)b.runs.get(), (const uint32_t*)b.stepCounts.get(), b.ordinals.get(), b.counts.get());
     });
-    if(unit) {
-        SHB_CUDA(cudaEventRecord(ac.hiJoinEv, ac.hiStream));
-        SHB_CUDA(cudaStreamWaitEvent(st, ac.hiJoinEv, 0));
+    for(size_t i = 0; i < std::min<size_t>(unit, AlignCache::kHiStreams); i++) {
+        SHB_CUDA(cudaEventRecord(ac.hiJoinEv[i], ac.hiStream[i]));
+        SHB_CUDA(cudaStreamWaitEvent(st, ac.hiJoinEv[i], 0));
     }
     lap(2, t0);
     SHB_CUDA(cudaEventRecord(ev.b, st));
@@ -519,6 +524,12 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         maxStage1Width = 2 * ac.dsMaxRow + 2 + 64;
         SHB_REQUIRE(maxStage1Width <= kMaxBandWidth, SHB_ERR_INVALID,
                     "Downsampled reads are too long for the stage-1 kernel (limit 8191 downsampled markers).");
+    }
+    if(ac.lengthCheckGeneration != c->markerGeneration) {       // the traceback packs a run length above a 28-bit ordinal
+        for(size_t r = 0; r + 1 < c->tocHost.size(); r++) {
+            SHB_REQUIRE(c->tocHost[r + 1] - c->tocHost[r] < (1ull << kRunLengthShift), SHB_ERR_INVALID, "A read has 2^28 or more markers.");
+        }
+        ac.lengthCheckGeneration = c->markerGeneration;
     }
     const uint32_t maxStage2Width = uint32_t(std::max(0, o.maxBand)) + 2 + 64;     // padded to a multiple of 64
     SHB_REQUIRE(maxStage2Width <= kMaxBandWidth, SHB_ERR_INVALID, "Align.maxBand too large for this implementation (limit 16382).");

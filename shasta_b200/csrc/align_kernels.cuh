@@ -735,9 +735,13 @@ __host__ __device__ inline uint32_t dpWavefrontC(uint32_t Wpad)
     return Wpad <= 256 ? Wpad / 64 : Wpad <= 384 ? 6 : Wpad <= 512 ? 8 : Wpad <= 768 ? 12 : Wpad <= kDpWavefrontMaxWidth ? 16 : 0;
 }
 
+// A run of consecutive diagonal steps (x0 - k, y0 - k), k = 0 .. length-1, as the traceback emits it (last step first):
+// .x = x0 | (length - 1) << 28, .y = y0. Reads have fewer than 2^28 markers (checked by the host).
+constexpr uint32_t kRunLengthShift = 28, kRunOrdinalMask = (1u << kRunLengthShift) - 1u;
+
 static __global__ void __launch_bounds__(128)
 tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __restrict__ jobs, const int2* __restrict__ endCells,
-                const uint32_t* __restrict__ trace, uint2* __restrict__ ordinals, uint32_t* __restrict__ stepCounts)
+                const uint32_t* __restrict__ trace, uint2* __restrict__ runs, uint32_t* __restrict__ runCounts)
 {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if(slot >= n) return;
@@ -753,8 +757,9 @@ tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __r
         const int32_t iFirst = C ? dpFirstColumn(job.lo) : 0;
         const uint32_t reciprocal = C ? (65536u + 2u * C - 1u) / (2u * C) : 0u;      // e / (2C) == (e * reciprocal) >> 16 for e < 1024
         const uint32_t* __restrict__ tr = trace + job.traceOffset;
-        uint2* __restrict__ out = ordinals + job.outOffset;
+        uint2* __restrict__ out = runs + job.outOffset;
         const int32_t hi = job.hi;
+        // One dependent load per iteration; the threads of a warp stay in step (one run or one gap step per iteration).
         while(i > 0 && j > 0) {
             const uint32_t e = uint32_t(j - i + hi);
             const uint32_t t = uint32_t(i - iFirst) + ((e * reciprocal) >> 16);
@@ -765,30 +770,72 @@ tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __r
             const uint32_t notDiag = (x | (x >> 1)) & 0x55555555u & ((2u << (2u * q)) - 1u);      // bit 2s: step s of the word, s <= q
             int32_t run = notDiag ? int32_t(q) - ((31 - __clz(notDiag)) >> 1) : int32_t(q) + 1;
             run = min(run, min(i, j));
+            const uint32_t code = (word >> (2u * q)) & 3u;
             if(run > 0) {
-                for(int32_t k = 0; k < run; k++) out[count + uint32_t(k)] = make_uint2(uint32_t(i - 1 - k), uint32_t(j - 1 - k));
-                count += uint32_t(run); i -= run; j -= run;
-            } else {
-                const uint32_t code = (word >> (2u * q)) & 3u;
-                if(code == 2u) j--;
-                else if(code == 3u) i--;
-                else break;
-            }
+                out[count++] = make_uint2(uint32_t(i - 1) | (uint32_t(run - 1) << kRunLengthShift), uint32_t(j - 1));
+                i -= run; j -= run;
+            } else if(code == 2u) j--;
+            else if(code == 3u) i--;
+            else break;
         }
     }
-    stepCounts[p] = count;
+    runCounts[p] = count;
 }
 
+// Expands the runs of one job (warp per job) into its diagonal steps and keeps, in order, those on equal k-mers
+// (src/AssemblerAlign3.cpp:279-295, src/Align4.cpp:1052-1068); counts[p] receives how many.
 static __global__ void __launch_bounds__(128)
 filterStepsKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __restrict__ jobs, const uint32_t* __restrict__ kmerIds,
-                  uint2* __restrict__ ordinals, const uint32_t* __restrict__ stepCounts, uint32_t* __restrict__ counts)
+                  const uint2* __restrict__ runs, const uint32_t* __restrict__ runCounts, uint2* __restrict__ ordinals,
+                  uint32_t* __restrict__ counts)
 {
     const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if(slot >= n) return;
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t p = order[slot];
     const DpJob job = jobs[p];
-    const uint32_t count = filterEqualSteps(ordinals + job.outOffset, stepCounts[p], kmerIds + job.aOffset, kmerIds + job.bOffset);
-    if((threadIdx.x & 31u) == 0) counts[p] = count;
+    const uint32_t* __restrict__ a = kmerIds + job.aOffset;
+    const uint32_t* __restrict__ b = kmerIds + job.bOffset;
+    const uint2* __restrict__ in = runs + job.outOffset;
+    uint2* __restrict__ out = ordinals + job.outOffset;
+    const uint32_t nRuns = runCounts[p];
+    uint32_t count = 0;
+    for(uint32_t base = 0; base < nRuns; base += 32) {
+        // One run per lane; exclusive prefix of the run lengths = index of each run's first step in this group.
+        const uint32_t r = base + lane;
+        uint2 d = make_uint2(0, 0);
+        uint32_t length = 0;
+        if(r < nRuns) { d = in[r]; length = (d.x >> kRunLengthShift) + 1u; }
+        const uint32_t x0 = d.x & kRunOrdinalMask, y0 = d.y;
+        uint32_t inclusive = length;
+#pragma unroll
+        for(int s = 1; s < 32; s <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inclusive, s);
+            if(lane >= uint32_t(s)) inclusive += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inclusive, 31);
+        const uint32_t first = inclusive - length;
+        for(uint32_t s0 = 0; s0 < total; s0 += 32) {
+            const uint32_t step = s0 + lane;
+            // The run that holds this step: the last lane whose first step is <= step (binary search over the lanes;
+            // empty trailing lanes have first == total > step).
+            uint32_t owner = 0;
+#pragma unroll
+            for(int w = 16; w > 0; w >>= 1) {
+                const uint32_t probe = owner + uint32_t(w);
+                const uint32_t v = __shfl_sync(0xffffffffu, first, int(probe & 31u));
+                if(v <= step) owner = probe;
+            }
+            const uint32_t k = step - __shfl_sync(0xffffffffu, first, int(owner));
+            const uint32_t x = __shfl_sync(0xffffffffu, x0, int(owner)) - k;
+            const uint32_t y = __shfl_sync(0xffffffffu, y0, int(owner)) - k;
+            const bool keep = step < total && a[x] == b[y];
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if(keep) out[count + __popc(m & ((1u << lane) - 1u))] = make_uint2(x, y);
+            count += __popc(m);
+        }
+    }
+    if(lane == 0) counts[p] = count;
 }
 
 // ---------------------------------------------------------------------------------------------
