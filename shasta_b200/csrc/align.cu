@@ -542,7 +542,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     fo.minAlignedFraction = o.minAlignedFraction;
     fo.suppressContainments = (!method4 && o.suppressContainments) ? 1u : 0u;     // method 4 applies it after the selection
 
-    const uint32_t batchMax = method4 ? 32768 : 131072;
+    const uint32_t batchMax = method4 ? 32768 : 262144;
     const uint64_t cellBudget = 192ull << 20;      // method 4: cells of scratch per batch
     Batch& b = ac.batch;
     c->scanWs.reserve(scanWorkspaceElements(4ull * batchMax * 64));
