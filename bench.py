@@ -161,7 +161,17 @@ def run_reference(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
+def _claim_stdout():
+    """stdout carries exactly one JSON line. Libraries (NCCL prints its version banner) write to fd 1 directly, so fd 1
+    is pointed at stderr for the whole run and the JSON line goes to a private copy of the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -121,12 +121,19 @@ def lowhash0_sharded(stages, params, read_count_total, group=None):
         it += group_size
     t_final = tick()
 
-    # Pair counts to the owner of readId0.
+    # Pair counts to the owner of readId0. Owners hold contiguous readId0 ranges (the concatenation of the ranks' candidates
+    # stays sorted), but not equal ones: readId0 < readId1 puts most pairs on low read ids, so the ranges are cut on a
+    # fine histogram (top bits of readId0, summed over the ranks) into groups of equal pair mass.
     rb = read_bits(read_count_total)
-    pair_shift = 32 + max(rb - log2w, 0)
+    fine_bits = max(log2w, min(8, rb))
+    pair_shift = 32 + max(rb - fine_bits, 0)
     keys, cnts = stages.local_pairs()
-    pk, pv, pc = stages.partition(keys, cnts, pair_shift, log2w)
+    pk, pv, pc_fine = stages.partition(keys, cnts, pair_shift, fine_bits)
     pk, pv = pk.clone(), pv.clone()
+    hist = torch.tensor(pc_fine, dtype=torch.int64, device=pk.device)
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    bounds = balanced_read_ranges(hist.cpu().numpy(), world)
+    pc = [int(sum(pc_fine[bounds[g]:bounds[g + 1]])) for g in range(world)]
     rk, _ = all_to_all_v(pk, pc, group)
     rv, _ = all_to_all_v(pv, pc, group)
     stages.set_pairs(rk, rv)

@@ -155,10 +155,11 @@ def _worker(rank, world, port, case, result_path):
         local_kmer = d["kmer"][toc[2 * rb]:toc[2 * re]]
         stages = NumpyStages(local_toc, local_kmer, d["flags"], rb, re, R, int(toc[-1]))
         cand, stats, info = D.lowhash0_sharded(stages, case["params"], R)
-        # every candidate emitted by this rank has readId0 in the top-bits range this rank owns
-        if len(cand):
-            owner = cand[:, 0].astype(np.int64) >> max(D.read_bits(R) - (world.bit_length() - 1), 0)
-            assert (owner == rank).all()
+        # the ranks own disjoint, increasing readId0 ranges (cut for equal pair mass, not equal width)
+        spans = [None] * world
+        dist.all_gather_object(spans, (int(cand[:, 0].min()), int(cand[:, 0].max())) if len(cand) else None)
+        spans = [x for x in spans if x is not None]
+        assert all(spans[g][1] < spans[g + 1][0] for g in range(len(spans) - 1)), spans
         allc = D.gather_candidates(cand)
         # rebalancing keeps the global order and evens the slice sizes
         rbc = D.rebalance_candidates(cand)
