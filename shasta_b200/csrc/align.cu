@@ -301,6 +301,14 @@ void buildSortedMarkers(shb_context* c, uint32_t k)
 
 struct DpTotals { unsigned long long traceWords = 0; double ms = 0.; };
 
+uint32_t envCount(const char* name, uint32_t dflt)
+{
+    const char* v = getenv(name);
+    if(!v) return dflt;
+    const long x = strtol(v, nullptr, 10);
+    return x > 0 ? uint32_t(x) : dflt;
+}
+
 // SHB_TRACE only: wall time of the stage-2 sub-phases (each bracketed by stream synchronisation), summed per call.
 double g_tracePhaseMs[4] = {0., 0., 0., 0.};
 
@@ -450,7 +458,7 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
         }
     }
     size_t unit = 0;
-    forEachClassConcurrently(c, classCounts, 32768, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
+    forEachClassConcurrently(c, classCounts, envCount("SHB_ALIGN_CHUNK", 32768), [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
         const uint32_t warps = warpsForClass(kClasses[k]);
         const size_t smem = smemForClass(kClasses[k], warps);
         BandedArgs gk = g;
@@ -542,7 +550,9 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     fo.minAlignedFraction = o.minAlignedFraction;
     fo.suppressContainments = (!method4 && o.suppressContainments) ? 1u : 0u;     // method 4 applies it after the selection
 
-    const uint32_t batchMax = method4 ? 32768 : 262144;
+    // SHB_ALIGN_BATCH / SHB_ALIGN_CHUNK: test hooks that shrink the batch and chunk sizes so that small inputs exercise the
+    // multi-batch, multi-chunk paths (tests/test_gpu_scale.py).
+    const uint32_t batchMax = envCount("SHB_ALIGN_BATCH", method4 ? 32768 : 262144);
     const uint64_t cellBudget = 192ull << 20;      // method 4: cells of scratch per batch
     Batch& b = ac.batch;
     c->scanWs.reserve(scanWorkspaceElements(4ull * batchMax * 64));

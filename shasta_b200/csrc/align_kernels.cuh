@@ -460,26 +460,6 @@ __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, 
     return n;
 }
 
-// Keep, in place and in order, the recorded steps whose k-mers are equal (src/AssemblerAlign3.cpp:279-295,
-// src/Align4.cpp:1052-1068). Returns the number kept.
-__device__ inline uint32_t filterEqualSteps(uint2* __restrict__ steps, uint32_t n, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b)
-{
-    const unsigned lane = threadIdx.x & 31u;
-    uint32_t count = 0;
-    for(uint32_t base = 0; base < n; base += 32) {
-        const uint32_t k = base + lane;
-        bool keep = false;
-        uint2 s = make_uint2(0, 0);
-        if(k < n) { s = steps[k]; keep = (a[s.x] == b[s.y]); }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        __syncwarp();
-        if(keep) steps[count + __popc(m & ((1u << lane) - 1u))] = s;
-        count += __popc(m);
-        __syncwarp();
-    }
-    return count;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Method 3, stage 1 (src/AssemblerAlign3.cpp:62-239): unbanded DP on the downsampled markers,
 // then the band for stage 2. One warp per candidate.
