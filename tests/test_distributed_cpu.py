@@ -189,9 +189,18 @@ CASES = [
 
 @pytest.mark.parametrize("case_index", range(len(CASES)))
 def test_sharded_lowhash_world2_gloo(case_index, tmp_path):
+    _run_world(2, case_index, tmp_path)
+
+
+def test_sharded_lowhash_world4_gloo(tmp_path):
+    # four ranks: two owner bits for the buckets, pair owners cut on the fine histogram into four unequal readId0 ranges
+    _run_world(4, 0, tmp_path)
+
+
+def _run_world(world, case_index, tmp_path):
     result = tmp_path / "result.txt"
-    port = 29600 + case_index + (os.getpid() % 200)
-    mp.spawn(_worker, args=(2, port, CASES[case_index], str(result)), nprocs=2, join=True)
+    port = 29600 + 10 * world + case_index + (os.getpid() % 200)
+    mp.spawn(_worker, args=(world, port, CASES[case_index], str(result)), nprocs=world, join=True)
     text = result.read_text()
     assert text.startswith("OK"), text
     assert int(text.split()[1]) > 20 and int(text.split()[2]) > 0
