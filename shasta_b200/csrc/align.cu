@@ -106,7 +106,7 @@ struct Batch {
     DeviceBuffer<uint32_t> trace;
     DeviceBuffer<uint2> ordinals, runs;
     DeviceBuffer<int2> endCells;
-    DeviceBuffer<uint32_t> stepCounts;
+    DeviceBuffer<uint32_t> runCounts;
     DeviceBuffer<uint8_t> cdata;
     // method 4
     DeviceBuffer<unsigned long long> cellCnt, cellOff;
@@ -412,7 +412,7 @@ void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs
 }
 
 // Scratch offsets + the banded DP + traceback for nJobs jobs whose lo/hi/state are set.
-void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* sequences, DpScores scores, uint32_t maxWidth,
+void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* sequences, DpScores scores,
                    Events& ev, DpTotals& totals)
 {
     cudaStream_t st = c->stream;
@@ -427,7 +427,7 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     auto t0 = std::chrono::steady_clock::now();
     unsigned long long* total64 = c->scalars.get() + 48;
     b.scanWs64.reserve(scanWorkspaceElements(nJobs));
-    b.twOff.reserve(nJobs); b.outOff.reserve(nJobs); b.counts.reserve(nJobs); b.endCells.reserve(nJobs); b.stepCounts.reserve(nJobs);
+    b.twOff.reserve(nJobs); b.outOff.reserve(nJobs); b.counts.reserve(nJobs); b.endCells.reserve(nJobs); b.runCounts.reserve(nJobs);
     exclusiveScan<unsigned long long>(b.tw.get(), b.twOff.get(), nJobs, total64, b.scanWs64.get(), st);
     const unsigned long long traceWords = readBack<unsigned long long>(total64, st);
     exclusiveScan<unsigned long long>(b.outCnt.get(), b.outOff.get(), nJobs, total64, b.scanWs64.get(), st);
@@ -445,7 +445,6 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     g.kmerIds = sequences; g.scores = scores;
     lap(3, t0);
     SHB_CUDA(cudaEventRecord(ev.a, st));
-    (void)maxWidth;
     // Per chunk: DP (warp per job) on its stream, then traceback (thread per job) and equal-k-mer filter (warp per job)
     // on the high-priority stream.
     AlignCache& ac = cache(c);
@@ -462,7 +461,7 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
         const uint32_t warps = warpsForClass(kClasses[k]);
         const size_t smem = smemForClass(kClasses[k], warps);
         BandedArgs gk = g;
-        gk.n = count; gk.order = b.order + offset; gk.wMin = 0; gk.wMax = kClasses[k].wMax;
+        gk.n = count; gk.order = b.order + offset; gk.wMax = kClasses[k].wMax;
         launchBanded(kClasses[k], ceilDiv(count, warps), warps * 32, smem, s, gk, (const DpJob*)b.jobs.get(), b.trace.get(), b.endCells.get());
         if(unit == ac.unitEvents.size()) {
             cudaEvent_t e = nullptr;
@@ -474,9 +473,9 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
         SHB_CUDA(cudaStreamWaitEvent(hs, ac.unitEvents[unit], 0));
         unit++;
         SHB_LAUNCH(tracebackKernel, ceilDiv(count, 128), 128, 0, hs, count, gk.order, (const DpJob*)b.jobs.get(),
-                   (const int2*)b.endCells.get(), (const uint32_t*)b.trace.get(), b.runs.get(), b.stepCounts.get());
+                   (const int2*)b.endCells.get(), (const uint32_t*)b.trace.get(), b.runs.get(), b.runCounts.get());
         SHB_LAUNCH(filterStepsKernel, ceilDiv(count, 4), 128, 0, hs, count, gk.order, (const DpJob*)b.jobs.get(), sequences,
-                   (const uint2*)b.runs.get(), (const uint32_t*)b.stepCounts.get(), b.ordinals.get(), b.counts.get());
+                   (const uint2*)b.runs.get(), (const uint32_t*)b.runCounts.get(), b.ordinals.get(), b.counts.get());
     });
     for(size_t i = 0; i < std::min<size_t>(unit, AlignCache::kHiStreams); i++) {
         SHB_CUDA(cudaEventRecord(ac.hiJoinEv[i], ac.hiStream[i]));
@@ -625,7 +624,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             SHB_CUDA(cudaEventRecord(dpEv1.a, st));
             forEachClassConcurrently(c, classCounts1, 0xffffffffu, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
                 Method3Args gk = g1;
-                gk.n = count; gk.order = b.order + offset; gk.wMin = 0;
+                gk.n = count; gk.order = b.order + offset;
                 if(k < kForwardClassCount) {
                     gk.wMax = 0;
                     launchStage1Forward(kForwardRows[k], ceilDiv(count, kDpMaxWarpsPerBlock), kDpMaxWarpsPerBlock * 32, s, gk,
@@ -656,7 +655,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 fprintf(stderr, "; active columns %.1f of %.1f per job\n", double(cols) / double(run ? run : 1), double(fullCols) / double(run ? run : 1));
             }
             SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());
-            runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
+            runBandedJobs(c, b, nJobs, c->kmerIds, scores, dpEv2, totals);
             phases.lap(2, st);
             // Epilogue per job == per candidate.
             b.infoWords.reserve(13ull * nJobs);
@@ -688,7 +687,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 SHB_LAUNCH(align4MakeJobsKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb, (const uint64_t*)c->toc.get(),
                            (const unsigned long long*)b.cellOff.get(), (const int32_t*)b.gridBands.get(),
                            (const uint32_t*)b.componentCount.get(), (const uint32_t*)b.jobOffsets.get(), b.jobs.get(), b.tw.get(), b.outCnt.get());
-                runBandedJobs(c, b, nJobs, c->kmerIds, scores, maxStage2Width, dpEv2, totals);
+                runBandedJobs(c, b, nJobs, c->kmerIds, scores, dpEv2, totals);
                 b.infoWords.reserve(13ull * nJobs); b.jobKeep.reserve(nJobs); b.jobBytes.reserve(nJobs);
                 // Align4's own filters (src/Align4.cpp:944-985), identical thresholds, no containment test.
                 SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),

@@ -471,7 +471,7 @@ struct Method3Args {
     const uint64_t* dsToc; const uint32_t* dsKmer; const uint32_t* dsOrdinal;
     DpScores scores;
     int32_t bandExtend, maxBand;
-    uint32_t wMin, wMax;            // wMax = widest padded band of this launch's class (sizes the scan kernel's shared memory)
+    uint32_t wMax;                  // widest padded band of this launch's class (sizes the scan kernel's shared memory)
 };
 
 template<int C> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
@@ -676,7 +676,7 @@ struct BandedArgs {
     const uint32_t* order;          // job indices of this launch's band class, longest first; n = how many
     const uint32_t* kmerIds;
     DpScores scores;
-    uint32_t wMin, wMax;
+    uint32_t wMax;                  // widest padded band of this launch's class (sizes the scan kernel's shared memory)
 };
 
 // Resident blocks per SM the register allocation aims for (the narrow classes are issue-bound and want the warps).
