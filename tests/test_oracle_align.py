@@ -152,3 +152,35 @@ def test_compute_alignments_driver_consistency():
     for i in range(len(r1)):
         ords = B.oracle_decompress(c1[int(t1[i]):int(t1[i + 1])])
         assert len(ords) == r1[i, 9] >= 50
+
+
+def test_alignment_golden_fixtures():
+    """The oracle against tests/golden/align_golden.npz: outputs of the reference's own Align4 / AlignmentInfo / compress code
+    (generated by tests/golden/make_align_golden.py in the build container); needs no reference build at test time."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_align_golden", os.path.join(here, "make_align_golden.py"))
+    MG = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(MG)
+    z = np.load(os.path.join(here, "align_golden.npz"))
+    for name, (synth_spec, count, opts) in MG.ALIGN_CASES.items():
+        o4 = B.make_align_options(**opts)
+        pairs = MG.case_pairs(synth_spec, count)
+        used = z[name + "_pairs"].tolist()
+        atoc, ctoc = z[name + "_align4_toc"], z[name + "_comp_toc"]
+        assert len(used) >= 0.8 * count
+        nonempty = 0
+        for slot, p in enumerate(used):
+            a, b = pairs[p]
+            gold = z[name + "_align4"][int(atoc[slot]):int(atoc[slot + 1])]
+            _, al, tie = B.oracle_align_pair(a, b, o4)
+            assert not tie
+            assert np.array_equal(al.reshape(-1, 2), gold), (name, p)
+            if len(gold):
+                nonempty += 1
+                assert np.array_equal(B.oracle_alignment_info(gold, len(a), len(b)), z[name + "_info"][slot])
+                gbytes = z[name + "_comp"][int(ctoc[slot]):int(ctoc[slot + 1])]
+                assert np.array_equal(B.oracle_compress(gold), gbytes)
+                assert np.array_equal(B.oracle_decompress(gbytes), gold)
+        assert nonempty >= 0.8 * len(used)
