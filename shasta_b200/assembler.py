@@ -195,6 +195,47 @@ class Assembler:
         data = mm_read_vector(self._name("CompressedAlignments.data"), np.uint8, object_size=1)
         self._compressed = (np.asarray(toc), np.asarray(data))
 
+    def computeSortedMarkers(self, threadCount=0):
+        """Assembler::computeSortedMarkers (src/AssemblerAlign4.cpp:190-261, binding src/PythonModule.cpp:210-212).
+        Kept for script compatibility (scripts/ComputeSortedMarkers.py): the markers sorted by k-mer id that Align4 needs are
+        derived on the device from the resident k-mer ids the first time an alignment method 4 call needs them and cached per
+        marker set (csrc/align.cu buildSortedMarkers), so there is no Data/SortedMarkers file to write."""
+        self.checkMarkersAreOpen()
+
+    def accessSortedMarkers(self):
+        """Assembler::accessSortedMarkers (src/PythonModule.cpp:213-214): nothing to open, see computeSortedMarkers."""
+        self.checkMarkersAreOpen()
+
+    def alignOrientedReads4(self, readId0, strand0, readId1, strand1, deltaX, deltaY, minEntryCountPerCell,
+                            maxDistanceFromBoundary, minAlignedMarkerCount, minAlignedFraction, maxSkip, maxDrift, maxTrim,
+                            maxBand, matchScore, mismatchScore, gapScore):
+        """Single-pair Align4 (src/AssemblerAlign4.cpp:13-61, binding src/PythonModule.cpp:302-327; scripts/AlignOrientedReads4.py).
+        Prints the reference's line and returns the number of aligned markers. The pair goes through the same device path as
+        computeAlignments with alignMethod 4, in the orientation that path stores: the lower read id on strand 0 (an oriented
+        pair and its reverse complement / its transpose describe the same alignment; the marker count can differ only where
+        the DP has score ties). matchScore / mismatchScore / gapScore are accepted for signature compatibility: Align4
+        hard-codes 6 / -1 / -1 (src/Align4.hpp:159-161)."""
+        from . import capi
+        self.checkKmersAreOpen()
+        if readId0 == readId1:
+            raise RuntimeError("alignOrientedReads4 needs two different reads.")
+        ctx = self._upload_markers()
+        same = int(strand0 == strand1)
+        cand = np.array([[min(readId0, readId1), max(readId0, readId1), same]], np.uint32)
+        o = capi.make_align_options(alignMethod=4, k=int(self.k), maxSkip=int(maxSkip), maxDrift=int(maxDrift), maxTrim=int(maxTrim),
+                                    minAlignedMarkerCount=int(minAlignedMarkerCount), minAlignedFraction=float(minAlignedFraction),
+                                    maxBand=int(maxBand), matchScore=int(matchScore), mismatchScore=int(mismatchScore),
+                                    gapScore=int(gapScore), suppressContainments=0, align4DeltaX=int(deltaX), align4DeltaY=int(deltaY),
+                                    align4MinEntryCountPerCell=int(minEntryCountPerCell),
+                                    align4MaxDistanceFromBoundary=int(maxDistanceFromBoundary))
+        try:
+            rec, _, _, _ = capi.compute_alignments(ctx, cand, o)
+        except capi.ShastaB200Error as e:
+            raise RuntimeError(str(e)) from None
+        markers = int(rec[0, 9]) if len(rec) else 0
+        print(f"The alignment has {markers} markers.")
+        return markers
+
     # ------------------------------------------------------------------ the two hot-path entry points
     def findAlignmentCandidatesLowHash0(self, m, hashFraction, minHashIterationCount, alignmentCandidatesPerRead,
                                         minBucketSize, maxBucketSize, minFrequency, log2MinHashBucketCount=0, threadCount=0):

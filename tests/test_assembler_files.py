@@ -66,6 +66,55 @@ def test_reader_on_reference_written_files(tiny_data_dir, golden_dir):
         A.Assembler(largeDataFileNamePrefix=tiny_data_dir).checkMarkersAreOpen()
 
 
+def test_companion_accessors_with_stubbed_device(tmp_path, golden_dir, monkeypatch, capsys):
+    """computeSortedMarkers / accessSortedMarkers / alignOrientedReads4 (src/PythonModule.cpp:210-214,302-327): host logic only.
+    The device call is replaced by a stub that records what the facade asks for."""
+    from shasta_b200 import capi
+    z = np.load(os.path.join(golden_dir, "tinytest_markers.npz"))
+    prefix = str(tmp_path / "Data") + "/"
+    os.makedirs(prefix)
+    A.mm_write_vector_of_vectors(prefix + "Markers", z["toc"], z["data"], data_object_size=7)
+    A.mm_write_vector(prefix + "ReadFlags", z["flags"], object_size=1)
+    A.mm_write_vector(prefix + "Kmers", np.zeros((1 << 20) * 24, np.uint8), object_size=24)
+    a = A.Assembler(largeDataFileNamePrefix=prefix)
+    with pytest.raises(RuntimeError, match="not accessible"):
+        a.computeSortedMarkers()
+    a.accessKmers()
+    a.accessMarkers()
+    a.computeSortedMarkers(threadCount=3)
+    a.accessSortedMarkers()
+
+    seen = {}
+
+    class StubContext:
+        def set_markers(self, toc, data, flags):
+            seen["markers"] = len(flags)
+
+    def stub_compute_alignments(ctx, cand, opts):
+        seen["cand"] = np.asarray(cand).copy()
+        seen["opts"] = opts
+        rec = np.zeros((1, 16), np.uint32)
+        rec[0, 9] = 321
+        return rec, np.zeros(2, np.uint64), np.zeros(0, np.uint8), None
+
+    monkeypatch.setattr(a, "_context", lambda: StubContext())
+    a._markers_on_device = False
+    monkeypatch.setattr(capi, "compute_alignments", stub_compute_alignments)
+    kw = dict(deltaX=200, deltaY=10, minEntryCountPerCell=10, maxDistanceFromBoundary=100, minAlignedMarkerCount=10,
+              minAlignedFraction=0.1, maxSkip=100, maxDrift=100, maxTrim=100, maxBand=1000, matchScore=6, mismatchScore=-1, gapScore=-1)
+    n = a.alignOrientedReads4(readId0=7, strand0=1, readId1=3, strand1=0, **kw)
+    assert n == 321 and "The alignment has 321 markers." in capsys.readouterr().out
+    assert seen["markers"] == 20
+    assert seen["cand"].tolist() == [[3, 7, 0]]            # lower read id first, opposite strands
+    o = seen["opts"]
+    assert (o.alignMethod, o.k, o.align4DeltaX, o.align4DeltaY, o.align4MinEntryCountPerCell, o.align4MaxDistanceFromBoundary) == (4, 10, 200, 10, 10, 100)
+    assert (o.maxSkip, o.maxDrift, o.maxTrim, o.maxBand, o.minAlignedMarkerCount, o.suppressContainments) == (100, 100, 100, 1000, 10, 0)
+    a.alignOrientedReads4(readId0=2, strand0=1, readId1=5, strand1=1, **kw)
+    assert seen["cand"].tolist() == [[2, 5, 1]]
+    with pytest.raises(RuntimeError, match="two different reads"):
+        a.alignOrientedReads4(readId0=4, strand0=0, readId1=4, strand1=1, **kw)
+
+
 @pytest.mark.gpu
 def test_script_sequence_on_reference_data_dir(tmp_path, golden_dir):
     # scripts/FindAlignmentCandidatesLowHash0.py + scripts/ComputeAlignments.py call sequence. The Data/ inputs are written
