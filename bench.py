@@ -161,6 +161,29 @@ def run_reference(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
+# The kernels that dominate the step (the banded / unbanded marker DPs) are bound by the integer ALU pipe, not by HBM or
+# the tensor cores (profiles/README.md: 89 % ALU-pipe busy, DRAM a few percent), so next to the contract's `roofline`
+# (the LowHash sweep, HBM by contract) the line carries the DP's own ceiling: the B200's integer ALU rate divided by the
+# ALU operations a DP cell needs.
+ALU_LANES_PER_SM = 64            # INT32 compare/select/min/max lanes per SM and clock (ncu: 2 warp instructions/clk/SM at 100 %)
+SM_COUNT = 148
+ALU_OPS_PER_CELL = 9             # equality test, score select, max, add-max, 2 compares, 2 code selects, trace insert
+
+
+def alignment_roofline(dp_cells, dp_ms, sm_mhz):
+    """dp_cells: DP cells the kernels were asked to fill during the timed steps (band cells incl. the padding to the band
+    class, plus the real cells of the trace-free stage 1); dp_ms: CUDA-event time of the DP launches of those steps
+    (stage 1, stage 2, traceback and filter, as they overlap on their streams)."""
+    if not dp_ms or not dp_cells:
+        return None
+    achieved = dp_cells / (1e-3 * dp_ms) / 1e9
+    peak = SM_COUNT * ALU_LANES_PER_SM * (sm_mhz or 1965.0) * 1e6 / ALU_OPS_PER_CELL / 1e9
+    return {"bound": "alu", "kernels": "bandedAlignKernel<C>, method3Stage1ForwardKernel<R> (+ tracebackKernel, filterStepsKernel overlapped)",
+            "achieved": achieved, "peak": peak, "unit": "G cell updates/s", "frac": achieved / peak,
+            "peak_source": "%d SMs x %d integer-ALU lanes x %.0f MHz / %d ALU operations per DP cell"
+                           % (SM_COUNT, ALU_LANES_PER_SM, sm_mhz or 1965.0, ALU_OPS_PER_CELL)}
+
+
 def _claim_stdout():
     """stdout carries exactly one JSON line. Libraries (NCCL prints its version banner) write to fd 1 directly, so fd 1
     is pointed at stderr for the whole run and the JSON line goes to a private copy of the original stdout."""
@@ -410,6 +433,10 @@ def main():
         "gpu_launches": int(stats_acc["launches"]), "clocks": clocks.summary(),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }
+    try:
+        line["alignment_roofline"] = alignment_roofline(stats_acc["dp_cells"], stats_acc["dp_ms"], (line["clocks"] or {}).get("sm_mhz"))
+    except Exception:       # informational only: never let it cost the bench line
+        line["alignment_roofline"] = None
     print(json.dumps(line), flush=True)
 
 
