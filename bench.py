@@ -28,32 +28,59 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# conf/Nanopore-May2022.conf (+ defaults of src/AssemblerOptions.cpp:327-489)
-MINHASH_MAY2022 = dict(m=4, hashFraction=0.01, minHashIterationCount=10, alignmentCandidatesPerRead=20.0,
-                       log2MinHashBucketCount=0, minBucketSize=5, maxBucketSize=30, minFrequency=5)
-ALIGN_MAY2022 = dict(alignMethod=3, k=14, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
-                     minAlignedFraction=0.1, matchScore=6, mismatchScore=-1, gapScore=-1, downsamplingFactor=0.05,
+# [MinHash] / [Align] values of the reference's configurations (conf/*.conf over the defaults of
+# src/AssemblerOptions.cpp:327-489), the ones BASELINE.json's configs name.
+MINHASH_DEFAULT = dict(m=4, hashFraction=0.01, minHashIterationCount=10, alignmentCandidatesPerRead=20.0,
+                       log2MinHashBucketCount=0, minBucketSize=0, maxBucketSize=10, minFrequency=2)
+ALIGN_DEFAULT = dict(alignMethod=3, k=10, maxSkip=30, maxDrift=30, maxTrim=30, minAlignedMarkerCount=100,
+                     minAlignedFraction=0.4, matchScore=6, mismatchScore=-1, gapScore=-1, downsamplingFactor=0.1,
                      bandExtend=10, maxBand=1000, suppressContainments=0)
+MINHASH_MAY2022 = dict(MINHASH_DEFAULT, minBucketSize=5, maxBucketSize=30, minFrequency=5)                  # conf/Nanopore-May2022.conf
+ALIGN_MAY2022 = dict(ALIGN_DEFAULT, k=14, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
+                     minAlignedFraction=0.1, downsamplingFactor=0.05)
+MINHASH_DEC2019 = dict(MINHASH_DEFAULT, minBucketSize=5, maxBucketSize=30, minFrequency=5)                  # conf/Nanopore-Dec2019.conf
+ALIGN_DEC2019 = dict(ALIGN_DEFAULT, k=10, minAlignedFraction=0.4)
+MINHASH_UL = dict(MINHASH_DEFAULT, minBucketSize=10, maxBucketSize=50, minFrequency=5)                      # conf/Nanopore-UL-May2022.conf
+MINHASH_HIFI = dict(MINHASH_DEFAULT, hashFraction=0.05, minHashIterationCount=100, minFrequency=3,          # conf/HiFi-Oct2021.conf
+                    minBucketSize=10, maxBucketSize=60)
+ALIGN_HIFI = dict(ALIGN_DEFAULT, k=14, downsamplingFactor=0.05, minAlignedFraction=0.97, minAlignedMarkerCount=200,
+                  maxSkip=6, maxDrift=4, maxTrim=2)
 
+NANOPORE = dict(min_bases=10_000, drop=0.12, ins=0.05)
 WORKLOADS = {
     # BASELINE.json configs[1]/[2]: 1M synthetic Nanopore reads (N50 30 kb, ~30x), Nanopore-May2022.conf
-    "nanopore-may2022-1M": dict(reads=1_000_000, n50=30_000, coverage=30.0),
-    # Smaller variants for quick runs
-    "nanopore-may2022-100k": dict(reads=100_000, n50=30_000, coverage=30.0),
-    "nanopore-may2022-10k": dict(reads=10_000, n50=30_000, coverage=30.0),
+    "nanopore-may2022-1M": dict(NANOPORE, reads=1_000_000, n50=30_000, coverage=30.0, minhash=MINHASH_MAY2022, align=ALIGN_MAY2022),
+    "nanopore-may2022-100k": dict(NANOPORE, reads=100_000, n50=30_000, coverage=30.0, minhash=MINHASH_MAY2022, align=ALIGN_MAY2022),
+    "nanopore-may2022-10k": dict(NANOPORE, reads=10_000, n50=30_000, coverage=30.0, minhash=MINHASH_MAY2022, align=ALIGN_MAY2022),
+    # configs[0]: 10k reads N50 20 kb, conf/Nanopore-Dec2019.conf (k = 10, default Align values, minAlignedFraction 0.4)
+    "nanopore-dec2019-10k": dict(NANOPORE, reads=10_000, n50=20_000, coverage=20.0, minhash=MINHASH_DEC2019, align=ALIGN_DEC2019),
+    # configs[3]: ultra-long, 200k reads N50 100 kb (>= 50 kb), conf/Nanopore-UL-May2022.conf; --align-method 4 for the Align4 run
+    "nanopore-ul-200k": dict(min_bases=50_000, drop=0.12, ins=0.05, reads=200_000, n50=100_000, coverage=30.0,
+                             minhash=MINHASH_UL, align=ALIGN_MAY2022),
+    "nanopore-ul-20k": dict(min_bases=50_000, drop=0.12, ins=0.05, reads=20_000, n50=100_000, coverage=30.0,
+                            minhash=MINHASH_UL, align=ALIGN_MAY2022),
+    # configs[4]: HiFi, 2M reads N50 15 kb (>= 8 kb), low error, conf/HiFi-Oct2021.conf (hashFraction 0.05, 100 iterations)
+    "hifi-2M": dict(min_bases=8_000, drop=0.004, ins=0.002, reads=2_000_000, n50=15_000, coverage=30.0,
+                    minhash=MINHASH_HIFI, align=ALIGN_HIFI),
+    "hifi-200k": dict(min_bases=8_000, drop=0.004, ins=0.002, reads=200_000, n50=15_000, coverage=30.0,
+                      minhash=MINHASH_HIFI, align=ALIGN_HIFI),
 }
 CPU_SAMPLE_READS = int(os.environ.get("SHB_CPU_SAMPLE_READS", "20000"))   # bounded sample: same coverage, smaller genome
+POLICY_SAMPLE_CANDIDATES = int(os.environ.get("SHB_POLICY_SAMPLE", "40000"))
+M64 = (1 << 64) - 1
 
 
-def synth_params(reads, n50, coverage, seed=1):
+def synth_params(wl, reads=None, seed=1):
+    """Marker-space read set of a workload (reads overrides the read count: the CPU sample keeps the coverage)."""
     from shasta_b200 import synth
+    reads = reads or wl["reads"]
     mean_gap = 13.55
-    mean_len = n50 * np.exp(-0.5 * 0.5 ** 2)          # log-normal: mean = N50 * exp(-sigma^2/2)
+    mean_len = wl["n50"] * np.exp(-0.5 * 0.5 ** 2)          # log-normal: mean = N50 * exp(-sigma^2/2)
     span = mean_len / mean_gap
-    genome_markers = int(max(reads * span / coverage, 4 * span))
-    return synth.SynthParams(reads=reads, k=14, genome_markers=genome_markers, mean_gap=mean_gap, n50_bases=n50,
-                             sigma=0.5, min_bases=10_000, drop=0.12, ins=0.05, repeat_period=5000, repeat_len=200,
-                             seed=seed)
+    genome_markers = int(max(reads * span / wl["coverage"], 4 * span))
+    return synth.SynthParams(reads=reads, k=wl["align"]["k"], genome_markers=genome_markers, mean_gap=mean_gap, n50_bases=wl["n50"],
+                             sigma=0.5, min_bases=wl["min_bases"], drop=wl["drop"], ins=wl["ins"], repeat_period=5000,
+                             repeat_len=200, seed=seed)
 
 
 class ClockSampler:
@@ -109,13 +136,13 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_once(d, cores):
+def cpu_reference_once(d, cores, minhash, align, keep=False):
     """The reference's CPU path on one read set: LowHash0 through the unmodified reference TUs (oracle/_ref) when they
-    are present (else the oracle port), then computeAlignments method 3 through the oracle port (reference control flow
+    are present (else the oracle port), then computeAlignments through the oracle port (reference control flow
     restated + the SeqAn stand-in DP; 'not SeqAn'), one thread per core.
-    Returns (candidates, lowhash seconds, stored alignments, alignment seconds, kind)."""
+    Returns dict(candidates, lowhash_s, alignments, align_s, kind[, cand, rec, ctoc, cdata, ties])."""
     from oracle import bindings as B
-    bp = B.LowHashParams(**MINHASH_MAY2022)
+    bp = B.LowHashParams(**minhash)
     if B.have_ref():
         c, _, _, sec_l = B.ref_lowhash0(d["toc"], d["data"], d["flags"], bp, threads=cores)
         kind = "reference"
@@ -124,36 +151,79 @@ def cpu_reference_once(d, cores):
         c, _, _ = B.oracle_lowhash0(d["toc"], d["data"], d["flags"], bp)
         sec_l = time.perf_counter() - t0
         kind = "port"
-    oo = B.make_align_options(**{k: v for k, v in ALIGN_MAY2022.items() if k in B.ALIGN_DEFAULTS})
+    oo = B.make_align_options(**{k: v for k, v in align.items() if k in B.ALIGN_DEFAULTS})
     t0 = time.perf_counter()
-    rec, _, _, _ = B.oracle_compute_alignments(d["toc"], d["kmer"], c, oo, threads=cores)
+    rec, ctoc, cdata, ties = B.oracle_compute_alignments(d["toc"], d["kmer"], c, oo, threads=cores)
     sec_a = time.perf_counter() - t0
-    return len(c), sec_l, len(rec), sec_a, kind
+    out = dict(candidates=len(c), lowhash_s=sec_l, alignments=len(rec), align_s=sec_a, kind=kind)
+    if keep:
+        out.update(cand=c, rec=rec, ctoc=ctoc, cdata=cdata, ties=ties)
+    return out
+
+
+def policy_exposure(d, cand, align, cores):
+    """How many candidate pairs are exposed to the (SeqAn-unpinned) tie-break rules of the DP at all: the oracle is run
+    under all 8 policies of include/shb_dp_policy.h on a bounded slice of the sample's candidates; a pair is invariant
+    when its stored result (kept or not, AlignmentData, compressed bytes) is the same under every policy."""
+    from oracle import bindings as B
+    cand = np.ascontiguousarray(cand[:POLICY_SAMPLE_CANDIDATES])
+    oo = B.make_align_options(**{k: v for k, v in align.items() if k in B.ALIGN_DEFAULTS})
+    default = B.default_dp_policy()
+    keys = (cand[:, 0].astype(np.uint64) << np.uint64(33)) | (cand[:, 1].astype(np.uint64) << np.uint64(1)) | (cand[:, 2] & 1).astype(np.uint64)
+
+    def per_candidate(rec, ctoc, cdata):
+        # one 64-bit value per candidate: 0 = not stored, else a hash of its record and compressed bytes
+        h = np.zeros(len(cand), np.uint64)
+        if len(rec):
+            rk = (rec[:, 0].astype(np.uint64) << np.uint64(33)) | (rec[:, 1].astype(np.uint64) << np.uint64(1)) | (rec[:, 2] & 1).astype(np.uint64)
+            order = np.argsort(keys, kind="stable")                  # candidate keys are unique
+            pos = order[np.searchsorted(keys[order], rk)]
+            with np.errstate(over="ignore"):
+                v = np.full(len(rec), 0xcbf29ce484222325, np.uint64)
+                for k in range(16):
+                    v = (v ^ rec[:, k].astype(np.uint64)) * np.uint64(0x100000001b3)
+                csum = np.concatenate([np.zeros(1, np.uint64), np.cumsum(cdata.astype(np.uint64) * (np.arange(len(cdata), dtype=np.uint64) % np.uint64(251) + np.uint64(1)))])
+                v ^= (csum[ctoc[1:].astype(np.int64)] - csum[ctoc[:-1].astype(np.int64)]) + (ctoc[1:] - ctoc[:-1]).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+            h[pos] = v | np.uint64(1)
+        return h
+    try:
+        base = per_candidate(*B.oracle_compute_alignments(d["toc"], d["kmer"], cand, oo, threads=cores)[:3])
+        differs = np.zeros(len(cand), bool)
+        for policy in range(8):
+            if policy == default:
+                continue
+            B.set_dp_policy(policy)
+            differs |= per_candidate(*B.oracle_compute_alignments(d["toc"], d["kmer"], cand, oo, threads=cores)[:3]) != base
+    finally:
+        B.set_dp_policy(default)
+    return {"candidates": int(len(cand)), "policy_invariant_fraction": float(1.0 - differs.mean()) if len(cand) else None,
+            "policies": 8, "default_policy_bits": int(default)}
 
 
 def run_reference(args, wl, rank):
     if rank != 0:
         return
     from shasta_b200 import synth
-    p = synth_params(CPU_SAMPLE_READS, wl["n50"], wl["coverage"], seed=2)
+    p = synth_params(wl, reads=min(CPU_SAMPLE_READS, wl["reads"]), seed=2)
     d = synth.generate(p)
     cores = os.cpu_count()
     for _ in range(args.warmup):
-        cpu_reference_once(d, cores)
+        cpu_reference_once(d, cores, wl["minhash"], wl["align"])
     tl = ta = 0.0
     for _ in range(args.steps):
-        n, sec_l, nal, sec_a, kind = cpu_reference_once(d, cores)
-        tl += sec_l
-        ta += sec_a
+        r = cpu_reference_once(d, cores, wl["minhash"], wl["align"])
+        tl += r["lowhash_s"]
+        ta += r["align_s"]
+    n, nal, kind = r["candidates"], r["alignments"], r["kind"]
     value = n * args.steps / (tl + ta)
     M = int(d["toc"][-1])
-    sample = (f"{CPU_SAMPLE_READS} synthetic reads ({M} markers both strands, {wl['coverage']}x, same generator/config), "
+    sample = (f"{p.reads} synthetic reads ({M} markers both strands, {wl['coverage']}x, same generator/config), "
               f"{n} candidates, {nal} stored alignments; LowHash0 {tl / args.steps:.2f} s ({kind}), alignment {ta / args.steps:.2f} s (port)")
     line = {
         "impl": "reference", "metric": "candidate_pairs_found_and_aligned_per_s", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tl + ta) / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/i32", "data": "synthetic",
-        "config": {"workload": args.workload, "minhash": MINHASH_MAY2022, "align": ALIGN_MAY2022, "sample": sample},
+        "config": {"workload": args.workload, "minhash": wl["minhash"], "align": wl["align"], "sample": sample},
         "lowhash_pairs_per_s": n * args.steps / tl, "aligned_pairs_per_s": n * args.steps / ta,
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -207,8 +277,9 @@ def main():
     ap.add_argument("--align-method", type=int, default=3, choices=[3, 4],
                     help="3 = what Nanopore-May2022.conf selects (default); 4 = Align4, --Align.alignMethod 4")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    ALIGN_MAY2022["alignMethod"] = args.align_method
+    wl = dict(WORKLOADS[args.workload])
+    wl["align"] = dict(wl["align"], alignMethod=args.align_method)
+    MINHASH, ALIGN = wl["minhash"], wl["align"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -244,8 +315,18 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def allsum_u64(x):
+        """Sum of 64-bit digests over the ranks, mod 2^64 (gathered as two 32-bit halves: exact)."""
+        x = int(x) & M64
+        if world == 1:
+            return x
+        t = torch.tensor([x & 0xffffffff, x >> 32], dtype=torch.int64, device="cuda")
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return sum(int(q[0].item()) | (int(q[1].item()) << 32) for q in parts) & M64
+
     # ---- synthetic input, generated on the device; the same read set for every N (strong scaling) ----------------
-    p = synth_params(wl["reads"], wl["n50"], wl["coverage"], seed=1)
+    p = synth_params(wl, seed=1)
     R = p.reads
     ctx = capi.Context(local_rank)
     t0 = time.perf_counter()
@@ -260,15 +341,16 @@ def main():
     M_local = dm.marker_count
     M = int(allsum(M_local))
     gen_s = time.perf_counter() - t0
-    lparams = capi.make_lowhash_params(**MINHASH_MAY2022)
-    aopts = capi.make_align_options(**ALIGN_MAY2022)
+    lparams = capi.make_lowhash_params(**MINHASH)
+    aopts = capi.make_align_options(**ALIGN)
     ctx.set_markers_device(dm.toc, dm.kmer_ptr, dm.flags, keepalive=dm, read_begin=rb, read_end=re,
                            read_count_total=R, total_marker_count=M)
     stages = D.CudaStages(ctx, local_rank) if world > 1 else None
     actx = capi.Context(local_rank) if world > 1 else ctx       # alignment context (all rows resident)
 
     stats_acc = {"sweep_ms": 0.0, "sweep_launches": 0, "launches": 0, "lowhash_s": 0.0, "align_s": 0.0, "gather_s": 0.0,
-                 "dp_ms": 0.0, "dp_cells": 0, "alignments": 0}
+                 "dp_ms": 0.0, "dp_cells": 0, "dp_useful_cells": 0, "alignments": 0}
+    last = {}
 
     def step(record, host_data7=None):
         """One pass of the hot path. host_data7 != None: end-to-end mode, the marker records come from (pinned) host
@@ -281,13 +363,14 @@ def main():
             cand, _, _, res = ctx.lowhash0(lparams, want_stats=True)
             sweep_ms, sweep_launches, launches = res.sweepMs, res.sweepLaunches, res.kernelLaunches
         else:
-            cand, _, info = D.lowhash0_sharded(stages, MINHASH_MAY2022, R)
+            cand, _, info = D.lowhash0_sharded(stages, MINHASH, R)
             if record:
                 for k, v in info["timing_s"].items():
                     stats_acc["sharded_" + k] = stats_acc.get("sharded_" + k, 0.0) + v
-            cand = D.rebalance_candidates(cand)
             res = stages.counters()
+            cand = D.rebalance_candidates(cand)
             sweep_ms, sweep_launches, launches = res.sweepMs, res.sweepLaunches, res.kernelLaunches
+        last["candidate_digest"] = res.candidateDigest
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         nal = 0
@@ -303,9 +386,12 @@ def main():
             nal = len(rec)
             d2h += rec.nbytes + ctoc.nbytes + cdata.nbytes
             launches += ares.kernelLaunches
+            last.update(alignment_data_digest=ares.alignmentDataDigest, compressed_digest=ares.compressedDigest,
+                        skipped=ares.skippedCount, too_wide=ares.tooWideCount, workers=ares.workers)
             if record:
                 stats_acc["dp_ms"] += ares.dpMs
                 stats_acc["dp_cells"] += ares.dpCells
+                stats_acc["dp_useful_cells"] += ares.dpUsefulCells
                 stats_acc["align_copy_ms"] = stats_acc.get("align_copy_ms", 0.0) + ares.outputCopyMs
                 stats_acc["align_lib_ms"] = stats_acc.get("align_lib_ms", 0.0) + ares.hostWallMs
         torch.cuda.synchronize()
@@ -340,8 +426,16 @@ def main():
     lowhash_s = allmax(stats_acc["lowhash_s"])
     align_s = allmax(stats_acc["align_s"] + stats_acc["gather_s"])
     value = total_cand * args.steps / wall
+    # Order-independent digests of what the last timed step produced, summed over the ranks: equal for every N, and equal
+    # to the digests of the CPU path's output on the same input (checked on the sample below and in tests/).
+    digests = {"candidates": "%016x" % allsum_u64(last.get("candidate_digest", 0)),
+               "alignment_data": "%016x" % allsum_u64(last.get("alignment_data_digest", 0)),
+               "compressed_alignments": "%016x" % allsum_u64(last.get("compressed_digest", 0)),
+               "definition": "include/shasta_b200.h: shb_digest_records / shb_digest_compressed (sum of per-record FNV-1a values mod 2^64)"}
+    skipped_total, too_wide_total = int(allsum(last.get("skipped", 0))), int(allsum(last.get("too_wide", 0)))
+    dp_cells_all, dp_useful_all, dp_ms_max = allsum(stats_acc["dp_cells"]), allsum(stats_acc["dp_useful_cells"]), allmax(stats_acc["dp_ms"])
 
-    # ---- end to end through the reference-facing calls with host buffers (single GPU) ------------------------------
+    # ---- end to end through the reference-facing calls with host buffers ------------------------------------------------
     e2e = None
     if want_e2e:
         host = torch.empty(M_local * 7, dtype=torch.uint8, pin_memory=True)
@@ -356,11 +450,13 @@ def main():
         barrier()
         e2e_wall = allmax(time.perf_counter() - t0)
         assert allsum(len(c2)) == total_cand and allsum(n2) == total_al, "host-buffer path and device-resident path disagree"
+        assert "%016x" % allsum_u64(last.get("alignment_data_digest", 0)) == digests["alignment_data"], "host-buffer path digest differs"
         if world == 1:
             assert np.array_equal(c2, cand)
         e2e = {"value": total_cand * e2e_steps / e2e_wall, "unit": "pairs/s",
                "h2d_bytes_per_step": int(allsum(M_local * 7 + dm.toc.nbytes + dm.flags.nbytes + (0 if args.no_align else len(c2) * 12))),
                "d2h_bytes_per_step": int(allsum(stats_acc["last_d2h"])), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps}
+        del host, data7
         # restore the device-resident markers for anything that follows
         ctx.set_markers_device(dm.toc, dm.kmer_ptr, dm.flags, keepalive=dm, read_begin=rb, read_end=re,
                                read_count_total=R, total_marker_count=M)
@@ -370,8 +466,8 @@ def main():
         return
 
     # ---- roofline of the dominant LowHash kernel (hash sweep) -------------------------------------------------------
-    iters = MINHASH_MAY2022["minHashIterationCount"]
-    frac_h = MINHASH_MAY2022["hashFraction"]
+    iters = MINHASH["minHashIterationCount"]
+    frac_h = MINHASH["hashFraction"]
     bytes_per_marker_iteration = 4.0 + 16.0 * frac_h
     launches = max(stats_acc["sweep_launches"], 1)
     iters_per_launch = iters * args.steps / launches
@@ -388,38 +484,74 @@ def main():
             traffic = tj["dram_bytes_per_marker_per_launch"] * M_local
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "lowhashSweepKernel<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "lowhashSweepKernel<%d>" % MINHASH["m"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "note": "achieved = ALGORITHMIC bytes (SURVEY 8d: M x (4 + 16 x hashFraction) per iteration, x iterations fused per "
+                        "launch) / CUDA-event launch time: an algorithmic-equivalent bandwidth. One launch reads the k-mer ids once for "
+                        "all its fused iterations, so the DRAM bytes actually moved (`traffic`) are a fraction of the algorithmic "
+                        "bytes; the kernel is bound by integer instruction issue (3 dependent 64-bit multiplies per feature and "
+                        "iteration), not by HBM.",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": 1e3 * avg_launch_s,
                 "iterations_fused_per_launch": iters_per_launch, "sweep_share_of_step": 1e-3 * sweep_ms / wall,
                 "alignment_gcups": (stats_acc["dp_cells"] / (1e-3 * stats_acc["dp_ms"]) / 1e9) if stats_acc["dp_ms"] else None}
 
+    # ---- the reference's CPU path on a bounded sample, and the GPU path on that SAME sample: parity at bench scale ------
     cpu_baseline = None
+    parity = None
     if not args.no_cpu_baseline and world == 1:
-        ps = synth_params(CPU_SAMPLE_READS, wl["n50"], wl["coverage"], seed=2)
+        ps = synth_params(wl, reads=min(CPU_SAMPLE_READS, wl["reads"]), seed=2)
         # Same generator as the numpy one (bit-identical), run on the device to save minutes of host time.
         dms = capi.synth_generate_device(ctx, ps, want_data7=True)
         d = {"toc": dms.toc, "data": dms.data7_to_host(), "flags": dms.flags, "kmer": dms.kmer_ids_to_host()}
-        dms.free()
         cores = os.cpu_count()
-        n, sec_l, nalc, sec_a, kind = cpu_reference_once(d, cores)
+        r = cpu_reference_once(d, cores, MINHASH, ALIGN, keep=True)
+        n, sec_l, nalc, sec_a, kind = r["candidates"], r["lowhash_s"], r["alignments"], r["align_s"], r["kind"]
         Ms = int(d["toc"][-1])
         cpu_baseline = {"value": n / (sec_l + sec_a), "unit": "pairs/s", "cores": cores, "kind": kind,
-                        "sample": f"{CPU_SAMPLE_READS} synthetic reads ({Ms} markers both strands, same coverage/config), {n} candidates, "
+                        "sample": f"{ps.reads} synthetic reads ({Ms} markers both strands, same coverage/config), {n} candidates, "
                                   f"{nalc} stored alignments; LowHash0 {sec_l:.2f} s ({kind}: unmodified reference TUs), "
                                   f"alignment {sec_a:.2f} s (port: reference control flow + SeqAn stand-in DP)",
                         "lowhash_pairs_per_s": n / sec_l, "aligned_pairs_per_s": n / sec_a}
+        # GPU on the sample, through the same C-ABI calls; every output compared with the CPU path's.
+        sctx = capi.Context(local_rank)
+        sctx.set_markers_device(dms.toc, dms.kmer_ptr, dms.flags, keepalive=dms)
+        gc, gstats, _, gres = sctx.lowhash0(lparams, want_stats=True)
+        parity = {"sample_reads": ps.reads, "candidates": int(len(gc)), "candidates_identical": bool(np.array_equal(gc, r["cand"]))}
+        if not args.no_align:
+            grec, gtoc, gdata, gares = capi.compute_alignments(sctx, gc, aopts)
+            parity.update(alignments=int(len(grec)),
+                          alignment_data_identical=bool(np.array_equal(grec, r["rec"])),
+                          compressed_identical=bool(np.array_equal(gtoc, r["ctoc"]) and np.array_equal(gdata, r["cdata"])),
+                          digests_match_cpu=bool(gares.alignmentDataDigest == capi.digest_records(r["rec"], 16)
+                                                 and gares.compressedDigest == capi.digest_compressed(r["rec"], r["ctoc"], r["cdata"])
+                                                 and gres.candidateDigest == capi.digest_candidates(r["cand"])))
+            ties = r["ties"]
+            parity["dp_tie_free_fraction"] = float(((ties & 6) == 0).mean()) if len(ties) else None
+            parity["dp_tie_free_definition"] = ("fraction of the sample's candidate pairs none of whose DP paths passes through a cell with "
+                                                "co-optimal predecessors or ends in a tied end cell (upper bound on the exposure to the "
+                                                "SeqAn-unpinned tie-break rules)")
+            parity["align4_component_tie_fraction"] = float((ties & 1).mean()) if len(ties) else None
+            try:
+                parity["policy_sweep"] = policy_exposure(d, r["cand"], ALIGN, cores)
+            except Exception as e:            # informational: never lose the line over it
+                parity["policy_sweep"] = {"error": str(e)}
+        sctx.close()
+        dms.free()
+        ok = parity["candidates_identical"] and parity.get("alignment_data_identical", True) and parity.get("compressed_identical", True)
+        assert ok, f"GPU and CPU paths disagree on the {ps.reads}-read sample: {parity}"
 
+    useful = stats_acc["dp_useful_cells"]
     line = {
         "metric": "candidate_pairs_found_and_aligned_per_s", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/i32", "data": "synthetic",
-        "config": {"workload": args.workload, "reads": R, "markers": M, "minhash": MINHASH_MAY2022, "align": ALIGN_MAY2022,
+        "config": {"workload": args.workload, "reads": R, "markers": M, "minhash": MINHASH, "align": ALIGN,
                    "parallelism": ("reads sharded by id over %d GPUs, bucket all-to-all per LowHash iteration, markers all-gathered for alignment" % world)
                    if world > 1 else "single GPU",
                    "l2": "inputs (k-mer ids %.1f GB) larger than L2" % (4e-9 * M_local), "generation_s": gen_s,
                    "align_included": not args.no_align},
-        "candidates": total_cand, "alignments": total_al,
+        "candidates": total_cand, "alignments": total_al, "skipped_candidates": skipped_total, "too_wide_candidates": too_wide_total,
+        "digests": digests, "parity_on_cpu_sample": parity,
         "lowhash_pairs_per_s": total_cand * args.steps / lowhash_s,
         "aligned_pairs_per_s": (total_cand * args.steps / align_s) if align_s else None,
         "lowhash_ms_per_step": 1e3 * lowhash_s / args.steps, "align_ms_per_step": 1e3 * align_s / args.steps,
@@ -429,7 +561,12 @@ def main():
         "gather_ms_per_step": 1e3 * stats_acc["gather_s"] / args.steps,
         "align_breakdown_ms_per_step": {"dp_kernels": stats_acc["dp_ms"] / args.steps,
                                         "result_copy_to_host": stats_acc.get("align_copy_ms", 0.0) / args.steps,
-                                        "library_call": stats_acc.get("align_lib_ms", 0.0) / args.steps},
+                                        "library_call": stats_acc.get("align_lib_ms", 0.0) / args.steps,
+                                        "workers": last.get("workers")},
+        "dp_cells": {"useful_per_step": useful / args.steps, "computed_per_step": stats_acc["dp_cells"] / args.steps,
+                     "useful_g_per_s": (dp_useful_all / (1e-3 * dp_ms_max) / 1e9) if dp_ms_max else None,
+                     "note": "useful = in-band, in-matrix cells (what the reference's DP fills) + the unbanded stage-1 cells; computed also "
+                             "counts the padding of the band classes to multiples of 64 offsets and the two barrier offsets"},
         "gpu_launches": int(stats_acc["launches"]), "clocks": clocks.summary(),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }

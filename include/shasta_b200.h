@@ -104,6 +104,9 @@ typedef struct {
     double   totalMs;               /* device time of the whole call */
     uint64_t sweepLaunches;         /* number of sweep kernel launches */
     uint64_t kernelLaunches;        /* all kernels launched by the call */
+    uint64_t candidateDigest;       /* order-independent digest of the emitted candidates (shb_digest_records of the
+                                       12-byte records as 3 words), computed on the device; for sharded runs the sum
+                                       of the ranks' digests (mod 2^64) equals the single-GPU digest */
 } shb_lowhash_result;
 
 /* One-shot single-GPU call on the markers held by ctx.
@@ -165,7 +168,8 @@ shb_status shb_lowhash_counters(shb_context* ctx, shb_lowhash_result* result);
  * (src/AssemblerKmers.cpp:182-186) is recomputed from it instead of reading the 4^k-entry Data/Kmers table.
  */
 typedef struct {
-    int32_t  alignMethod;            /* 3 (what every shipped conf selects) or 4 (Align4); 0/1 are not on the path */
+    int32_t  alignMethod;            /* 3 (what every shipped conf selects), 4 (Align4) or 1 (unbanded SeqAn-style DP on all
+                                        markers, src/AssemblerAlign1.cpp); 0 (AlignmentGraph) is not on the path */
     int32_t  maxSkip;
     int32_t  maxDrift;
     int32_t  maxTrim;
@@ -198,7 +202,24 @@ typedef struct {
     uint64_t kernelLaunches;
     double   outputCopyMs;          /* host wall time of the final device->host copy of the results */
     double   hostWallMs;            /* host wall time of the whole call */
+    uint64_t dpUsefulCells;         /* ... of which in-band, in-matrix cells (what the reference's DP fills; dpCells also counts
+                                       the padding of the band classes and the barrier offsets) */
+    uint64_t tooWideCount;          /* candidates skipped because their unbanded stage needs a band wider than 16384 offsets
+                                       (included in skippedCount; the reference has no such limit) */
+    uint64_t workers;               /* host worker threads (streams) the batches were spread over */
+    uint64_t alignmentDataDigest;   /* order-independent digests of the AlignmentData records (16 words each) and of the */
+    uint64_t compressedDigest;      /* compressed alignments (pair + bytes), computed on the device: additive over any
+                                       partition of the candidates (multi-GPU parity: sum of the ranks' digests) */
 } shb_align_result;
+
+/* The digest used above, on host buffers (for checking results that came from somewhere else, e.g. the CPU path):
+ *   per record of `words` uint32 words: h = 0xcbf29ce484222325; for each word: h = (h ^ word) * 0x100000001b3;
+ *   h ^= h >> 32;  the digest is the sum of the records' h (mod 2^64).                                              */
+uint64_t shb_digest_records(const uint32_t* records, uint64_t count, uint32_t words);
+/* Compressed alignments: per alignment the same FNV chain over readId0, readId1, isSameStrand (from its 64-byte
+ * AlignmentData record) and then its compressed bytes one by one; summed. */
+uint64_t shb_digest_compressed(const uint32_t* alignmentData, uint64_t count, const uint64_t* compressedToc,
+                               const uint8_t* compressedData);
 
 /* Computes the marker alignment of every candidate on the markers held by ctx (all reads must be
  * resident on this GPU).
@@ -216,6 +237,20 @@ shb_status shb_compute_alignments(shb_context* ctx, const void* candidates, uint
                                   uint64_t** compressedToc, uint8_t** compressedData,
                                   shb_align_result* result);
 
+/* One pair of oriented reads, in exactly the orientation given (orientedReadId = (readId<<1)|strand). Replaces the
+ * single-pair members Assembler::alignOrientedReads4 (src/AssemblerAlign4.cpp:13-61; Python src/PythonModule.cpp:302-327),
+ * alignOrientedReads3 (src/AssemblerAlign3.cpp:23-313) and alignOrientedReads1 (src/AssemblerAlign1.cpp:129-148), selected by
+ * options->alignMethod. The pair goes through the same device path as shb_compute_alignments, so the thresholds in
+ * `options` apply (pass permissive ones for the unfiltered single-pair semantics of methods 1 and 3; Align4 applies the same
+ * thresholds internally, src/Align4.cpp:944-985) and suppressContainments should be 0.
+ *   ordinals      : receives uint32[2*markerCount] (ordinal0, ordinal1) pairs of the alignment, or NULL when no alignment
+ *                   passes; free with shb_free.
+ *   alignmentInfo : optional, 13 words = words 3..15 of the AlignmentData record (AlignmentInfo, src/Alignment.hpp:86-200).
+ */
+shb_status shb_align_oriented_reads(shb_context* ctx, uint32_t orientedReadId0, uint32_t orientedReadId1,
+                                    const shb_align_options* options, uint32_t** ordinals, uint64_t* markerCount,
+                                    uint32_t* alignmentInfo13);
+
 /* Replaces Assembler::computeAlignmentTable (src/AssemblerAlign.cpp:509-571): for every oriented read the
  * indices of the alignments it is involved in (4 entries per alignment: both reads x both strands), each row
  * sorted by the other OrientedReadId (OrientedReadPair::getOther, src/OrientedReadPair.hpp:63-85).
@@ -225,6 +260,16 @@ shb_status shb_compute_alignments(shb_context* ctx, const void* candidates, uint
  */
 shb_status shb_compute_alignment_table(shb_context* ctx, const void* alignmentData, uint64_t alignmentCount,
                                        uint64_t readCount, uint32_t** tableToc, uint32_t** tableData);
+
+/* Replaces AlignmentCandidates::computeCandidateTable (src/AssemblerAlignmentCandidates.cpp:379-448): for every
+ * oriented read the indices of the candidates it is involved in (4 entries per candidate: both reads x both
+ * strands), each row sorted by (other OrientedReadId, candidate index).
+ *   candidates : n 12-byte OrientedReadPair records (host).
+ *   tableToc   : receives uint64[2*readCount+1]; tableData: uint64[4n]  (= Data/CandidateTable.toc/.data payload,
+ *                VectorOfVectors<uint64_t,uint64_t>, src/AlignmentCandidates.hpp:38). Free both with shb_free.
+ */
+shb_status shb_compute_candidate_table(shb_context* ctx, const void* candidates, uint64_t candidateCount,
+                                       uint64_t readCount, uint64_t** tableToc, uint64_t** tableData);
 
 /* ------------------------------------------------------------------------------------------
  * Bench / test utilities (not part of the reference's interface): the marker-space synthetic read

@@ -20,7 +20,8 @@
  *     container, and no reference test pins its output). Scores are those of any correct overlap
  *     alignment; the TIE-BREAK rule among equal-score paths follows SURVEY.md Appendix A
  *     (diagonal > vertical > horizontal; first strict maximum in column-major order over last-row /
- *     last-column cells) and is isolated in this one function.
+ *     last-column cells), lives in include/shb_dp_policy.h (shared with the CUDA kernels) and is applied in this one
+ *     function, which also records whether the chosen path was exposed to a tie at all.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -34,6 +35,34 @@ uint32_t orc_murmurhash2(const void* key, int len, uint32_t seed);
 uint32_t orc_kmer_downsampling_hash(uint32_t kmerId, uint32_t k);
 
 #define ORC_MIN_VALUE INT_MIN     /* seqan::MinValue<int>::VALUE */
+
+/* ---------------------------------------------------------------------------------------------
+ * Tie-break policy of the DP: compile-time default from include/shb_dp_policy.h (shared with the CUDA
+ * kernels), switchable at run time so that the exposure of a data set to the choice can be measured.
+ * bit 0: diagonal wins ties against a gap move; bit 1: vertical before horizontal; bit 2: first maximum
+ * (column-major) is the end cell.
+ */
+#include "../include/shb_dp_policy.h"
+static int orc_dp_policy = SHB_DP_POLICY_BITS;
+void orc_set_dp_policy(int bits) { orc_dp_policy = bits & 7; }
+int orc_get_dp_policy(void) { return orc_dp_policy; }
+
+/* Tie exposure of the DP calls made by the calling thread since the last reset:
+ * bit 0: some cell ON THE CHOSEN PATH had two or more predecessors giving its score (a co-optimal
+ *        path branches off there); bit 1: another end-cell candidate had the best score. */
+static __thread int orc_tls_tie = 0;
+void orc_reset_tie_flags(void) { orc_tls_tie = 0; }
+int orc_get_tie_flags(void) { return orc_tls_tie; }
+
+/* Per-thread scratch of the DP (grow-only; one DP call per candidate and stage would otherwise malloc/free
+ * a trace of nx*W bytes each time). */
+static __thread uint8_t* tlsTrace = NULL; static __thread size_t tlsTraceCap = 0;
+static __thread int32_t* tlsRows = NULL;  static __thread size_t tlsRowsCap = 0;
+void orc_release_thread_scratch(void)
+{
+    free(tlsTrace); tlsTrace = NULL; tlsTraceCap = 0;
+    free(tlsRows); tlsRows = NULL; tlsRowsCap = 0;
+}
 
 /* ---------------------------------------------------------------------------------------------
  * Overlap alignment, linear gaps, all four end gaps free, optional band lo <= i - j <= hi where
@@ -52,13 +81,17 @@ int orc_overlap_align(const uint32_t* a, int64_t nx, const uint32_t* b, int64_t 
     if(lo > hi || hi < -ny || lo > nx) return ORC_MIN_VALUE;
     if(lo < -ny) lo = -ny;
     if(hi > nx) hi = nx;
+    const int diagWins = orc_dp_policy & 1, vertFirst = (orc_dp_policy >> 1) & 1, endFirst = (orc_dp_policy >> 2) & 1;
     const int64_t W = hi - lo + 1;                 /* cells per column at most */
-    uint8_t* trace = (uint8_t*)malloc((size_t)(nx + 1) * (size_t)W);
-    int32_t* prev = (int32_t*)malloc(sizeof(int32_t) * (size_t)(W + 2));
-    int32_t* cur = (int32_t*)malloc(sizeof(int32_t) * (size_t)(W + 2));
+    const size_t traceBytes = (size_t)(nx + 1) * (size_t)W;
+    if(traceBytes > tlsTraceCap) { free(tlsTrace); tlsTraceCap = traceBytes + traceBytes / 4 + 4096; tlsTrace = (uint8_t*)malloc(tlsTraceCap); }
+    if((size_t)(2 * (W + 2)) > tlsRowsCap) { free(tlsRows); tlsRowsCap = (size_t)(2 * (W + 2)) + 1024; tlsRows = (int32_t*)malloc(sizeof(int32_t) * tlsRowsCap); }
+    uint8_t* trace = tlsTrace;
+    int32_t* prev = tlsRows;
+    int32_t* cur = tlsRows + (W + 2);
     int64_t prevLo = 0, prevHi = -1;
-    int best = ORC_MIN_VALUE; int64_t bi = -1, bj = -1; int haveBest = 0;
-    enum { T_NONE = 0, T_DIAG = 1, T_VERT = 2, T_HORZ = 3 };
+    int best = ORC_MIN_VALUE; int64_t bi = -1, bj = -1; int haveBest = 0, endTie = 0;
+    enum { T_NONE = 0, T_DIAG = 1, T_VERT = 2, T_HORZ = 3, T_TIE = 4 };
 
     for(int64_t i = 0; i <= nx; i++) {
         int64_t jlo = i - hi; if(jlo < 0) jlo = 0;
@@ -69,27 +102,38 @@ int orc_overlap_align(const uint32_t* a, int64_t nx, const uint32_t* b, int64_t 
             if(i == 0 || j == 0) { s = 0; t = T_NONE; }
             else {
                 /* diagonal predecessor (i-1,j-1) is always in band */
-                s = prev[j - 1 - prevLo] + ((a[i-1] == b[j-1]) ? match : mismatch);
-                t = T_DIAG;
-                if(j - 1 >= jlo) {                              /* vertical: (i, j-1) */
-                    const int32_t v = cur[j - 1 - jlo] + gap;
-                    if(v > s) { s = v; t = T_VERT; }
-                }
-                if(j <= prevHi && j >= prevLo) {                /* horizontal: (i-1, j) */
-                    const int32_t h = prev[j - prevLo] + gap;
-                    if(h > s) { s = h; t = T_HORZ; }
-                }
+                const int32_t d = prev[j - 1 - prevLo] + ((a[i-1] == b[j-1]) ? match : mismatch);
+                const int haveV = (j - 1 >= jlo);                       /* vertical: (i, j-1) */
+                const int haveH = (j <= prevHi && j >= prevLo);         /* horizontal: (i-1, j) */
+                const int32_t v = haveV ? cur[j - 1 - jlo] + gap : 0;
+                const int32_t h = haveH ? prev[j - prevLo] + gap : 0;
+                /* the better gap move, then against the diagonal (include/shb_dp_policy.h) */
+                int haveG = 0; int32_t g = 0; uint8_t tg = T_NONE; int ties = 0;
+                if(haveV && haveH) {
+                    haveG = 1;
+                    if(v > h || (v == h && vertFirst)) { g = v; tg = T_VERT; } else { g = h; tg = T_HORZ; }
+                    if(v == h) ties = 1;
+                } else if(haveV) { haveG = 1; g = v; tg = T_VERT; }
+                else if(haveH) { haveG = 1; g = h; tg = T_HORZ; }
+                if(!haveG || d > g || (d == g && diagWins)) { s = d; t = T_DIAG; if(haveG && d == g) ties = 1; else ties = 0; }
+                else { s = g; t = tg; if(d == g) ties = 1; }
+                if(ties) t |= T_TIE;
             }
             cur[j - jlo] = s;
             tcol[j - jlo] = t;
             if(j == ny || i == nx) {
-                if(!haveBest || s > best) { best = s; bi = i; bj = j; haveBest = 1; }
+                if(haveBest && s == best) endTie = 1;
+                if(!haveBest || s > best || (s == best && !endFirst)) {
+                    if(!haveBest || s > best) endTie = 0;
+                    best = s; bi = i; bj = j; haveBest = 1;
+                }
             }
         }
         int32_t* tmp = prev; prev = cur; cur = tmp;
         prevLo = jlo; prevHi = jhi;
     }
-    if(!haveBest) { free(trace); free(prev); free(cur); return ORC_MIN_VALUE; }
+    if(!haveBest) return ORC_MIN_VALUE;
+    if(endTie) orc_tls_tie |= 2;
 
     /* Traceback. */
     uint64_t cap = 1024, n = 0;
@@ -97,7 +141,9 @@ int orc_overlap_align(const uint32_t* a, int64_t nx, const uint32_t* b, int64_t 
     int64_t i = bi, j = bj;
     while(i > 0 && j > 0) {
         int64_t jlo = i - hi; if(jlo < 0) jlo = 0;
-        const uint8_t t = trace[(size_t)i * (size_t)W + (size_t)(j - jlo)];
+        const uint8_t tt = trace[(size_t)i * (size_t)W + (size_t)(j - jlo)];
+        const uint8_t t = tt & 3;
+        if(tt & T_TIE) orc_tls_tie |= 1;
         if(t == T_DIAG) {
             if(n == cap) { cap *= 2; path = (uint32_t*)realloc(path, sizeof(uint32_t) * 2 * cap); }
             path[2*n] = (uint32_t)(i - 1); path[2*n+1] = (uint32_t)(j - 1); n++;
@@ -111,7 +157,6 @@ int orc_overlap_align(const uint32_t* a, int64_t nx, const uint32_t* b, int64_t 
         path[2*k] = path[2*(n-1-k)]; path[2*k+1] = path[2*(n-1-k)+1];
         path[2*(n-1-k)] = t0; path[2*(n-1-k)+1] = t1;
     }
-    free(trace); free(prev); free(cur);
     *pathOut = path; *pathLen = n;
     return best;
 }
@@ -545,10 +590,12 @@ static void* workerMain(void* arg)
         const uint32_t* a = w->kmerIds + w->toc[o0]; const uint32_t nx = (uint32_t)(w->toc[o0+1] - w->toc[o0]);
         const uint32_t* b = w->kmerIds + w->toc[o1]; const uint32_t ny = (uint32_t)(w->toc[o1+1] - w->toc[o1]);
         int status = 0, tie = 0;
+        orc_reset_tie_flags();
         if(w->o->alignMethod == 3) status = orc_align_method3(a, nx, b, ny, w->o, &al);
         else if(w->o->alignMethod == 4) status = orc_align_method4(a, nx, b, ny, w->o, &al, &tie);
         else status = alignMethod1(a, nx, b, ny, w->o, &al);
-        w->tie[i] = (uint8_t)tie;
+        /* bit 0: Align4 component tie; bit 1: a DP path of this candidate branched on a tie; bit 2: end-cell tie */
+        w->tie[i] = (uint8_t)((tie ? 1 : 0) | (orc_get_tie_flags() << 1));
         w->keep[i] = 0;
         if(status) continue;                                                    /* exception: candidate skipped, :419-434 */
         orc_info info; orc_alignment_info(al.ord, al.n, nx, ny, &info);
@@ -572,13 +619,15 @@ static void* workerMain(void* arg)
         w->keep[i] = 1;
     }
     free(al.ord);
+    orc_release_thread_scratch();
     return NULL;
 }
 
 /*
  * toc uint64[2R+1], kmerIds uint32[M] (the kmerId column of the markers), candidates uint32[n][3].
  * Outputs (malloc'ed): records uint32[count][16], compressedToc uint64[count+1], compressedData bytes,
- * ties uint8[n] (method-4 ambiguity flag per candidate, may be NULL).
+ * ties uint8[n] per candidate (may be NULL): bit 0 = two kept Align4 components tie on markerCount, bit 1 = a DP path of
+ * the candidate passed through a cell with co-optimal predecessors, bit 2 = the DP end cell had a co-optimal rival.
  */
 int orc_compute_alignments(const uint64_t* toc, const uint32_t* kmerIds, const uint32_t* candidates, uint64_t n,
                            const orc_align_options* o, uint32_t threads,
@@ -648,6 +697,40 @@ void orc_compute_alignment_table(const uint32_t* records, uint64_t n, uint64_t R
     orc_te* e = (orc_te*)malloc(sizeof(orc_te) * (4 * n + 1));
     for(uint64_t i = 0; i < n; i++) {
         const uint32_t r0 = records[16*i], r1 = records[16*i+1], same = records[16*i+2] & 0xff;
+        const uint32_t o0 = 2 * r0, o1 = 2 * r1 + (same ? 0 : 1);
+        const uint32_t rows[4] = {o0, o1, o0 ^ 1, o1 ^ 1};
+        const uint32_t others[4] = {o1, o0, o1 ^ 1, o0 ^ 1};
+        for(int k = 0; k < 4; k++) {
+            orc_te* slot = &e[toc[rows[k]] + fill[rows[k]]++];
+            slot->other = others[k]; slot->index = (uint32_t)i;
+        }
+    }
+    for(uint64_t o = 0; o < 2 * R; o++) qsort(e + toc[o], toc[o+1] - toc[o], sizeof(orc_te), cmp_te);
+    for(uint64_t i = 0; i < 4 * n; i++) table[i] = e[i].index;
+    free(fill); free(e);
+}
+
+
+/* ---------------------------------------------------------------------------------------------
+ * AlignmentCandidates::computeCandidateTable — src/AssemblerAlignmentCandidates.cpp:379-448.
+ * candidates: uint32[n][3] (readId0, readId1, isSameStrand). Outputs (caller allocated): toc uint64[2R+1],
+ * table uint64[4n]: for each oriented read the indices of the candidates it is involved in (both reads, both
+ * strands: :389-399), each row sorted by (other OrientedReadId, candidate index) (:417-440, sort of
+ * pair<OrientedReadId, uint32_t>).
+ */
+void orc_compute_candidate_table(const uint32_t* candidates, uint64_t n, uint64_t R, uint64_t* toc, uint64_t* table)
+{
+    memset(toc, 0, sizeof(uint64_t) * (2 * R + 1));
+    for(uint64_t i = 0; i < n; i++) {
+        const uint32_t r0 = candidates[3*i], r1 = candidates[3*i+1], same = candidates[3*i+2] & 0xff;
+        const uint32_t o0 = 2 * r0, o1 = 2 * r1 + (same ? 0 : 1);
+        toc[o0 + 1]++; toc[o1 + 1]++; toc[(o0 ^ 1) + 1]++; toc[(o1 ^ 1) + 1]++;
+    }
+    for(uint64_t o = 0; o < 2 * R; o++) toc[o + 1] += toc[o];
+    uint64_t* fill = (uint64_t*)calloc(2 * R + 1, sizeof(uint64_t));
+    orc_te* e = (orc_te*)malloc(sizeof(orc_te) * (4 * n + 1));
+    for(uint64_t i = 0; i < n; i++) {
+        const uint32_t r0 = candidates[3*i], r1 = candidates[3*i+1], same = candidates[3*i+2] & 0xff;
         const uint32_t o0 = 2 * r0, o1 = 2 * r1 + (same ? 0 : 1);
         const uint32_t rows[4] = {o0, o1, o0 ^ 1, o1 ^ 1};
         const uint32_t others[4] = {o1, o0, o1 ^ 1, o0 ^ 1};

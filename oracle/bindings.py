@@ -390,6 +390,34 @@ def oracle_compute_alignment_table(records, read_count):
     return toc, table[:4 * len(rec)].copy()
 
 
+def oracle_compute_candidate_table(candidates, read_count):
+    """Returns (toc uint64[2R+1], table uint64[4n]) — src/AssemblerAlignmentCandidates.cpp:379-448."""
+    lib = _olib()
+    cand = np.ascontiguousarray(candidates, np.uint32).reshape(-1, 3)
+    toc = np.zeros(2 * read_count + 1, np.uint64)
+    table = np.zeros(4 * len(cand) + 1, np.uint64)
+    lib.orc_compute_candidate_table.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.orc_compute_candidate_table(cand.ctypes.data, len(cand), read_count, toc.ctypes.data, table.ctypes.data)
+    return toc, table[:4 * len(cand)].copy()
+
+
+def set_dp_policy(bits):
+    """Tie-break policy of the oracle's DP at run time (include/shb_dp_policy.h: bit 0 diagonal wins ties, bit 1 vertical
+    before horizontal, bit 2 first maximum is the end cell). Returns the previous policy."""
+    lib = _olib()
+    lib.orc_get_dp_policy.restype = C.c_int
+    lib.orc_set_dp_policy.argtypes = [C.c_int]
+    old = lib.orc_get_dp_policy()
+    lib.orc_set_dp_policy(int(bits))
+    return old
+
+
+def default_dp_policy():
+    lib = _olib()
+    lib.orc_get_dp_policy.restype = C.c_int
+    return lib.orc_get_dp_policy()
+
+
 def ref_write_data_dir(fasta, prefix, k=10, probability=0.1, seed=231, min_read_length=10000, threads=4):
     lib = ref_lib()
     lib.ref_write_data_dir.restype = C.c_int

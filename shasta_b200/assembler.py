@@ -210,18 +210,13 @@ class Assembler:
                             maxDistanceFromBoundary, minAlignedMarkerCount, minAlignedFraction, maxSkip, maxDrift, maxTrim,
                             maxBand, matchScore, mismatchScore, gapScore):
         """Single-pair Align4 (src/AssemblerAlign4.cpp:13-61, binding src/PythonModule.cpp:302-327; scripts/AlignOrientedReads4.py).
-        Prints the reference's line and returns the number of aligned markers. The pair goes through the same device path as
-        computeAlignments with alignMethod 4, in the orientation that path stores: the lower read id on strand 0 (an oriented
-        pair and its reverse complement / its transpose describe the same alignment; the marker count can differ only where
-        the DP has score ties). matchScore / mismatchScore / gapScore are accepted for signature compatibility: Align4
+        Prints the reference's line and returns the number of aligned markers. The two oriented reads are aligned in exactly
+        the orientation and order given (shb_align_oriented_reads): read 0 is the horizontal sequence of the cell grid and of
+        the DP, as in the reference. matchScore / mismatchScore / gapScore are accepted for signature compatibility: Align4
         hard-codes 6 / -1 / -1 (src/Align4.hpp:159-161)."""
         from . import capi
         self.checkKmersAreOpen()
-        if readId0 == readId1:
-            raise RuntimeError("alignOrientedReads4 needs two different reads.")
         ctx = self._upload_markers()
-        same = int(strand0 == strand1)
-        cand = np.array([[min(readId0, readId1), max(readId0, readId1), same]], np.uint32)
         o = capi.make_align_options(alignMethod=4, k=int(self.k), maxSkip=int(maxSkip), maxDrift=int(maxDrift), maxTrim=int(maxTrim),
                                     minAlignedMarkerCount=int(minAlignedMarkerCount), minAlignedFraction=float(minAlignedFraction),
                                     maxBand=int(maxBand), matchScore=int(matchScore), mismatchScore=int(mismatchScore),
@@ -229,12 +224,26 @@ class Assembler:
                                     align4MinEntryCountPerCell=int(minEntryCountPerCell),
                                     align4MaxDistanceFromBoundary=int(maxDistanceFromBoundary))
         try:
-            rec, _, _, _ = capi.compute_alignments(ctx, cand, o)
+            ords, _ = capi.align_oriented_reads(ctx, 2 * int(readId0) + int(strand0), 2 * int(readId1) + int(strand1), o)
         except capi.ShastaB200Error as e:
             raise RuntimeError(str(e)) from None
-        markers = int(rec[0, 9]) if len(rec) else 0
-        print(f"The alignment has {markers} markers.")
-        return markers
+        self._last_alignment = ords
+        print(f"The alignment has {len(ords)} markers.")
+        return len(ords)
+
+    def computeCandidateTable(self):
+        """Assembler::computeCandidateTable (src/AssemblerAlignmentCandidates.cpp:379-448, called at srcMain/main.cpp:706).
+        Writes Data/CandidateTable.{toc,data} (VectorOfVectors<uint64_t,uint64_t>)."""
+        from . import capi
+        self.checkAlignmentCandidatesAreOpen()
+        self.checkMarkersAreOpen()
+        try:
+            toc, table = capi.compute_candidate_table(self._context(), self._candidates, len(self._markers[2]))
+        except capi.ShastaB200Error as e:
+            raise RuntimeError(str(e)) from None
+        self._candidate_table = (toc, table)
+        mm_write_vector_of_vectors(self._name("CandidateTable"), toc, table, data_object_size=8, toc_dtype=np.uint64,
+                                   page_size=self.page_size)
 
     # ------------------------------------------------------------------ the two hot-path entry points
     def findAlignmentCandidatesLowHash0(self, m, hashFraction, minHashIterationCount, alignmentCandidatesPerRead,

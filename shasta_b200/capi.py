@@ -32,7 +32,8 @@ class LowHashParams(C.Structure):
 class LowHashResult(C.Structure):
     _fields_ = [("iterations", C.c_uint64), ("log2BucketCount", C.c_uint64), ("lowHashCount", C.c_uint64),
                 ("pairCount", C.c_uint64), ("candidateCount", C.c_uint64), ("sweepMs", C.c_double),
-                ("totalMs", C.c_double), ("sweepLaunches", C.c_uint64), ("kernelLaunches", C.c_uint64)]
+                ("totalMs", C.c_double), ("sweepLaunches", C.c_uint64), ("kernelLaunches", C.c_uint64),
+                ("candidateDigest", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -52,7 +53,9 @@ class AlignOptions(C.Structure):
 class AlignResult(C.Structure):
     _fields_ = [("candidateCount", C.c_uint64), ("alignmentCount", C.c_uint64), ("skippedCount", C.c_uint64),
                 ("dpCells", C.c_uint64), ("dpMs", C.c_double), ("totalMs", C.c_double), ("kernelLaunches", C.c_uint64),
-                ("outputCopyMs", C.c_double), ("hostWallMs", C.c_double)]
+                ("outputCopyMs", C.c_double), ("hostWallMs", C.c_double), ("dpUsefulCells", C.c_uint64),
+                ("tooWideCount", C.c_uint64), ("workers", C.c_uint64), ("alignmentDataDigest", C.c_uint64),
+                ("compressedDigest", C.c_uint64)]
 
 
 # Defaults of src/AssemblerOptions.cpp:380-489
@@ -96,6 +99,13 @@ def lib():
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                              C.POINTER(AlignResult)]
         L.shb_compute_alignment_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_align_oriented_reads.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(AlignOptions), C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_uint64), C.c_void_p]
+        L.shb_compute_candidate_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_digest_records.restype = C.c_uint64
+        L.shb_digest_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        L.shb_digest_compressed.restype = C.c_uint64
+        L.shb_digest_compressed.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.shb_synth_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -325,6 +335,53 @@ def compute_alignment_table(ctx: Context, records, read_count):
     lib().shb_free(toc)
     lib().shb_free(data)
     return tocn, datan
+
+
+def align_oriented_reads(ctx: Context, oriented_read_id0, oriented_read_id1, options: AlignOptions):
+    """Single pair in the orientation given (shb_align_oriented_reads). Returns (ordinals uint32[n,2], info uint32[13])."""
+    ords = C.c_void_p()
+    n = C.c_uint64()
+    info = np.zeros(13, np.uint32)
+    _check(lib().shb_align_oriented_reads(ctx._h, int(oriented_read_id0), int(oriented_read_id1), C.byref(options), C.byref(ords),
+                                          C.byref(n), _ptr(info)))
+    if not ords or n.value == 0:
+        if ords:
+            lib().shb_free(ords)
+        return np.zeros((0, 2), np.uint32), info
+    out = np.ctypeslib.as_array(C.cast(ords, C.POINTER(C.c_uint32)), (n.value, 2)).copy()
+    lib().shb_free(ords)
+    return out, info
+
+
+def compute_candidate_table(ctx: Context, candidates, read_count):
+    """AlignmentCandidates::computeCandidateTable. Returns (toc uint64[2R+1], table uint64[4n])."""
+    cand = candidates_to_records(candidates)
+    toc = C.c_void_p()
+    data = C.c_void_p()
+    _check(lib().shb_compute_candidate_table(ctx._h, _ptr(cand), len(cand), read_count, C.byref(toc), C.byref(data)))
+    tocn = np.ctypeslib.as_array(C.cast(toc, C.POINTER(C.c_uint64)), (2 * read_count + 1,)).copy()
+    datan = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint64)), (4 * len(cand),)).copy() if len(cand) else np.zeros(0, np.uint64)
+    lib().shb_free(toc)
+    lib().shb_free(data)
+    return tocn, datan
+
+
+def digest_records(records, words):
+    """shb_digest_records on a host array of `words`-word records (order independent; sums over partitions)."""
+    r = np.ascontiguousarray(records, np.uint32).reshape(-1, words)
+    return int(lib().shb_digest_records(_ptr(r), len(r), words))
+
+
+def digest_candidates(cand):
+    """Digest of candidates given as uint32[n,3] (readId0, readId1, isSameStrand)."""
+    return digest_records(candidates_to_records(cand), 3)
+
+
+def digest_compressed(records, ctoc, cdata):
+    r = np.ascontiguousarray(records, np.uint32).reshape(-1, 16)
+    t = np.ascontiguousarray(ctoc, np.uint64)
+    d = np.ascontiguousarray(cdata, np.uint8)
+    return int(lib().shb_digest_compressed(_ptr(r), len(r), _ptr(t), _ptr(d)))
 
 
 def _records_to_array(ptr, n):

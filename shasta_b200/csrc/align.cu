@@ -4,13 +4,19 @@
 #include "context.cuh"
 #include "align_kernels.cuh"
 #include "hostpool.cuh"
+#include "digest.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <exception>
+#include <memory>
+#include <mutex>
 #include <chrono>
 #include <cstring>
 #include <sys/mman.h>
 #include <thread>
 #include <limits>
+#include <map>
 #include <vector>
 
 namespace shb {
@@ -98,16 +104,15 @@ template<class... Args> void launchBanded(const DpClass& k, uint32_t blocks, uin
     }
 }
 
-// Buffers shared by both methods for one batch of candidates.
+// Buffers for one batch of candidates (both methods).
 struct Batch {
-    DeviceBuffer<uint32_t> cand, counts, infoWords, jobKeep, jobBytes, keep, keepIndex, bytes32, selected, records;
+    DeviceBuffer<uint32_t> cand, counts, infoWords, jobKeep, jobBytes, keep, keepIndex, bytes32, selected;
     DeviceBuffer<DpJob> jobs1, jobs;
-    DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, bytes64, bytesOff, scanWs64, ctoc;
+    DeviceBuffer<unsigned long long> tw, twOff, outCnt, outOff, bytes64, bytesOff, scanWs64;
     DeviceBuffer<uint32_t> trace;
     DeviceBuffer<uint2> ordinals, runs;
     DeviceBuffer<int2> endCells;
     DeviceBuffer<uint32_t> runCounts;
-    DeviceBuffer<uint8_t> cdata;
     // method 4
     DeviceBuffer<unsigned long long> cellCnt, cellOff;
     DeviceBuffer<uint32_t> gridCounts, gridAux, gridList, componentCount, jobOffsets;
@@ -119,7 +124,66 @@ struct Batch {
     const uint32_t* order = nullptr;
 };
 
-// Derived per-marker data cached in the context (per marker generation).
+// Device-side counters of one worker (one unsigned long long each).
+enum WorkerScalar { kScTotal64 = 0, kScTotal32 = 1, kScSkipped = 2, kScForwardCells = 3, kScTooWide = 4, kScBandCells = 5,
+                    kScDigits = 16, kScCount = 16 + 256 };
+
+// One host thread's private streams and scratch. computeAlignments runs the batches of a call on a few of these
+// concurrently: while one worker waits for a device-side size (scratch is sized from scans on the device), the kernels of
+// the others keep the GPU busy, so the host round trips leave the critical path.
+struct AlignWorker {
+    cudaStream_t stream = nullptr;
+    // side streams: the band classes of one batch are independent launches (disjoint jobs and scratch), so the few
+    // long jobs of the wide classes run beside the big narrow-band launch instead of after it
+    static constexpr int kSideStreams = 3;
+    cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t forkEv = nullptr, joinEv[kSideStreams] = {nullptr, nullptr, nullptr};
+    // high-priority streams for the short latency-bound kernels (traceback, filter) that follow each DP chunk: their
+    // blocks are scheduled ahead of the pending blocks of the other chunks' DP kernels
+    static constexpr int kHiStreams = 4;
+    cudaStream_t hiStream[kHiStreams] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t hiJoinEv[kHiStreams] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> unitEvents;
+    cudaEvent_t dp1a = nullptr, dp1b = nullptr, dp2a = nullptr, dp2b = nullptr;
+    Batch batch;
+    SortWorkspace sortWs;
+    DeviceBuffer<uint32_t> scanWs;
+    DeviceBuffer<unsigned long long> scalars;
+    // per call
+    double dpMs = 0.;
+    uint64_t traceWords = 0, launches = 0;
+
+    void init()
+    {
+        if(stream) return;
+        int least = 0, greatest = 0;
+        SHB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        SHB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        SHB_CUDA(cudaEventCreateWithFlags(&forkEv, cudaEventDisableTiming));
+        for(int i = 0; i < kSideStreams; i++) {
+            SHB_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+            SHB_CUDA(cudaEventCreateWithFlags(&joinEv[i], cudaEventDisableTiming));
+        }
+        for(int i = 0; i < kHiStreams; i++) {
+            SHB_CUDA(cudaStreamCreateWithPriority(&hiStream[i], cudaStreamNonBlocking, greatest));
+            SHB_CUDA(cudaEventCreateWithFlags(&hiJoinEv[i], cudaEventDisableTiming));
+        }
+        SHB_CUDA(cudaEventCreate(&dp1a)); SHB_CUDA(cudaEventCreate(&dp1b));
+        SHB_CUDA(cudaEventCreate(&dp2a)); SHB_CUDA(cudaEventCreate(&dp2b));
+        scalars.reserve(kScCount);
+    }
+    ~AlignWorker()
+    {
+        for(int i = 0; i < kHiStreams; i++) { if(hiStream[i]) cudaStreamDestroy(hiStream[i]); if(hiJoinEv[i]) cudaEventDestroy(hiJoinEv[i]); }
+        for(cudaEvent_t e : unitEvents) cudaEventDestroy(e);
+        for(int i = 0; i < kSideStreams; i++) { if(side[i]) cudaStreamDestroy(side[i]); if(joinEv[i]) cudaEventDestroy(joinEv[i]); }
+        for(cudaEvent_t e : {forkEv, dp1a, dp1b, dp2a, dp2b}) if(e) cudaEventDestroy(e);
+        if(stream) cudaStreamDestroy(stream);
+    }
+    unsigned long long* sc(int k) { return scalars.get() + k; }
+};
+
+// Derived per-marker data cached in the context (per marker generation), the workers, and the device-side result arena.
 struct AlignCache {
     // method 3: downsampled marker CSR
     DeviceBuffer<uint64_t> dsToc;
@@ -131,30 +195,12 @@ struct AlignCache {
     DeviceBuffer<uint32_t> sortedKmer, sortedOrdinal;
     uint64_t sortedGeneration = ~0ull;
     uint64_t lengthCheckGeneration = ~0ull;
-    // per-batch scratch and the device-side result accumulation: kept across calls so that a steady-state call does
-    // not allocate or free device memory
-    Batch batch;
+    // workers and the device-side result accumulation: kept across calls so that a steady-state call does not allocate
+    // or free device memory
+    std::vector<std::unique_ptr<AlignWorker>> workers;
     DeviceBuffer<uint32_t> outRecords;
     DeviceBuffer<unsigned long long> outToc;
     DeviceBuffer<uint8_t> outData;
-    // side streams: the band classes of one batch are independent launches (disjoint jobs and scratch), so the few
-    // long jobs of the wide classes run beside the big narrow-band launch instead of after it
-    static constexpr int kSideStreams = 3;
-    cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
-    cudaEvent_t forkEv = nullptr, joinEv[kSideStreams] = {nullptr, nullptr, nullptr};
-    // high-priority stream for the short latency-bound kernels (traceback, filter) that follow each DP chunk: their
-    // blocks are scheduled ahead of the pending blocks of the other chunks' DP kernels
-    static constexpr int kHiStreams = 4;
-    cudaStream_t hiStream[kHiStreams] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t hiJoinEv[kHiStreams] = {nullptr, nullptr, nullptr, nullptr};
-    std::vector<cudaEvent_t> unitEvents;
-    ~AlignCache()
-    {
-        for(int i = 0; i < kHiStreams; i++) { if(hiStream[i]) cudaStreamDestroy(hiStream[i]); if(hiJoinEv[i]) cudaEventDestroy(hiJoinEv[i]); }
-        for(cudaEvent_t e : unitEvents) cudaEventDestroy(e);
-        for(int i = 0; i < kSideStreams; i++) { if(side[i]) cudaStreamDestroy(side[i]); if(joinEv[i]) cudaEventDestroy(joinEv[i]); }
-        if(forkEv) cudaEventDestroy(forkEv);
-    }
 };
 
 AlignCache& cache(shb_context* c)
@@ -164,21 +210,13 @@ AlignCache& cache(shb_context* c)
 }
 
 // Runs launch(k, count, offset, stream) for every non-empty band class, cut into chunks of at most chunkMax jobs:
-// the widest classes first, round-robin over the side streams and the main stream, so that independent launches
+// the widest classes first, round-robin over the side streams and the worker's main stream, so that independent launches
 // (disjoint jobs and scratch) overlap: the few long jobs of the wide classes run beside the big narrow-band launch,
 // and the latency-bound traceback of one chunk runs beside the issue-bound DP of the next. The main stream continues
 // after all of them.
-template<class F> void forEachClassConcurrently(shb_context* c, const std::vector<uint64_t>& classCounts, uint32_t chunkMax, F launch)
+template<class F> void forEachClassConcurrently(AlignWorker& w, const std::vector<uint64_t>& classCounts, uint32_t chunkMax, F launch)
 {
-    AlignCache& ac = cache(c);
-    cudaStream_t st = c->stream;
-    if(!ac.forkEv) {
-        SHB_CUDA(cudaEventCreateWithFlags(&ac.forkEv, cudaEventDisableTiming));
-        for(int i = 0; i < AlignCache::kSideStreams; i++) {
-            SHB_CUDA(cudaStreamCreateWithFlags(&ac.side[i], cudaStreamNonBlocking));
-            SHB_CUDA(cudaEventCreateWithFlags(&ac.joinEv[i], cudaEventDisableTiming));
-        }
-    }
+    cudaStream_t st = w.stream;
     struct Unit { int k; uint32_t count; uint64_t offset; };
     std::vector<Unit> units;
     const int classCount = int(classCounts.size());
@@ -191,23 +229,23 @@ template<class F> void forEachClassConcurrently(shb_context* c, const std::vecto
         for(uint64_t begin = 0; begin < count; begin += per) units.push_back({k, uint32_t(std::min(per, count - begin)), offsets[k] + begin});
     }
     if(units.empty()) return;
-    constexpr int kStreams = AlignCache::kSideStreams + 1;      // the last one is the main stream
-    bool used[AlignCache::kSideStreams] = {false, false, false};
-    if(units.size() > 1) SHB_CUDA(cudaEventRecord(ac.forkEv, st));
+    constexpr int kStreams = AlignWorker::kSideStreams + 1;      // the last one is the main stream
+    bool used[AlignWorker::kSideStreams] = {false, false, false};
+    if(units.size() > 1) SHB_CUDA(cudaEventRecord(w.forkEv, st));
     for(size_t u = 0; u < units.size(); u++) {
         // the last unit always goes to the main stream
         const int i = (u + 1 == units.size()) ? kStreams - 1 : int(u % kStreams);
         cudaStream_t s = st;
-        if(i < AlignCache::kSideStreams) {
-            s = ac.side[i];
-            if(!used[i]) { SHB_CUDA(cudaStreamWaitEvent(s, ac.forkEv, 0)); used[i] = true; }
+        if(i < AlignWorker::kSideStreams) {
+            s = w.side[i];
+            if(!used[i]) { SHB_CUDA(cudaStreamWaitEvent(s, w.forkEv, 0)); used[i] = true; }
         }
         launch(units[u].k, units[u].count, units[u].offset, s);
     }
-    for(int i = 0; i < AlignCache::kSideStreams; i++) {
+    for(int i = 0; i < AlignWorker::kSideStreams; i++) {
         if(!used[i]) continue;
-        SHB_CUDA(cudaEventRecord(ac.joinEv[i], ac.side[i]));
-        SHB_CUDA(cudaStreamWaitEvent(st, ac.joinEv[i], 0));
+        SHB_CUDA(cudaEventRecord(w.joinEv[i], w.side[i]));
+        SHB_CUDA(cudaStreamWaitEvent(st, w.joinEv[i], 0));
     }
 }
 
@@ -249,7 +287,7 @@ void buildDownsampled(shb_context* c, uint32_t k, double factor)
         total = running;
     }
     if(M == 0) SHB_CUDA(cudaMemsetAsync(ds.dsToc.get(), 0, (uint64_t(rows) + 1) * 8, st));
-    // Longest downsampled row (bounds the stage-1 band classes).
+    // Longest downsampled row (diagnostics; candidates whose stage 1 is too wide are skipped one by one).
     std::vector<uint64_t> hostToc(uint64_t(rows) + 1);
     SHB_CUDA(cudaMemcpyAsync(hostToc.data(), ds.dsToc.get(), (uint64_t(rows) + 1) * 8, cudaMemcpyDeviceToHost, st));
     SHB_CUDA(cudaStreamSynchronize(st));
@@ -299,8 +337,6 @@ void buildSortedMarkers(shb_context* c, uint32_t k)
     sc.sortedGeneration = c->markerGeneration;
 }
 
-struct DpTotals { unsigned long long traceWords = 0; double ms = 0.; };
-
 uint32_t envCount(const char* name, uint32_t dflt)
 {
     const char* v = getenv(name);
@@ -308,31 +344,6 @@ uint32_t envCount(const char* name, uint32_t dflt)
     const long x = strtol(v, nullptr, 10);
     return x > 0 ? uint32_t(x) : dflt;
 }
-
-// SHB_TRACE only: wall time of the stage-2 sub-phases (each bracketed by stream synchronisation), summed per call.
-double g_tracePhaseMs[4] = {0., 0., 0., 0.};
-
-// Host-side phase timing, printed to stderr when SHB_TRACE is set (diagnostics only).
-struct PhaseClock {
-    bool on = getenv("SHB_TRACE") != nullptr;
-    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    void lap(int phase, cudaStream_t st)
-    {
-        if(!on) return;
-        cudaStreamSynchronize(st);
-        const auto now = std::chrono::steady_clock::now();
-        acc[phase] += std::chrono::duration<double, std::milli>(now - t).count();
-        t = now;
-    }
-    void report(const char* const* names, int n) const
-    {
-        if(!on) return;
-        fprintf(stderr, "[shb] computeAlignments phases (ms):");
-        for(int i = 0; i < n; i++) fprintf(stderr, " %s=%.1f", names[i], acc[i]);
-        fprintf(stderr, "\n");
-    }
-};
 
 void parallelMemcpy(uint8_t* dst, const uint8_t* src, uint64_t n)
 {
@@ -350,10 +361,10 @@ void parallelMemcpy(uint8_t* dst, const uint8_t* src, uint64_t n)
 
 // Device -> pageable host copy through two pinned staging buffers: the DMA of chunk k overlaps the host memcpy of
 // chunk k-1 (a plain cudaMemcpy into pageable memory serialises the two).
-void copyToHostPipelined(shb_context* c, void* dstHost, const void* srcDevice, uint64_t bytes)
+void copyToHostPipelined(shb_context* c, void* dstHost, const void* srcDevice, uint64_t bytes, bool pageLocked)
 {
     if(bytes == 0) return;
-    if(HostPool::instance().isPageLocked(dstHost)) {        // recycled, page-locked result block: direct DMA
+    if(pageLocked) {        // recycled, page-locked result block: direct DMA
         SHB_CUDA(cudaMemcpyAsync(dstHost, srcDevice, bytes, cudaMemcpyDeviceToHost, c->stream));
         return;
     }
@@ -382,10 +393,10 @@ void copyToHostPipelined(shb_context* c, void* dstHost, const void* srcDevice, u
 
 // Groups the runnable jobs by band class (longest first inside a class). Returns per-class counts; b.order holds the
 // job indices, class after class.
-void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs, std::vector<uint64_t>& classCounts,
-                     uint32_t forwardClasses = 0)
+void buildClassOrder(AlignWorker& w, const DpJob* jobs, uint32_t nJobs, std::vector<uint64_t>& classCounts, uint32_t forwardClasses = 0)
 {
-    cudaStream_t st = c->stream;
+    cudaStream_t st = w.stream;
+    Batch& b = w.batch;
     classCounts.assign(kClassCount + forwardClasses, 0);
     if(nJobs == 0) return;
     if(!b.classLimits.get()) {
@@ -399,10 +410,9 @@ void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs
     SHB_LAUNCH(dpClassKeysKernel, ceilDiv(nJobs, 256), 256, 0, st, jobs, nJobs, (const uint32_t*)b.classLimits.get(), uint32_t(kClassCount),
                forwardClasses, b.orderKeysA.get(), b.orderValsA.get());
     const int ranges[1][2] = {{0, kDpLengthKeyBits + kDpClassKeyBits}};
-    const bool inB = radixSort<true>(b.orderKeysA.get(), b.orderKeysB.get(), b.orderValsA.get(), b.orderValsB.get(), nJobs, ranges, 1, c->sortWs, st);
+    const bool inB = radixSort<true>(b.orderKeysA.get(), b.orderKeysB.get(), b.orderValsA.get(), b.orderValsB.get(), nJobs, ranges, 1, w.sortWs, st);
     b.order = inB ? b.orderValsB.get() : b.orderValsA.get();
-    // scalars: 512 entries, allocated once at context creation
-    unsigned long long* dCounts = c->scalars.get() + 64;
+    unsigned long long* dCounts = w.sc(kScDigits);
     SHB_CUDA(cudaMemsetAsync(dCounts, 0, 256 * sizeof(unsigned long long), st));
     SHB_LAUNCH(digitCountKernel, ceilDiv(nJobs, 256), 256, 0, st, (const uint64_t*)(inB ? b.orderKeysB.get() : b.orderKeysA.get()), nJobs, kDpLengthKeyBits, kDpClassNone, dCounts);
     unsigned long long h[256];
@@ -412,20 +422,11 @@ void buildClassOrder(shb_context* c, Batch& b, const DpJob* jobs, uint32_t nJobs
 }
 
 // Scratch offsets + the banded DP + traceback for nJobs jobs whose lo/hi/state are set.
-void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* sequences, DpScores scores,
-                   Events& ev, DpTotals& totals)
+void runBandedJobs(AlignWorker& w, uint32_t nJobs, const uint32_t* sequences, DpScores scores)
 {
-    cudaStream_t st = c->stream;
-    static const bool traceOn = getenv("SHB_TRACE") != nullptr;
-    auto lap = [&](int k, std::chrono::steady_clock::time_point& t0) {
-        if(!traceOn) return;
-        cudaStreamSynchronize(st);
-        const auto t1 = std::chrono::steady_clock::now();
-        g_tracePhaseMs[k] += std::chrono::duration<double, std::milli>(t1 - t0).count();
-        t0 = t1;
-    };
-    auto t0 = std::chrono::steady_clock::now();
-    unsigned long long* total64 = c->scalars.get() + 48;
+    cudaStream_t st = w.stream;
+    Batch& b = w.batch;
+    unsigned long long* total64 = w.sc(kScTotal64);
     b.scanWs64.reserve(scanWorkspaceElements(nJobs));
     b.twOff.reserve(nJobs); b.outOff.reserve(nJobs); b.counts.reserve(nJobs); b.endCells.reserve(nJobs); b.runCounts.reserve(nJobs);
     exclusiveScan<unsigned long long>(b.tw.get(), b.twOff.get(), nJobs, total64, b.scanWs64.get(), st);
@@ -435,178 +436,128 @@ void runBandedJobs(shb_context* c, Batch& b, uint32_t nJobs, const uint32_t* seq
     b.trace.reserve(traceWords + 1);
     b.ordinals.reserve(ordinalSlots + 1);
     b.runs.reserve(ordinalSlots + 1);
-    totals.traceWords += traceWords;
+    w.traceWords += traceWords;
     SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nJobs, 256), 256, 0, st, b.jobs.get(), nJobs, (const unsigned long long*)b.twOff.get(),
                (const unsigned long long*)b.outOff.get());
+    SHB_LAUNCH(bandCellsKernel, ceilDiv(nJobs, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nJobs, w.sc(kScBandCells));
     SHB_CUDA(cudaMemsetAsync(b.counts.get(), 0, 4ull * nJobs, st));
     std::vector<uint64_t> classCounts;
-    buildClassOrder(c, b, b.jobs.get(), nJobs, classCounts);
+    buildClassOrder(w, b.jobs.get(), nJobs, classCounts);
     BandedArgs g;
     g.kmerIds = sequences; g.scores = scores;
-    lap(3, t0);
-    SHB_CUDA(cudaEventRecord(ev.a, st));
+    SHB_CUDA(cudaEventRecord(w.dp2a, st));
     // Per chunk: DP (warp per job) on its stream, then traceback (thread per job) and equal-k-mer filter (warp per job)
-    // on the high-priority stream.
-    AlignCache& ac = cache(c);
-    if(!ac.hiStream[0]) {
-        int least = 0, greatest = 0;
-        SHB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        for(int i = 0; i < AlignCache::kHiStreams; i++) {
-            SHB_CUDA(cudaStreamCreateWithPriority(&ac.hiStream[i], cudaStreamNonBlocking, greatest));
-            SHB_CUDA(cudaEventCreateWithFlags(&ac.hiJoinEv[i], cudaEventDisableTiming));
-        }
-    }
+    // on a high-priority stream.
     size_t unit = 0;
-    forEachClassConcurrently(c, classCounts, envCount("SHB_ALIGN_CHUNK", 32768), [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
+    forEachClassConcurrently(w, classCounts, envCount("SHB_ALIGN_CHUNK", 32768), [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
         const uint32_t warps = warpsForClass(kClasses[k]);
         const size_t smem = smemForClass(kClasses[k], warps);
         BandedArgs gk = g;
         gk.n = count; gk.order = b.order + offset; gk.wMax = kClasses[k].wMax;
         launchBanded(kClasses[k], ceilDiv(count, warps), warps * 32, smem, s, gk, (const DpJob*)b.jobs.get(), b.trace.get(), b.endCells.get());
-        if(unit == ac.unitEvents.size()) {
+        if(unit == w.unitEvents.size()) {
             cudaEvent_t e = nullptr;
             SHB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ac.unitEvents.push_back(e);
+            w.unitEvents.push_back(e);
         }
-        SHB_CUDA(cudaEventRecord(ac.unitEvents[unit], s));
-        cudaStream_t hs = ac.hiStream[unit % AlignCache::kHiStreams];
-        SHB_CUDA(cudaStreamWaitEvent(hs, ac.unitEvents[unit], 0));
+        SHB_CUDA(cudaEventRecord(w.unitEvents[unit], s));
+        cudaStream_t hs = w.hiStream[unit % AlignWorker::kHiStreams];
+        SHB_CUDA(cudaStreamWaitEvent(hs, w.unitEvents[unit], 0));
         unit++;
         SHB_LAUNCH(tracebackKernel, ceilDiv(count, 128), 128, 0, hs, count, gk.order, (const DpJob*)b.jobs.get(),
                    (const int2*)b.endCells.get(), (const uint32_t*)b.trace.get(), b.runs.get(), b.runCounts.get());
         SHB_LAUNCH(filterStepsKernel, ceilDiv(count, 4), 128, 0, hs, count, gk.order, (const DpJob*)b.jobs.get(), sequences,
                    (const uint2*)b.runs.get(), (const uint32_t*)b.runCounts.get(), b.ordinals.get(), b.counts.get());
     });
-    for(size_t i = 0; i < std::min<size_t>(unit, AlignCache::kHiStreams); i++) {
-        SHB_CUDA(cudaEventRecord(ac.hiJoinEv[i], ac.hiStream[i]));
-        SHB_CUDA(cudaStreamWaitEvent(st, ac.hiJoinEv[i], 0));
+    for(size_t i = 0; i < std::min<size_t>(unit, AlignWorker::kHiStreams); i++) {
+        SHB_CUDA(cudaEventRecord(w.hiJoinEv[i], w.hiStream[i]));
+        SHB_CUDA(cudaStreamWaitEvent(st, w.hiJoinEv[i], 0));
     }
-    lap(2, t0);
-    SHB_CUDA(cudaEventRecord(ev.b, st));
+    SHB_CUDA(cudaEventRecord(w.dp2b, st));
 }
 
-} // namespace
-
-void destroyAlignCache(shb_context* c)
-{
-    if(c->alignCache) { delete static_cast<AlignCache*>(c->alignCache); c->alignCache = nullptr; }
-}
-
-
-void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, const shb_align_options& o,
-                       void** alignmentDataOut, uint64_t* alignmentCountOut,
-                       uint64_t** compressedTocOut, uint8_t** compressedDataOut, shb_align_result* result)
-{
-    SHB_REQUIRE(c->haveMarkers, SHB_ERR_STATE, "Markers are not accessible.");
-    SHB_REQUIRE(c->readBegin == 0 && c->readEnd == c->readCountTotal, SHB_ERR_STATE,
-                "computeAlignments needs the markers of all reads on this GPU.");
-    SHB_REQUIRE(o.alignMethod == 3 || o.alignMethod == 4, SHB_ERR_INVALID,
-                "Only Align.alignMethod 3 and 4 are implemented (0 and 1 are not on the hot path).");
-    SHB_REQUIRE(o.gapScore <= 0, SHB_ERR_INVALID, "Align.gapScore must not be positive.");
-    SHB_REQUIRE(o.k >= 1 && o.k <= 16, SHB_ERR_INVALID, "Invalid k.");
-    SHB_REQUIRE(n == 0 || candidatesHost != nullptr, SHB_ERR_INVALID, "Null candidates.");
-    SHB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    g_launchCount = 0;
-    const auto wall0 = std::chrono::steady_clock::now();
-    Events totalEv, dpEv1, dpEv2;
-    SHB_CUDA(cudaEventRecord(totalEv.a, st));
-    double dpMs = 0.;
-    const bool method4 = (o.alignMethod == 4);
-
-    // src/AssemblerAlign.cpp:378 asserts readIds[0] < readIds[1].
-    const uint32_t* cand = static_cast<const uint32_t*>(candidatesHost);
-    for(uint64_t i = 0; i < n; i++) {
-        SHB_REQUIRE(cand[3*i] < cand[3*i+1] && cand[3*i+1] < c->readCountTotal, SHB_ERR_INVALID, "Invalid alignment candidate.");
-    }
-
-    AlignCache& ac = cache(c);
-    uint32_t maxStage1Width = 0;
-    if(method4) {
-        SHB_REQUIRE(o.align4DeltaX >= 1 && o.align4DeltaY >= 1 && o.align4DeltaX < (1ull << 31) && o.align4DeltaY < (1ull << 31),
-                    SHB_ERR_INVALID, "Invalid Align.align4.deltaX / deltaY.");
-        buildSortedMarkers(c, o.k);
-    } else {
-        buildDownsampled(c, o.k, o.downsamplingFactor);
-        maxStage1Width = 2 * ac.dsMaxRow + 2 + 64;
-        SHB_REQUIRE(maxStage1Width <= kMaxBandWidth, SHB_ERR_INVALID,
-                    "Downsampled reads are too long for the stage-1 kernel (limit 8191 downsampled markers).");
-    }
-    if(ac.lengthCheckGeneration != c->markerGeneration) {       // the traceback packs a run length above a 28-bit ordinal
-        for(size_t r = 0; r + 1 < c->tocHost.size(); r++) {
-            SHB_REQUIRE(c->tocHost[r + 1] - c->tocHost[r] < (1ull << kRunLengthShift), SHB_ERR_INVALID, "A read has 2^28 or more markers.");
-        }
-        ac.lengthCheckGeneration = c->markerGeneration;
-    }
-    const uint32_t maxStage2Width = uint32_t(std::max(0, o.maxBand)) + 2 + 64;     // padded to a multiple of 64
-    SHB_REQUIRE(maxStage2Width <= kMaxBandWidth, SHB_ERR_INVALID, "Align.maxBand too large for this implementation (limit 16382).");
-
-    // Method 3 uses the configured scores; Align4 hard-codes 6/-1/-1 (src/Align4.hpp:159-161: never overwritten).
-    const DpScores scores = method4 ? DpScores{6, -1, -1} : DpScores{o.matchScore, o.mismatchScore, o.gapScore};
-    FilterOptions fo;
-    fo.minAlignedMarkerCount = uint64_t(o.minAlignedMarkerCount); fo.maxSkip = uint64_t(o.maxSkip);
-    fo.maxDrift = uint64_t(o.maxDrift); fo.maxTrim = uint64_t(o.maxTrim);
-    fo.minAlignedFraction = o.minAlignedFraction;
-    fo.suppressContainments = (!method4 && o.suppressContainments) ? 1u : 0u;     // method 4 applies it after the selection
-
-    // SHB_ALIGN_BATCH / SHB_ALIGN_CHUNK: test hooks that shrink the batch and chunk sizes so that small inputs exercise the
-    // multi-batch, multi-chunk paths (tests/test_gpu_scale.py).
-    const uint32_t batchMax = envCount("SHB_ALIGN_BATCH", method4 ? 32768 : 262144);
-    const uint64_t cellBudget = 192ull << 20;      // method 4: cells of scratch per batch
-    Batch& b = ac.batch;
-    c->scanWs.reserve(scanWorkspaceElements(4ull * batchMax * 64));
-    // scalars: 512 entries, allocated once at context creation
-    unsigned long long* total64 = c->scalars.get() + 48;
-    uint32_t* total32 = reinterpret_cast<uint32_t*>(c->scalars.get() + 32);
-
-    // Kept alignments accumulate on the device and are copied to the host once at the end.
-    DeviceBuffer<uint32_t>& outRecords = ac.outRecords;
-    DeviceBuffer<unsigned long long>& outToc = ac.outToc;
-    DeviceBuffer<uint8_t>& outData = ac.outData;
+// What one call shares between its workers.
+struct AlignCall {
+    shb_context* c;
+    AlignCache* ac;
+    const uint32_t* cand; uint64_t n;
+    shb_align_options o;
+    bool method4;
+    DpScores scores; FilterOptions fo;
+    uint32_t batchMax;
+    // batch dispenser (method 4 sizes a batch by its grid cells, so the cut is made under the lock, in order)
+    std::mutex dispenserMutex;
+    uint64_t nextBegin = 0, nextIndex = 0;
+    // device-side result arena: segments in completion order + the ledger that puts them back into candidate order
+    struct Segment { uint64_t recordBase = 0, kept = 0, byteBase = 0, bytes = 0; };
+    std::mutex arenaMutex;
+    std::map<uint64_t, Segment> ledger;     // by batch index (guarded by arenaMutex)
     uint64_t outCount = 0, outBytes = 0;
-    unsigned long long* skippedDev = c->scalars.get() + 56;
-    unsigned long long* forwardCellsDev = c->scalars.get() + 57;          // cells of the trace-free stage-1 jobs
-    SHB_CUDA(cudaMemsetAsync(skippedDev, 0, 2 * sizeof(unsigned long long), st));
-    uint64_t dpCells = 0;
-    const std::vector<uint64_t>& toc = c->tocHost;
+    // failure of any worker stops the others
+    std::atomic<bool> failed{false};
+    std::exception_ptr error;
+    std::mutex errorMutex;
+};
 
-    PhaseClock phases;
-    phases.lap(0, st);
-    for(uint64_t begin = 0; begin < n; ) {
-        // Batch size: bounded number of candidates and (method 4) of grid cells.
-        uint32_t nb = 0;
-        if(method4) {
-            uint64_t cells = 0;
-            while(begin + nb < n && nb < batchMax) {
-                const uint64_t i = begin + nb;
-                const uint64_t o0 = 2ull * cand[3*i], o1 = 2ull * cand[3*i+1] + ((cand[3*i+2] & 0xff) ? 0 : 1);
-                const uint64_t nx = toc[o0+1] - toc[o0], ny = toc[o1+1] - toc[o1];
-                uint64_t cc = 2;
-                if(nx && ny) cc += ((nx + ny - 2) / o.align4DeltaX + 1) * ((nx + ny - 2) / o.align4DeltaY + 1);
-                if(nb && cells + cc > cellBudget) break;
-                cells += cc; nb++;
-            }
-        } else nb = uint32_t(std::min<uint64_t>(batchMax, n - begin));
+// Next batch [begin, begin + nb) and its index; false when the candidates are exhausted.
+bool nextBatch(AlignCall& call, uint64_t& begin, uint32_t& nb, uint64_t& index)
+{
+    std::lock_guard<std::mutex> lock(call.dispenserMutex);
+    if(call.nextBegin >= call.n || call.failed.load()) return false;
+    begin = call.nextBegin;
+    nb = 0;
+    if(call.method4) {
+        const std::vector<uint64_t>& toc = call.c->tocHost;
+        const uint64_t cellBudget = 192ull << 20;      // cells of grid scratch per batch
+        uint64_t cells = 0;
+        while(begin + nb < call.n && nb < call.batchMax) {
+            const uint64_t i = begin + nb;
+            const uint64_t o0 = 2ull * call.cand[3*i], o1 = 2ull * call.cand[3*i+1] + ((call.cand[3*i+2] & 0xff) ? 0 : 1);
+            const uint64_t nx = toc[o0+1] - toc[o0], ny = toc[o1+1] - toc[o1];
+            uint64_t cc = 2;
+            if(nx && ny) cc += ((nx + ny - 2) / call.o.align4DeltaX + 1) * ((nx + ny - 2) / call.o.align4DeltaY + 1);
+            if(nb && cells + cc > cellBudget) break;
+            cells += cc; nb++;
+        }
+    } else nb = uint32_t(std::min<uint64_t>(call.batchMax, call.n - begin));
+    index = call.nextIndex++;
+    call.nextBegin += nb;
+    return true;
+}
 
-        b.cand.reserve(3ull * nb);
-        SHB_CUDA(cudaMemcpyAsync(b.cand.get(), cand + 3 * begin, 12ull * nb, cudaMemcpyHostToDevice, st));
-        b.keep.reserve(nb); b.keepIndex.reserve(nb); b.bytes32.reserve(nb); b.bytes64.reserve(nb); b.bytesOff.reserve(nb);
-        b.scanWs64.reserve(scanWorkspaceElements(nb));
-        uint32_t nJobs = 0;
-        const uint32_t* jobIndex = nullptr;
-        DpTotals totals;
-        bool stage1Timed = false;
+// One batch of candidates on one worker, up to the point where its kept alignments sit in the arena.
+void processBatch(AlignCall& call, AlignWorker& w, uint64_t begin, uint32_t nb, uint64_t batchIndex)
+{
+    shb_context* c = call.c;
+    AlignCache& ac = *call.ac;
+    const shb_align_options& o = call.o;
+    cudaStream_t st = w.stream;
+    Batch& b = w.batch;
+    unsigned long long* total64 = w.sc(kScTotal64);
+    uint32_t* total32 = reinterpret_cast<uint32_t*>(w.sc(kScTotal32));
 
-        if(!method4) {
-            // ---- method 3 ---------------------------------------------------------------------------
-            nJobs = nb;
-            b.jobs1.reserve(nb); b.jobs.reserve(nb); b.tw.reserve(nb); b.twOff.reserve(nb); b.outCnt.reserve(nb);
-            SHB_LAUNCH(method3SetupKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb,
-                       (const uint64_t*)c->toc.get(), (const uint64_t*)ac.dsToc.get(), b.jobs1.get(), b.jobs.get(), b.tw.get(), b.outCnt.get(), forwardCellsDev);
+    b.cand.reserve(3ull * nb);
+    SHB_CUDA(cudaMemcpyAsync(b.cand.get(), call.cand + 3 * begin, 12ull * nb, cudaMemcpyHostToDevice, st));
+    b.keep.reserve(nb); b.keepIndex.reserve(nb); b.bytes32.reserve(nb); b.bytes64.reserve(nb); b.bytesOff.reserve(nb);
+    b.scanWs64.reserve(scanWorkspaceElements(nb));
+    w.scanWs.reserve(scanWorkspaceElements(std::max<uint64_t>(nb, 4096)));
+    uint32_t nJobs = 0;
+    const uint32_t* jobIndex = nullptr;
+    bool stage1Timed = false;
+
+    if(!call.method4) {
+        // ---- methods 3 and 1 -----------------------------------------------------------------------
+        const bool method1 = (o.alignMethod == 1);
+        nJobs = nb;
+        b.jobs1.reserve(nb); b.jobs.reserve(nb); b.tw.reserve(nb); b.twOff.reserve(nb); b.outCnt.reserve(nb);
+        SHB_LAUNCH(method3SetupKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb,
+                   (const uint64_t*)c->toc.get(), method1 ? (const uint64_t*)nullptr : (const uint64_t*)ac.dsToc.get(), b.jobs1.get(), b.jobs.get(),
+                   b.tw.get(), b.outCnt.get(), w.sc(kScForwardCells), kMaxBandWidth, w.sc(kScTooWide));
+        if(!method1) {
             exclusiveScan<unsigned long long>(b.tw.get(), b.twOff.get(), nb, total64, b.scanWs64.get(), st);
             const unsigned long long traceWords1 = readBack<unsigned long long>(total64, st);
             b.trace.reserve(traceWords1 + 1);
-            dpCells += 16ull * traceWords1;
+            w.traceWords += traceWords1;
             SHB_LAUNCH(setTraceOffsetsKernel, ceilDiv(nb, 256), 256, 0, st, b.jobs1.get(), nb, (const unsigned long long*)b.twOff.get(),
                        (const unsigned long long*)nullptr);
             // Ordinal slots (also the stage-1 path scratch): offsets must be in jobs[] before stage 1 runs.
@@ -618,11 +569,11 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
             Method3Args g1;
             g1.candidates = b.cand.get(); g1.candidateBegin = begin; g1.n = nb;
             g1.toc = c->toc.get(); g1.dsToc = ac.dsToc.get(); g1.dsKmer = ac.dsKmer.get(); g1.dsOrdinal = ac.dsOrdinal.get();
-            g1.scores = scores; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
+            g1.scores = call.scores; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
             std::vector<uint64_t> classCounts1;
-            buildClassOrder(c, b, b.jobs1.get(), nb, classCounts1, kForwardClassCount);
-            SHB_CUDA(cudaEventRecord(dpEv1.a, st));
-            forEachClassConcurrently(c, classCounts1, 0xffffffffu, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
+            buildClassOrder(w, b.jobs1.get(), nb, classCounts1, kForwardClassCount);
+            SHB_CUDA(cudaEventRecord(w.dp1a, st));
+            forEachClassConcurrently(w, classCounts1, 0xffffffffu, [&](int k, uint32_t count, uint64_t offset, cudaStream_t s) {
                 Method3Args gk = g1;
                 gk.n = count; gk.order = b.order + offset;
                 if(k < kForwardClassCount) {
@@ -637,143 +588,293 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                 gk.wMax = cls.wMax;
                 launchStage1(cls, ceilDiv(count, warps), warps * 32, smem, s, gk, b.jobs1.get(), b.trace.get(), b.jobs.get(), b.ordinals.get());
             });
-            SHB_CUDA(cudaEventRecord(dpEv1.b, st));
-            phases.lap(1, st);
-            if(phases.on && begin == 0) {        // SHB_TRACE: band-width and active-column statistics of the first batch
+            SHB_CUDA(cudaEventRecord(w.dp1b, st));
+            stage1Timed = true;
+            if(getenv("SHB_TRACE") && begin == 0) {        // band-width and active-column statistics of the first batch
                 std::vector<DpJob> h(nb);
-                SHB_CUDA(cudaMemcpy(h.data(), b.jobs.get(), sizeof(DpJob) * nb, cudaMemcpyDeviceToHost));
+                SHB_CUDA(cudaMemcpyAsync(h.data(), b.jobs.get(), sizeof(DpJob) * nb, cudaMemcpyDeviceToHost, st));
+                SHB_CUDA(cudaStreamSynchronize(st));
                 uint64_t hist[12] = {0}, run = 0, cols = 0, fullCols = 0;
                 for(const DpJob& j : h) {
                     if(j.state != kStateRun) continue;
                     run++;
-                    const uint32_t w = uint32_t(j.hi - j.lo + 1);
-                    hist[std::min<uint32_t>(11, (w + 7) / 8)]++;
+                    const uint32_t wd = uint32_t(j.hi - j.lo + 1);
+                    hist[std::min<uint32_t>(11, (wd + 7) / 8)]++;
                     cols += uint64_t(dpLastColumn(j.nx, j.ny, j.hi) - dpFirstColumn(j.lo)); fullCols += j.nx;
                 }
                 fprintf(stderr, "[shb] stage-2 jobs %llu of %u; band width histogram (bins of 8 offsets, last = wider):", (unsigned long long)run, nb);
                 for(int k = 0; k < 12; k++) fprintf(stderr, " %llu", (unsigned long long)hist[k]);
                 fprintf(stderr, "; active columns %.1f of %.1f per job\n", double(cols) / double(run ? run : 1), double(fullCols) / double(run ? run : 1));
             }
-            SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());
-            runBandedJobs(c, b, nJobs, c->kmerIds, scores, dpEv2, totals);
-            phases.lap(2, st);
-            // Epilogue per job == per candidate.
-            b.infoWords.reserve(13ull * nJobs);
-            SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
-                       (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.keep.get(), b.bytes32.get(), skippedDev);
-            stage1Timed = true;
-        } else {
-            // ---- method 4 ---------------------------------------------------------------------------
-            b.cellCnt.reserve(nb); b.cellOff.reserve(nb); b.componentCount.reserve(nb); b.jobOffsets.reserve(nb); b.selected.reserve(nb);
-            SHB_LAUNCH(align4CellCountKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb, (const uint64_t*)c->toc.get(),
-                       uint32_t(o.align4DeltaX), uint32_t(o.align4DeltaY), b.cellCnt.get());
-            exclusiveScan<unsigned long long>(b.cellCnt.get(), b.cellOff.get(), nb, total64, b.scanWs64.get(), st);
-            const unsigned long long cells = readBack<unsigned long long>(total64, st);
-            b.gridCounts.reserve(cells + 1); b.gridAux.reserve(cells + 1); b.gridList.reserve(cells + 1);
-            b.gridFlags.reserve(cells + 1); b.gridBands.reserve(cells + 1);
-            Align4Args g;
-            g.candidates = b.cand.get(); g.n = nb; g.toc = c->toc.get();
-            g.sortedKmer = ac.sortedKmer.get(); g.sortedOrdinal = ac.sortedOrdinal.get();
-            g.deltaX = uint32_t(o.align4DeltaX); g.deltaY = uint32_t(o.align4DeltaY);
-            g.minEntryCountPerCell = o.align4MinEntryCountPerCell; g.maxDistanceFromBoundary = o.align4MaxDistanceFromBoundary;
-            g.maxBand = int64_t(uint64_t(o.maxBand));
-            g.cellOffsets = b.cellOff.get(); g.counts = b.gridCounts.get(); g.aux = b.gridAux.get(); g.list = b.gridList.get();
-            g.flags = b.gridFlags.get(); g.bands = b.gridBands.get(); g.componentCount = b.componentCount.get();
-            SHB_LAUNCH(align4FrontEndKernel, ceilDiv(nb, 4), 128, 0, st, g);
-            exclusiveScan<uint32_t>(b.componentCount.get(), b.jobOffsets.get(), nb, total32, c->scanWs.get(), st);
-            nJobs = readBack<uint32_t>(total32, st);
-            if(nJobs) {
-                b.jobs.reserve(nJobs); b.tw.reserve(nJobs); b.outCnt.reserve(nJobs);
-                SHB_LAUNCH(align4MakeJobsKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb, (const uint64_t*)c->toc.get(),
-                           (const unsigned long long*)b.cellOff.get(), (const int32_t*)b.gridBands.get(),
-                           (const uint32_t*)b.componentCount.get(), (const uint32_t*)b.jobOffsets.get(), b.jobs.get(), b.tw.get(), b.outCnt.get());
-                runBandedJobs(c, b, nJobs, c->kmerIds, scores, dpEv2, totals);
-                b.infoWords.reserve(13ull * nJobs); b.jobKeep.reserve(nJobs); b.jobBytes.reserve(nJobs);
-                // Align4's own filters (src/Align4.cpp:944-985), identical thresholds, no containment test.
-                SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
-                           (const uint32_t*)b.counts.get(), fo, b.infoWords.get(), b.jobKeep.get(), b.jobBytes.get(),
-                           (unsigned long long*)nullptr);
-            } else {
-                b.infoWords.reserve(13); b.jobKeep.reserve(1); b.jobBytes.reserve(1); b.jobs.reserve(1); b.counts.reserve(1); b.ordinals.reserve(1);
-            }
-            SHB_LAUNCH(align4SelectKernel, ceilDiv(nb, 256), 256, 0, st, nb, (const uint32_t*)b.jobOffsets.get(),
-                       (const uint32_t*)b.componentCount.get(), (const uint32_t*)b.jobKeep.get(), (const uint32_t*)b.infoWords.get(),
-                       (const uint32_t*)b.jobBytes.get(), o.suppressContainments ? 1u : 0u, uint32_t(o.maxTrim),
-                       b.selected.get(), b.keep.get(), b.bytes32.get());
-            jobIndex = b.selected.get();
         }
-        dpCells += 16ull * totals.traceWords;
-
-        // ---- compaction + output of the kept alignments ---------------------------------------------------
-        phases.lap(3, st);
-        exclusiveScan<uint32_t>(b.keep.get(), b.keepIndex.get(), nb, total32, c->scanWs.get(), st);
-        const uint32_t kept = readBack<uint32_t>(total32, st);
-        SHB_LAUNCH(widenBytesKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.bytes32.get(), nb, b.bytes64.get());
-        exclusiveScan<unsigned long long>(b.bytes64.get(), b.bytesOff.get(), nb, total64, b.scanWs64.get(), st);
-        const unsigned long long bytes = readBack<unsigned long long>(total64, st);
+        SHB_LAUNCH(stage2TraceWordsKernel, ceilDiv(nb, 256), 256, 0, st, (const DpJob*)b.jobs.get(), nb, b.tw.get());
+        runBandedJobs(w, nJobs, c->kmerIds, call.scores);
+        // Epilogue per job == per candidate.
+        b.infoWords.reserve(13ull * nJobs);
+        SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
+                   (const uint32_t*)b.counts.get(), call.fo, b.infoWords.get(), b.keep.get(), b.bytes32.get(), w.sc(kScSkipped));
+    } else {
+        // ---- method 4 ---------------------------------------------------------------------------
+        b.cellCnt.reserve(nb); b.cellOff.reserve(nb); b.componentCount.reserve(nb); b.jobOffsets.reserve(nb); b.selected.reserve(nb);
+        SHB_LAUNCH(align4CellCountKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb, (const uint64_t*)c->toc.get(),
+                   uint32_t(o.align4DeltaX), uint32_t(o.align4DeltaY), b.cellCnt.get());
+        exclusiveScan<unsigned long long>(b.cellCnt.get(), b.cellOff.get(), nb, total64, b.scanWs64.get(), st);
+        const unsigned long long cells = readBack<unsigned long long>(total64, st);
+        b.gridCounts.reserve(cells + 1); b.gridAux.reserve(cells + 1); b.gridList.reserve(cells + 1);
+        b.gridFlags.reserve(cells + 1); b.gridBands.reserve(cells + 1);
+        Align4Args g;
+        g.candidates = b.cand.get(); g.n = nb; g.toc = c->toc.get();
+        g.sortedKmer = ac.sortedKmer.get(); g.sortedOrdinal = ac.sortedOrdinal.get();
+        g.deltaX = uint32_t(o.align4DeltaX); g.deltaY = uint32_t(o.align4DeltaY);
+        g.minEntryCountPerCell = o.align4MinEntryCountPerCell; g.maxDistanceFromBoundary = o.align4MaxDistanceFromBoundary;
+        g.maxBand = int64_t(uint64_t(o.maxBand));
+        g.cellOffsets = b.cellOff.get(); g.counts = b.gridCounts.get(); g.aux = b.gridAux.get(); g.list = b.gridList.get();
+        g.flags = b.gridFlags.get(); g.bands = b.gridBands.get(); g.componentCount = b.componentCount.get();
+        SHB_LAUNCH(align4FrontEndKernel, ceilDiv(nb, 4), 128, 0, st, g);
+        exclusiveScan<uint32_t>(b.componentCount.get(), b.jobOffsets.get(), nb, total32, w.scanWs.get(), st);
+        nJobs = readBack<uint32_t>(total32, st);
         if(nJobs) {
-            float ms = 0.f;
-            SHB_CUDA(cudaEventElapsedTime(&ms, dpEv2.a, dpEv2.b));
-            dpMs += ms;
+            b.jobs.reserve(nJobs); b.tw.reserve(nJobs); b.outCnt.reserve(nJobs);
+            SHB_LAUNCH(align4MakeJobsKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.cand.get(), nb, (const uint64_t*)c->toc.get(),
+                       (const unsigned long long*)b.cellOff.get(), (const int32_t*)b.gridBands.get(),
+                       (const uint32_t*)b.componentCount.get(), (const uint32_t*)b.jobOffsets.get(), b.jobs.get(), b.tw.get(), b.outCnt.get());
+            runBandedJobs(w, nJobs, c->kmerIds, call.scores);
+            b.infoWords.reserve(13ull * nJobs); b.jobKeep.reserve(nJobs); b.jobBytes.reserve(nJobs);
+            // Align4's own filters (src/Align4.cpp:944-985), identical thresholds, no containment test.
+            SHB_LAUNCH(alignmentInfoKernel, ceilDiv(nJobs, 4), 128, 0, st, nJobs, (const DpJob*)b.jobs.get(), (const uint2*)b.ordinals.get(),
+                       (const uint32_t*)b.counts.get(), call.fo, b.infoWords.get(), b.jobKeep.get(), b.jobBytes.get(),
+                       (unsigned long long*)nullptr);
+        } else {
+            b.infoWords.reserve(13); b.jobKeep.reserve(1); b.jobBytes.reserve(1); b.jobs.reserve(1); b.counts.reserve(1); b.ordinals.reserve(1);
         }
-        if(stage1Timed) {
-            float ms = 0.f;
-            SHB_CUDA(cudaEventElapsedTime(&ms, dpEv1.a, dpEv1.b));
-            dpMs += ms;
-        }
+        SHB_LAUNCH(align4SelectKernel, ceilDiv(nb, 256), 256, 0, st, nb, (const uint32_t*)b.jobOffsets.get(),
+                   (const uint32_t*)b.componentCount.get(), (const uint32_t*)b.jobKeep.get(), (const uint32_t*)b.infoWords.get(),
+                   (const uint32_t*)b.jobBytes.get(), o.suppressContainments ? 1u : 0u, uint32_t(o.maxTrim),
+                   b.selected.get(), b.keep.get(), b.bytes32.get());
+        jobIndex = b.selected.get();
+    }
+
+    // ---- compaction + output of the kept alignments ---------------------------------------------------
+    exclusiveScan<uint32_t>(b.keep.get(), b.keepIndex.get(), nb, total32, w.scanWs.get(), st);
+    SHB_LAUNCH(widenBytesKernel, ceilDiv(nb, 256), 256, 0, st, (const uint32_t*)b.bytes32.get(), nb, b.bytes64.get());
+    exclusiveScan<unsigned long long>(b.bytes64.get(), b.bytesOff.get(), nb, total64, b.scanWs64.get(), st);
+    struct { unsigned long long bytes; uint32_t kept; } totals;
+    SHB_CUDA(cudaMemcpyAsync(&totals.bytes, total64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SHB_CUDA(cudaMemcpyAsync(&totals.kept, total32, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SHB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t kept = totals.kept;
+    const unsigned long long bytes = totals.bytes;
+    if(nJobs) {
+        float ms = 0.f;
+        SHB_CUDA(cudaEventElapsedTime(&ms, w.dp2a, w.dp2b));
+        w.dpMs += ms;
+    }
+    if(stage1Timed) {
+        float ms = 0.f;
+        SHB_CUDA(cudaEventElapsedTime(&ms, w.dp1a, w.dp1b));
+        w.dpMs += ms;
+    }
+    {
+        // The arena may have to grow (realloc + copy): writers hold the lock until their kernel has finished, so nothing
+        // is in flight into the arena while another worker moves it.
+        std::lock_guard<std::mutex> lock(call.arenaMutex);
+        AlignCall::Segment seg;
+        seg.recordBase = call.outCount; seg.kept = kept; seg.byteBase = call.outBytes; seg.bytes = bytes;
         if(kept) {
-            outRecords.reserve(16ull * (outCount + kept), true, st);
-            outToc.reserve(outCount + kept + 1, true, st);
-            outData.reserve(outBytes + bytes + 16, true, st);
+            ac.outRecords.reserve(16ull * (call.outCount + kept), true, st);
+            ac.outToc.reserve(call.outCount + kept + 1, true, st);
+            ac.outData.reserve(call.outBytes + bytes + 16, true, st);
+            // compressedToc entries are written as arena offsets; computeAlignments rebases them once the final order of the
+            // segments is known.
             SHB_LAUNCH(alignmentWriteKernel, ceilDiv(nb, 4), 128, 0, st, nb, (const uint32_t*)b.cand.get(), (const DpJob*)b.jobs.get(),
                        (const uint2*)b.ordinals.get(), (const uint32_t*)b.counts.get(), (const uint32_t*)b.infoWords.get(), jobIndex,
                        (const uint32_t*)b.keep.get(), (const uint32_t*)b.keepIndex.get(), (const unsigned long long*)b.bytesOff.get(),
-                       outCount, outBytes, outRecords.get(), outToc.get(), outData.get());
-            outCount += kept;
-            outBytes += bytes;
+                       call.outCount, call.outBytes, ac.outRecords.get(), ac.outToc.get(), ac.outData.get());
+            SHB_CUDA(cudaStreamSynchronize(st));
+            call.outCount += kept;
+            call.outBytes += bytes;
         }
-        phases.lap(4, st);
-        begin += nb;
+        call.ledger[batchIndex] = seg;
+    }
+}
+
+void workerMain(AlignCall& call, AlignWorker& w)
+{
+    try {
+        SHB_CUDA(cudaSetDevice(call.c->device));
+        g_launchCount = 0;
+        w.dpMs = 0.; w.traceWords = 0;
+        SHB_CUDA(cudaMemsetAsync(w.scalars.get(), 0, kScCount * sizeof(unsigned long long), w.stream));
+        uint64_t begin = 0, index = 0; uint32_t nb = 0;
+        while(nextBatch(call, begin, nb, index)) processBatch(call, w, begin, nb, index);
+        SHB_CUDA(cudaStreamSynchronize(w.stream));
+    } catch(...) {
+        std::lock_guard<std::mutex> lock(call.errorMutex);
+        if(!call.error) call.error = std::current_exception();
+        call.failed.store(true);
+    }
+    w.launches = g_launchCount;
+}
+
+// toc[k] += delta for the n entries of one segment.
+__global__ void rebaseTocKernel(unsigned long long* __restrict__ toc, uint64_t n, long long delta)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i < n) toc[i] = (unsigned long long)((long long)toc[i] + delta);
+}
+
+} // namespace
+
+void destroyAlignCache(shb_context* c)
+{
+    if(c->alignCache) { delete static_cast<AlignCache*>(c->alignCache); c->alignCache = nullptr; }
+}
+
+
+// explicitOrientation: the candidates may carry kCandidateStrand0Bit and need not satisfy readId0 < readId1
+// (shb_align_oriented_reads); computeAlignments proper rejects both, like the reference (src/AssemblerAlign.cpp:378).
+void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, const shb_align_options& o,
+                       void** alignmentDataOut, uint64_t* alignmentCountOut,
+                       uint64_t** compressedTocOut, uint8_t** compressedDataOut, shb_align_result* result,
+                       bool explicitOrientation)
+{
+    SHB_REQUIRE(c->haveMarkers, SHB_ERR_STATE, "Markers are not accessible.");
+    SHB_REQUIRE(c->readBegin == 0 && c->readEnd == c->readCountTotal, SHB_ERR_STATE,
+                "computeAlignments needs the markers of all reads on this GPU.");
+    SHB_REQUIRE(o.alignMethod == 1 || o.alignMethod == 3 || o.alignMethod == 4, SHB_ERR_INVALID,
+                "Only Align.alignMethod 1, 3 and 4 are implemented (0, the AlignmentGraph method, is not on the hot path).");
+    SHB_REQUIRE(o.gapScore <= 0, SHB_ERR_INVALID, "Align.gapScore must not be positive.");
+    SHB_REQUIRE(o.k >= 1 && o.k <= 16, SHB_ERR_INVALID, "Invalid k.");
+    SHB_REQUIRE(n == 0 || candidatesHost != nullptr, SHB_ERR_INVALID, "Null candidates.");
+    SHB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    g_launchCount = 0;
+    const auto wall0 = std::chrono::steady_clock::now();
+    Events totalEv;
+    SHB_CUDA(cudaEventRecord(totalEv.a, st));
+
+    AlignCall call;
+    call.c = c; call.ac = &cache(c); call.o = o; call.n = n;
+    call.method4 = (o.alignMethod == 4);
+    // src/AssemblerAlign.cpp:378 asserts readIds[0] < readIds[1].
+    call.cand = static_cast<const uint32_t*>(candidatesHost);
+    for(uint64_t i = 0; i < n; i++) {
+        const uint32_t r0 = call.cand[3*i], r1 = call.cand[3*i+1], w = call.cand[3*i+2];
+        if(explicitOrientation) SHB_REQUIRE(r0 < c->readCountTotal && r1 < c->readCountTotal && (w & ~(0xffu | kCandidateStrand0Bit)) == 0,
+                                            SHB_ERR_INVALID, "Invalid oriented read pair.");
+        else SHB_REQUIRE(r0 < r1 && r1 < c->readCountTotal && (w & 0xffffff00u) == 0, SHB_ERR_INVALID, "Invalid alignment candidate.");
     }
 
-    const uint64_t count = outCount;
-    SHB_CUDA(cudaStreamSynchronize(st));
+    AlignCache& ac = *call.ac;
+    if(call.method4) {
+        SHB_REQUIRE(o.align4DeltaX >= 1 && o.align4DeltaY >= 1 && o.align4DeltaX < (1ull << 31) && o.align4DeltaY < (1ull << 31),
+                    SHB_ERR_INVALID, "Invalid Align.align4.deltaX / deltaY.");
+        buildSortedMarkers(c, o.k);
+    } else if(o.alignMethod == 3) {
+        buildDownsampled(c, o.k, o.downsamplingFactor);
+    }
+    if(ac.lengthCheckGeneration != c->markerGeneration) {       // the traceback packs a run length above a 28-bit ordinal
+        for(size_t r = 0; r + 1 < c->tocHost.size(); r++) {     // (the reference's Uint24 positions cap a read at 2^24 markers anyway)
+            SHB_REQUIRE(c->tocHost[r + 1] - c->tocHost[r] < (1ull << kRunLengthShift), SHB_ERR_INVALID, "A read has 2^28 or more markers.");
+        }
+        ac.lengthCheckGeneration = c->markerGeneration;
+    }
+    const uint32_t maxStage2Width = uint32_t(std::max(0, o.maxBand)) + 3 + 64;     // W <= maxBand + 1, two barriers, padded to 64
+    SHB_REQUIRE(maxStage2Width <= kMaxBandWidth, SHB_ERR_INVALID, "Align.maxBand too large for this implementation (limit 16317).");
+
+    // Methods 1 and 3 use the configured scores; Align4 hard-codes 6/-1/-1 (src/Align4.hpp:159-161: never overwritten).
+    call.scores = call.method4 ? DpScores{6, -1, -1} : DpScores{o.matchScore, o.mismatchScore, o.gapScore};
+    call.fo.minAlignedMarkerCount = uint64_t(o.minAlignedMarkerCount); call.fo.maxSkip = uint64_t(o.maxSkip);
+    call.fo.maxDrift = uint64_t(o.maxDrift); call.fo.maxTrim = uint64_t(o.maxTrim);
+    call.fo.minAlignedFraction = o.minAlignedFraction;
+    call.fo.suppressContainments = (!call.method4 && o.suppressContainments) ? 1u : 0u;     // method 4 applies it after the selection
+
+    // SHB_ALIGN_BATCH / SHB_ALIGN_CHUNK / SHB_ALIGN_WORKERS: test hooks that shrink the batch and chunk sizes so that small
+    // inputs exercise the multi-batch, multi-chunk, multi-worker paths (tests/test_gpu_scale.py).
+    call.batchMax = envCount("SHB_ALIGN_BATCH", call.method4 ? 32768 : (o.alignMethod == 1 ? 16384 : 262144));
+    const uint64_t batchEstimate = (n + call.batchMax - 1) / call.batchMax;
+    const uint32_t workerCount = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(envCount("SHB_ALIGN_WORKERS", 2), batchEstimate)));
+    while(ac.workers.size() < workerCount) ac.workers.emplace_back(new AlignWorker());
+    for(uint32_t k = 0; k < workerCount; k++) ac.workers[k]->init();
+    SHB_CUDA(cudaStreamSynchronize(st));        // derived marker data ready before the workers read it
+
+    if(n) {
+        // Always on their own threads (also a single worker), so that the launch counters stay per thread.
+        std::vector<std::thread> threads;
+        for(uint32_t k = 0; k < workerCount; k++) threads.emplace_back([&call, &ac, k] { workerMain(call, *ac.workers[k]); });
+        for(std::thread& t : threads) t.join();
+        if(call.error) std::rethrow_exception(call.error);
+    }
+
+    // ---- results: segments back into candidate order, digests, copy to the host --------------------------------------
+    const uint64_t count = call.outCount, outBytes = call.outBytes;
     const auto copy0 = std::chrono::steady_clock::now();
-    void* recOut = allocHostResult(64 * count);
-    uint64_t* tocOut = (uint64_t*)allocHostResult(8 * (count + 1));
-    uint8_t* dataOut = (uint8_t*)allocHostResult(outBytes);
-    SHB_REQUIRE(recOut && tocOut && dataOut, SHB_ERR_OOM, "Out of host memory for the alignments.");
+    HostResult recOut(allocHostResult(64 * count)), tocOut(allocHostResult(8 * (count + 1))), dataOut(allocHostResult(outBytes));
+    SHB_REQUIRE(recOut.p && tocOut.p && dataOut.p, SHB_ERR_OOM, "Out of host memory for the alignments.");
+    unsigned long long* digests = c->scalars.get() + 58;
+    SHB_CUDA(cudaMemsetAsync(digests, 0, 2 * sizeof(unsigned long long), st));
     if(count) {
-        copyToHostPipelined(c, recOut, outRecords.get(), 64 * count);
-        copyToHostPipelined(c, tocOut, outToc.get(), 8 * count);
-        copyToHostPipelined(c, dataOut, outData.get(), outBytes);
+        const bool lockedRec = HostPool::instance().isPageLocked(recOut.p), lockedToc = HostPool::instance().isPageLocked(tocOut.p),
+                   lockedData = HostPool::instance().isPageLocked(dataOut.p);
+        uint64_t finalRecords = 0, finalBytes = 0;
+        for(const auto& entry : call.ledger) {
+            const AlignCall::Segment& seg = entry.second;
+            if(!seg.kept) continue;
+            unsigned long long* segToc = ac.outToc.get() + seg.recordBase;
+            const long long delta = (long long)finalBytes - (long long)seg.byteBase;     // the write kernel stored byteBase + offset
+            if(delta) SHB_LAUNCH(rebaseTocKernel, ceilDiv(seg.kept, 256), 256, 0, st, segToc, seg.kept, delta);
+            SHB_LAUNCH(digestRecordsKernel, ceilDiv(seg.kept, 256), 256, 0, st, (const uint32_t*)ac.outRecords.get() + 16 * seg.recordBase,
+                       seg.kept, 16u, digests);
+            SHB_LAUNCH(digestCompressedKernel, ceilDiv(seg.kept, 256), 256, 0, st, (const uint32_t*)ac.outRecords.get() + 16 * seg.recordBase,
+                       seg.kept, (const unsigned long long*)segToc, finalBytes + seg.bytes,
+                       (const uint8_t*)ac.outData.get() + seg.byteBase - finalBytes, digests);
+            copyToHostPipelined(c, static_cast<uint8_t*>(recOut.p) + 64 * finalRecords, ac.outRecords.get() + 16 * seg.recordBase, 64 * seg.kept, lockedRec);
+            copyToHostPipelined(c, static_cast<uint8_t*>(tocOut.p) + 8 * finalRecords, segToc, 8 * seg.kept, lockedToc);
+            copyToHostPipelined(c, static_cast<uint8_t*>(dataOut.p) + finalBytes, ac.outData.get() + seg.byteBase, seg.bytes, lockedData);
+            finalRecords += seg.kept; finalBytes += seg.bytes;
+        }
         SHB_CUDA(cudaStreamSynchronize(st));
     }
-    const unsigned long long skipped = readBack<unsigned long long>(skippedDev, st);
-    dpCells += readBack<unsigned long long>(forwardCellsDev, st);
-    phases.lap(5, st);
-    {
-        static const char* const names[] = {"prepare", "setup+stage1", "stage2", "epilogue", "compact+write", "copy_to_host"};
-        phases.report(names, 6);
-        if(phases.on) {
-            fprintf(stderr, "[shb] stage-2 detail (ms): dp+traceback+filter=%.1f setup=%.1f\n", g_tracePhaseMs[2], g_tracePhaseMs[3]);
-            for(double& v : g_tracePhaseMs) v = 0.;
-        }
+    // Counters of the workers.
+    unsigned long long skipped = 0, forwardCells = 0, tooWide = 0, bandCells = 0, digestHost[2] = {0, 0};
+    uint64_t traceWords = 0, launches = g_launchCount;
+    double dpMs = 0.;
+    for(uint32_t k = 0; k < workerCount && n; k++) {
+        AlignWorker& w = *ac.workers[k];
+        unsigned long long h[6];
+        SHB_CUDA(cudaMemcpyAsync(h, w.scalars.get(), sizeof(h), cudaMemcpyDeviceToHost, st));
+        SHB_CUDA(cudaStreamSynchronize(st));
+        skipped += h[kScSkipped]; forwardCells += h[kScForwardCells]; tooWide += h[kScTooWide]; bandCells += h[kScBandCells];
+        traceWords += w.traceWords; launches += w.launches; dpMs += w.dpMs;
     }
-    tocOut[count] = outBytes;
-    if(count == 0) tocOut[0] = 0;
+    SHB_CUDA(cudaMemcpyAsync(digestHost, digests, sizeof(digestHost), cudaMemcpyDeviceToHost, st));
+    SHB_CUDA(cudaStreamSynchronize(st));
+    uint64_t* tocHostOut = static_cast<uint64_t*>(tocOut.p);
+    tocHostOut[count] = outBytes;
+    if(count == 0) tocHostOut[0] = 0;
     SHB_CUDA(cudaEventRecord(totalEv.b, st));
     SHB_CUDA(cudaStreamSynchronize(st));
     float totalMs = 0.f;
     SHB_CUDA(cudaEventElapsedTime(&totalMs, totalEv.a, totalEv.b));
-    *alignmentDataOut = recOut; *alignmentCountOut = count; *compressedTocOut = tocOut; *compressedDataOut = dataOut;
+    if(getenv("SHB_TRACE")) {
+        fprintf(stderr, "[shb] computeAlignments: %u worker(s), %llu batches, %llu candidates skipped as too wide for the DP kernels\n",
+                workerCount, (unsigned long long)call.ledger.size(), tooWide);
+    }
     if(result) {
+        memset(result, 0, sizeof(*result));
         result->candidateCount = n; result->alignmentCount = count; result->skippedCount = skipped;
-        result->dpCells = dpCells; result->dpMs = dpMs; result->totalMs = totalMs; result->kernelLaunches = g_launchCount;
+        result->dpCells = 16ull * traceWords + forwardCells;
+        result->dpUsefulCells = bandCells + forwardCells;
+        result->tooWideCount = tooWide;
+        result->dpMs = dpMs / double(workerCount); result->totalMs = totalMs; result->kernelLaunches = launches;
+        result->alignmentDataDigest = digestHost[0]; result->compressedDigest = digestHost[1];
+        result->workers = workerCount;
         const auto wall1 = std::chrono::steady_clock::now();
         result->outputCopyMs = std::chrono::duration<double, std::milli>(wall1 - copy0).count();
         result->hostWallMs = std::chrono::duration<double, std::milli>(wall1 - wall0).count();
     }
+    *alignmentDataOut = recOut.take(); *alignmentCountOut = count;
+    *compressedTocOut = static_cast<uint64_t*>(tocOut.take()); *compressedDataOut = static_cast<uint8_t*>(dataOut.take());
 }
 
 } // namespace shb

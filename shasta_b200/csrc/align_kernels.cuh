@@ -8,6 +8,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "../../include/shb_dp_policy.h"
 
 namespace shb {
 
@@ -91,10 +92,40 @@ constexpr uint32_t kStateRun = 0, kStateEmpty = 1, kStateSkipped = 2;
 
 struct DpScores { int32_t match, mismatch, gap; };
 
+// The two oriented reads of candidate p (src/AssemblerAlign.cpp:381-382): (readId0, strand 0) and (readId1, sameStrand ? 0 : 1).
+// Bit 8 of the third word (never set by computeAlignments' callers: the record's padding is zero) flips both strands: the
+// single-pair entry point shb_align_oriented_reads uses it to align a pair in exactly the orientation it was given.
+constexpr uint32_t kCandidateStrand0Bit = 0x100u;
+__device__ __forceinline__ void candidateOrientedReads(const uint32_t* __restrict__ candidates, uint64_t p, uint64_t& o0, uint64_t& o1)
+{
+    const uint32_t r0 = candidates[3ull * p], r1 = candidates[3ull * p + 1], w = candidates[3ull * p + 2];
+    const uint32_t strand0 = (w & kCandidateStrand0Bit) ? 1u : 0u;
+    const bool same = (w & 0xffu) != 0;
+    o0 = 2ull * r0 + strand0;
+    o1 = 2ull * r1 + (same ? strand0 : 1u - strand0);
+}
+
 constexpr int32_t kNegInf = -(1 << 29);
 constexpr int kDpMaxWarpsPerBlock = 4;
 
-__host__ __device__ inline uint32_t dpPaddedWidth(int32_t lo, int32_t hi) { return (uint32_t(hi - lo + 1) + 63u) & ~63u; }
+// Tie-break rules (include/shb_dp_policy.h, shared with the CPU oracle): which move wins when two give the same score.
+//   viaGap  : the cell takes the better gap move g = gapIn + gap instead of the diagonal move
+//   horzWins: of the two gap inputs the horizontal one is taken
+__device__ __forceinline__ bool dpViaGap(int32_t g, int32_t diag) { return SHB_DP_DIAG_WINS_TIES ? (g > diag) : (g >= diag); }
+__device__ __forceinline__ bool dpHorzWins(int32_t horzIn, int32_t vertIn) { return SHB_DP_VERT_BEFORE_HORZ ? (horzIn > vertIn) : (horzIn >= vertIn); }
+// End cell: candidate (s2,i2,j2) replaces (s,i,j)? Column-major visiting order = (i, then j) ascending.
+__device__ __forceinline__ bool dpEndCellBetter(int32_t s2, int32_t i2, int32_t j2, int32_t s, int32_t i, int32_t j)
+{
+    if(s2 != s) return s2 > s;
+    return SHB_DP_END_FIRST_MAX ? (i2 < i || (i2 == i && j2 < j)) : (i2 > i || (i2 == i && j2 > j));
+}
+constexpr int32_t kEndCellNone = SHB_DP_END_FIRST_MAX ? 0x7fffffff : -1;        // bestI / bestJ of "no candidate yet"
+
+// Physical band layout of the wavefront kernels: band offset e = j - i + hi in [0, W) sits at physical offset p = e + 1;
+// p = 0 and p = W + 1 are BARRIER offsets whose gap score is "minus infinity", so that nothing flows around the band
+// edges; physical offsets beyond W + 1 are padding that only the barrier ever reads. Width classes are multiples of 64.
+__host__ __device__ inline uint32_t dpPaddedWidth(int32_t lo, int32_t hi) { return (uint32_t(hi - lo + 1) + 2u + 63u) & ~63u; }
+constexpr int32_t kGapBarrier = -(1 << 28);
 // Columns of the matrix that hold at least one in-band cell: max(0, lo) <= i <= min(nx, ny + hi). The wavefront kernel
 // only visits these (a band that enters through the top edge or leaves through the bottom edge skips the rest).
 constexpr uint32_t kDpWavefrontMaxWidth = 1024;
@@ -174,7 +205,8 @@ __device__ inline void bandedOverlapDp(const uint32_t* __restrict__ a, uint32_t 
             uint32_t code = 0;
             if(valid && !boundary) {
                 const int32_t vert = below + sc.gap;
-                code = (horz > max(diag, vert)) ? 3u : ((vert > diag) ? 2u : 1u);
+                const bool horzWins = dpHorzWins(horz, vert);
+                code = dpViaGap(max(horz, vert), diag) ? (horzWins ? 3u : 2u) : 1u;
             }
             hCur[e] = H;
             uint32_t acc = (traceAcc[e] >> 2) | (code << 30);
@@ -192,13 +224,13 @@ __device__ inline void bandedOverlapDp(const uint32_t* __restrict__ a, uint32_t 
 #pragma unroll
                 for(int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
                 const unsigned who = __ballot_sync(0xffffffffu, valid && H == mx);
-                if(who && mx > bestScore) {
-                    const int first = __ffs(who) - 1;
-                    bestScore = mx; bestI = i; bestJ = ((c << 5) + first) + i - hi;
+                if(who && (SHB_DP_END_FIRST_MAX ? (mx > bestScore) : (mx >= bestScore))) {
+                    const int pick = SHB_DP_END_FIRST_MAX ? (__ffs(who) - 1) : (31 - __clz(who));
+                    bestScore = mx; bestI = i; bestJ = ((c << 5) + pick) + i - hi;
                 }
             } else if(eLastRow >= (c << 5) && eLastRow < (c << 5) + 32 && eLastRow < W && eLastRow >= 0) {
                 const int32_t s = __shfl_sync(0xffffffffu, H, eLastRow & 31);
-                if(s > bestScore) { bestScore = s; bestI = i; bestJ = int32_t(ny); }
+                if(SHB_DP_END_FIRST_MAX ? (s > bestScore) : (s >= bestScore)) { bestScore = s; bestI = i; bestJ = int32_t(ny); }
             }
         }
         __syncwarp();
@@ -207,54 +239,59 @@ __device__ inline void bandedOverlapDp(const uint32_t* __restrict__ a, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Register-resident wavefront version of the same DP for bands of up to 64*C offsets (C <= 16).
-// The band offsets are cut into 64 sub-chunks of C consecutive offsets; lane l owns sub-chunks 2l ("A") and 2l+1
-// ("B"). Cell (i, e) depends on (i-1, e), (i-1, e+1) and (i, e-1), so sub-chunk s can process column i at step
-// T = 2i + s: on even steps every lane advances its A sub-chunk, on odd steps its B sub-chunk (no divergence, every
-// lane busy every step), and the only inter-lane traffic is one shuffle per step (the neighbouring sub-chunk's
-// boundary score). All scores of the previous column live in registers; no shared memory, no scan.
-// Same recurrence, tie-break and end-cell rules as bandedOverlapDp (bit-identical results, tested against the oracle);
-// the end cell is selected with the order-independent formulation "maximum score, then smallest i, then smallest j".
+// Register-resident wavefront version of the same DP for bands of up to 64*C - 2 offsets (C <= 16).
+// The 64*C PHYSICAL offsets (band offset e at p = e + 1, barriers at p = 0 and p = W + 1, see dpPaddedWidth) are cut into
+// 64 sub-chunks of C consecutive offsets; lane l owns sub-chunks 2l ("A") and 2l+1 ("B"). Cell (i, p) depends on (i-1, p),
+// (i-1, p+1) and (i, p-1), so sub-chunk s can process column i at step T = 2i + s: on even steps every lane advances its A
+// sub-chunk, on odd steps its B sub-chunk (no divergence, every lane busy every step), and the only inter-lane traffic is
+// one shuffle per half-step (the neighbouring sub-chunk's boundary score). All scores of the previous column live in
+// registers; no shared memory, no scan.
+// Same recurrence, tie-break and end-cell rules as bandedOverlapDp (bit-identical results, tested against the oracle); the
+// end cell is selected with the order-independent formulation of dpEndCellBetter.
+//
 // Per-offset constants of a sub-chunk, fixed for the whole job. The cell of band offset e is inside the matrix for
 // columns first <= i <= min(nx, ny + hi - e), where first = max(0, hi - e); in column `first` it is a boundary cell
-// (i == 0 or j == 0, score 0). cap = INT_MAX inside the band, "minus infinity" for the padding offsets e >= W, which
-// must never carry a finite score (they would open a path around the band edge).
-template<int C> struct SubChunkLimits { int32_t first[C]; int32_t cap[C]; };
+// (i == 0 or j == 0, score 0). gap = the gap score, or kGapBarrier for the two barrier offsets: a barrier cell can only
+// be entered by a gap move, so its score is "minus infinity" plus something bounded, whatever its neighbours hold, and
+// no finite score ever passes through it; no per-cell clamp and no special case for the first / last lane is needed
+// (lane 0's first offset and lane 31's last offset are barrier or padding, so the values their shuffles wrap around
+// are never used by an in-band cell).
+template<int C> struct SubChunkLimits { int32_t first[C]; int32_t gap[C]; };
 
-template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimits<C>& lim, int32_t e0, int32_t W, int32_t hi)
+template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimits<C>& lim, int32_t p0, int32_t W, int32_t hi, int32_t gap)
 {
 #pragma unroll
     for(int c = 0; c < C; c++) {
-        const int32_t e = e0 + c;
-        lim.first[c] = (e < W) ? max(0, hi - e) : 0x7fffffff;
-        lim.cap[c] = (e < W) ? 0x7fffffff : kNegInf;
+        const int32_t e = p0 + c - 1;
+        lim.first[c] = (e >= 0 && e < W) ? max(0, hi - e) : 0x7fffffff;
+        lim.gap[c] = (e == -1 || e == W) ? kGapBarrier : gap;
     }
 }
 
 // Trace layout of the wavefront kernel: the codes are stored by STEP, not by column. Lane l works on column
 // i = t2 - l in step t2, and every lane stores the codes of its last 16 steps in the same step (t2 % 16 == 15), so the
-// stores are warp-uniform and fully coalesced: word (t2 >> 4) * Wpad + e holds, at bits 2*(t2 % 16), the code of cell
-// (t2 - e / (2C), e). The traceback re-aligns two such words into a by-column word with one funnel shift.
+// stores are warp-uniform and fully coalesced: word (t2 >> 4) * Wpad + p holds, at bits 2*(t2 % 16), the code of cell
+// (t2 - p / (2C), p). The traceback re-aligns two such words into a by-column word with one funnel shift.
 
-// One sub-chunk (C consecutive band offsets starting at e0) of column i. Straight-line code for the common interior
-// cell; cells outside the matrix are NOT masked: above the matrix they only ever combine "minus infinity" values
-// (kNegInf plus a bounded drift), below the matrix their values are never read by an in-matrix cell, and their trace
-// codes are never visited by the traceback. bw[] = b[j-1] for the C offsets (sentinel outside the row).
+// One sub-chunk (C consecutive physical offsets) of column i. Straight-line code for the common interior cell; cells
+// outside the matrix are NOT masked: above the matrix they only ever combine "minus infinity" values (kNegInf plus a
+// bounded drift), below the matrix their values are never read by an in-matrix cell, and their trace codes are never
+// visited by the traceback. bw[] = b[j-1] for the C offsets (sentinel outside the row).
 // Boundary = false leaves out the test for the boundary cell (i == 0 or j == 0): for columns past max(0, hi).
 template<int C, bool Boundary> __device__ __forceinline__ void systolicSubChunk(
     int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t i, uint32_t ai,
-    int32_t below /* H(i, e0-1) */, int32_t top /* H(i-1, e0+C) */, const uint32_t* bw, DpScores sc)
+    int32_t below /* H(i, p0-1) */, int32_t top /* H(i-1, p0+C) */, const uint32_t* bw, DpScores sc)
 {
     int32_t vertIn = below;
 #pragma unroll
     for(int c = 0; c < C; c++) {
-        const int32_t diag = H[c] + ((ai == bw[c]) ? sc.match : sc.mismatch);   // from H(i-1, e)
-        const int32_t horzIn = (c + 1 < C) ? H[c + 1] : top;                    // H(i-1, e+1); vertIn = H(i, e-1)
-        // max(diag, vert, horz) with the tie order diag > vert > horz, as one max, one add-max and two compares.
+        const int32_t diag = H[c] + ((ai == bw[c]) ? sc.match : sc.mismatch);   // from H(i-1, p)
+        const int32_t horzIn = (c + 1 < C) ? H[c + 1] : top;                    // H(i-1, p+1); vertIn = H(i, p-1)
+        // max(diag, vert, horz) as one max and one add-max; the tie order (include/shb_dp_policy.h) only enters the code.
         const int32_t gapIn = max(vertIn, horzIn);
-        int32_t h = __viaddmax_s32(gapIn, sc.gap, diag);
-        const uint32_t code = (h > diag) ? ((horzIn > vertIn) ? 3u : 2u) : 1u;
-        h = min(h, lim.cap[c]);
+        int32_t h = __viaddmax_s32(gapIn, lim.gap[c], diag);
+        const bool viaGap = SHB_DP_DIAG_WINS_TIES ? (h > diag) : (gapIn + lim.gap[c] >= diag);
+        const uint32_t code = viaGap ? (dpHorzWins(horzIn, vertIn) ? 3u : 2u) : 1u;
         if(Boundary) h = (i == lim.first[c]) ? 0 : h;
         H[c] = h;
         vertIn = h;
@@ -263,7 +300,8 @@ template<int C, bool Boundary> __device__ __forceinline__ void systolicSubChunk(
 }
 
 // End-cell candidates of one sub-chunk in column i (rare: only the lanes whose offsets touch the last row or the
-// last column get here). bestJ is tracked as j + hi (fixed up by the caller).
+// last column get here). bestJ is tracked as j + hi (fixed up by the caller). e0 = band offset of the sub-chunk's first
+// physical offset (p0 - 1).
 template<int C> __device__ __forceinline__ void systolicEndCells(
     const int32_t (&H)[C], const SubChunkLimits<C>& lim, int32_t e0, int32_t i, int32_t cStar /* offset index on row ny */,
     int32_t nx, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
@@ -273,10 +311,10 @@ template<int C> __device__ __forceinline__ void systolicEndCells(
         // the cell on the last row j == ny of this column, and every in-matrix cell (j <= ny) of the last column
         const bool lastRow = (c == cStar);
         const bool lastColumn = (i == nx) && (c <= cStar) && (lim.first[c] <= nx);
-        if((lastRow || lastColumn) && lim.cap[c] == 0x7fffffff && i >= lim.first[c]) {
+        if((lastRow || lastColumn) && i >= lim.first[c]) {                  // first == INT_MAX outside the band
             const int32_t h = H[c];
             const int32_t jPlusHi = e0 + c + i;
-            if(h > bestScore || (h == bestScore && (i < bestI || (i == bestI && jPlusHi < bestJ)))) { bestScore = h; bestI = i; bestJ = jPlusHi; }
+            if(dpEndCellBetter(h, i, jPlusHi, bestScore, bestI, bestJ)) { bestScore = h; bestI = i; bestJ = jPlusHi; }
         }
     }
 }
@@ -294,24 +332,30 @@ template<int C> struct SystolicState {
     int32_t bestScore, bestI, bestJ;
 };
 
-// 16 steps. Checked = false: no boundary cell and no end cell can occur in these steps for any lane.
+// 16 steps. Checked = false: no boundary cell and no end cell can occur in these steps for any lane, and every k-mer
+// the lanes load lies inside its row (see the block ranges in bandedOverlapDpSystolic), so the loads are unconditional.
 template<int C, bool Checked> __device__ __forceinline__ void systolicBlock(
-    SystolicState<C>& s, int32_t lane, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc)
+    SystolicState<C>& s, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc)
 {
     constexpr int kUnroll = (C == 1) ? 16 : (C == 2) ? 8 : (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
 #pragma unroll kUnroll
     for(int step = 0; step < 16; step++) {
         uint32_t ai = 0xfffffffeu;
-        if(uint32_t(s.i - 1) < uint32_t(nx)) ai = __ldg(s.ap);
         uint32_t bIn = 0xffffffffu;                     // enters the window after this step
-        if(uint32_t(s.jNext) < uint32_t(ny)) bIn = __ldg(s.bNext);
-        // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i.
-        int32_t below = __shfl_up_sync(0xffffffffu, s.HB[C - 1], 1);
-        if(lane == 0) below = kNegInf;
+        if(Checked) {
+            if(uint32_t(s.i - 1) < uint32_t(nx)) ai = __ldg(s.ap);
+            if(uint32_t(s.jNext) < uint32_t(ny)) bIn = __ldg(s.bNext);
+        } else {
+            ai = __ldg(s.ap);
+            bIn = __ldg(s.bNext);
+        }
+        // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i
+        // (lane 0: its own value comes back, which only the barrier offset p = 0 reads).
+        const int32_t below = __shfl_up_sync(0xffffffffu, s.HB[C - 1], 1);
         systolicSubChunk<C, Checked>(s.HA, s.TA, s.limA, s.i, ai, below, s.HB[0], s.bw, sc);
-        // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1.
-        int32_t top = __shfl_down_sync(0xffffffffu, s.HA[0], 1);
-        if(lane == 31) top = kNegInf;
+        // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1
+        // (lane 31: its own value comes back, read only by barrier / padding offsets).
+        const int32_t top = __shfl_down_sync(0xffffffffu, s.HA[0], 1);
         systolicSubChunk<C, Checked>(s.HB, s.TB, s.limB, s.i, ai, s.HA[C - 1], top, s.bw + C, sc);
         if(Checked) {
             // End-cell bookkeeping for both sub-chunks: offsets eA + cStar (row ny) and, in column nx, all rows.
@@ -338,12 +382,13 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     const int32_t W = hi - lo + 1;
     const uint32_t WpadJob = dpPaddedWidth(lo, hi);
     SystolicState<C> s;
-    const int32_t eA = (2 * lane) * C, eB = (2 * lane + 1) * C;
+    const int32_t pA = (2 * lane) * C, pB = (2 * lane + 1) * C;         // physical offsets of the lane's sub-chunks
+    const int32_t eA = pA - 1, eB = pB - 1;                             // ... as band offsets
 #pragma unroll
     for(int c = 0; c < C; c++) { s.HA[c] = kNegInf; s.HB[c] = kNegInf; s.TA[c] = 0; s.TB[c] = 0; }
-    initSubChunkLimits<C>(s.limA, eA, W, hi);
-    initSubChunkLimits<C>(s.limB, eB, W, hi);
-    s.bestScore = kNegInf * 2; s.bestI = 0x7fffffff; s.bestJ = 0x7fffffff;
+    initSubChunkLimits<C>(s.limA, pA, W, hi, sc.gap);
+    initSubChunkLimits<C>(s.limB, pB, W, hi, sc.gap);
+    s.bestScore = kNegInf * 2; s.bestI = kEndCellNone; s.bestJ = kEndCellNone;
     // Only the columns iFirst..iLast hold in-band cells. Column of this lane in step t2 is i = iFirst + t2 - lane;
     // the row of its first offset in that column is jA = eA + i - hi.
     const int32_t iFirst = dpFirstColumn(lo), iLast = dpLastColumn(nxU, nyU, hi);
@@ -364,32 +409,36 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     const int32_t blocks = (iLast - iFirst + 47) >> 4;
     // Boundary cells only occur in columns <= max(0, hi), which lane 31 leaves after step max(0, hi) - iFirst + 31.
     // End cells (row ny, column nx) first occur in step min(nx - iFirst, ny + hi - iFirst - 64C + 32): lane 0 reaching
-    // column nx, or lane 31's last offset reaching row ny. The blocks in between run without either test.
+    // column nx, or lane 31's last offset reaching row ny. The blocks in between run without either test, and in them
+    // every lane's column satisfies max(0, hi) < i < nx and every window row (including the element prefetched for the
+    // next step) satisfies 1 <= j <= ny, so their loads need no range test: lane 0's barrier offset p = 0 sits on row
+    // i - hi - 1 >= 1 because lane 0 is 31 columns ahead of lane 31, and lane 31's prefetch index 64C - 2 + i - hi is at
+    // most ny - 1 up to step ny + hi - iFirst - 64C + 32.
     const int32_t headBlocks = ((max(0, hi) - iFirst + 31) >> 4) + 1;
     const int32_t firstEndStep = min(nx - iFirst, ny + hi - iFirst - 64 * C + 32);
     const int32_t tailBlock = max(0, firstEndStep) >> 4;
     uint32_t* row = trace;
     for(int32_t blk = 0; blk < blocks; blk++, row += WpadJob) {
-        if(blk < headBlocks || blk >= tailBlock) systolicBlock<C, true>(s, lane, eA, eB, rowEndA, nx, ny, sc);
-        else systolicBlock<C, false>(s, lane, eA, eB, rowEndA, nx, ny, sc);
+        if(blk < headBlocks || blk >= tailBlock) systolicBlock<C, true>(s, eA, eB, rowEndA, nx, ny, sc);
+        else systolicBlock<C, false>(s, eA, eB, rowEndA, nx, ny, sc);
         // Warp-uniform, coalesced trace store of the block's 16 steps.
 #pragma unroll
         for(int c = 0; c < C; c++) {
-            if(uint32_t(eA + c) < WpadJob) row[eA + c] = s.TA[c];
-            if(uint32_t(eB + c) < WpadJob) row[eB + c] = s.TB[c];
+            if(uint32_t(pA + c) < WpadJob) row[pA + c] = s.TA[c];
+            if(uint32_t(pB + c) < WpadJob) row[pB + c] = s.TB[c];
         }
     }
     bestScore = s.bestScore; bestI = s.bestI; bestJ = s.bestJ;
-    if(bestI != 0x7fffffff) bestJ -= hi;          // bestJ was tracked as j + hi
-    // Warp reduction of the end cell: maximum score, then smallest i, then smallest j.
+    if(bestI != kEndCellNone) bestJ -= hi;          // bestJ was tracked as j + hi
+    // Warp reduction of the end cell.
 #pragma unroll
     for(int d = 16; d > 0; d >>= 1) {
         const int32_t s2 = __shfl_xor_sync(0xffffffffu, bestScore, d);
         const int32_t i2 = __shfl_xor_sync(0xffffffffu, bestI, d);
         const int32_t j2 = __shfl_xor_sync(0xffffffffu, bestJ, d);
-        if(s2 > bestScore || (s2 == bestScore && (i2 < bestI || (i2 == bestI && j2 < bestJ)))) { bestScore = s2; bestI = i2; bestJ = j2; }
+        if(dpEndCellBetter(s2, i2, j2, bestScore, bestI, bestJ)) { bestScore = s2; bestI = i2; bestJ = j2; }
     }
-    if(bestI == 0x7fffffff) { bestI = -1; bestJ = -1; }
+    if(bestI == kEndCellNone) { bestI = -1; bestJ = -1; }
     __syncwarp();
 }
 
@@ -411,14 +460,15 @@ __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, 
     // By-column word (codes of columns 16*block .. 16*block+15) of offset base + lane.
     auto loadWindow = [&](int32_t block, int32_t base) -> uint32_t {
         const int32_t e = base + lane;
-        if(block < 0 || e < 0 || e >= Wpad) return 0u;
+        if(block < 0 || e < 0 || e + 1 >= Wpad) return 0u;
         if(pairWidth == 0) return trace[uint64_t(uint32_t(block)) * uint32_t(Wpad) + uint32_t(e)];
-        const uint32_t skew = uint32_t(e / pairWidth);                      // the lane that computed this offset
+        const uint32_t p = uint32_t(e) + 1u;                                // physical offset (barrier at p = 0)
+        const uint32_t skew = p / uint32_t(pairWidth);                      // the lane that computed this offset
         const uint64_t row = uint64_t(uint32_t(block)) + (skew >> 4);
-        const uint32_t w0 = trace[row * uint32_t(Wpad) + uint32_t(e)];
+        const uint32_t w0 = trace[row * uint32_t(Wpad) + p];
         const uint32_t sh = 2u * (skew & 15u);
         if(sh == 0) return w0;
-        const uint32_t w1 = trace[(row + 1) * uint32_t(Wpad) + uint32_t(e)];
+        const uint32_t w1 = trace[(row + 1) * uint32_t(Wpad) + p];
         return __funnelshift_r(w0, w1, sh);
     };
     int32_t block = (i - iFirst) >> 4;
@@ -578,7 +628,7 @@ method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob
     }
     const int32_t lastLane = (ny - 1) / R, rLast = (ny - 1) % R;        // where row ny lives
     int32_t upH = 0, upMn = kNoDiagonalStep, upMx = INT32_MIN;          // row R*lane of the previous column
-    int32_t bestScore = 0, bestI = 0x7fffffff, bestJ = 0x7fffffff, bestMn = kNoDiagonalStep, bestMx = INT32_MIN;
+    int32_t bestScore = 0, bestI = kEndCellNone, bestJ = kEndCellNone, bestMn = kNoDiagonalStep, bestMx = INT32_MIN;
 
     const int32_t steps = nx + lastLane;                                // lanes beyond lastLane only hold dead rows
 #pragma unroll 2
@@ -600,8 +650,8 @@ method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob
                 const bool eq = (ai == bk[r]);
                 const int32_t diag = dH + (eq ? sc.match : sc.mismatch);
                 const int32_t gapIn = max(vH, hH);
-                const int32_t h = __viaddmax_s32(gapIn, sc.gap, diag);  // diag > vert > horz on ties
-                const bool viaGap = h > diag, viaHorz = hH > vH;
+                const int32_t h = __viaddmax_s32(gapIn, sc.gap, diag);  // tie order: include/shb_dp_policy.h
+                const bool viaGap = SHB_DP_DIAG_WINS_TIES ? (h > diag) : (gapIn + sc.gap >= diag), viaHorz = dpHorzWins(hH, vH);
                 const int32_t off = ao - bo[r];
                 const int32_t stepMn = min(dMn, eq ? off : kNoMatchingStep);
                 const int32_t stepMx = max(dMx, eq ? off : INT32_MIN);
@@ -622,19 +672,19 @@ method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob
 #undef SHB_PICK_ROW
                 default: break;
                 }
-                if(h > bestScore) { bestScore = h; bestI = i; bestJ = ny; bestMn = mn; bestMx = mx; }
+                if(SHB_DP_END_FIRST_MAX ? (h > bestScore) : (h >= bestScore)) { bestScore = h; bestI = i; bestJ = ny; bestMn = mn; bestMx = mx; }
             }
             if(i == nx) {
 #pragma unroll
                 for(int r = 0; r < R; r++) {
                     const int32_t j = R * lane + r + 1;
-                    if(j <= ny && H[r] > bestScore) { bestScore = H[r]; bestI = i; bestJ = j; bestMn = Mn[r]; bestMx = Mx[r]; }
+                    if(j <= ny && (SHB_DP_END_FIRST_MAX ? (H[r] > bestScore) : (H[r] >= bestScore))) { bestScore = H[r]; bestI = i; bestJ = j; bestMn = Mn[r]; bestMx = Mx[r]; }
                 }
             }
         }
         upH = inH; upMn = inMn; upMx = inMx;
     }
-    // Maximum score, then smallest i, then smallest j.
+    // Maximum score, then the visiting order of the end-cell rule.
 #pragma unroll
     for(int d = 16; d > 0; d >>= 1) {
         const int32_t s2 = __shfl_xor_sync(0xffffffffu, bestScore, d);
@@ -642,13 +692,13 @@ method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob
         const int32_t j2 = __shfl_xor_sync(0xffffffffu, bestJ, d);
         const int32_t mn2 = __shfl_xor_sync(0xffffffffu, bestMn, d);
         const int32_t mx2 = __shfl_xor_sync(0xffffffffu, bestMx, d);
-        if(s2 > bestScore || (s2 == bestScore && (i2 < bestI || (i2 == bestI && j2 < bestJ)))) {
+        if(dpEndCellBetter(s2, i2, j2, bestScore, bestI, bestJ)) {
             bestScore = s2; bestI = i2; bestJ = j2; bestMn = mn2; bestMx = mx2;
         }
     }
     if(lane == 0) {
         DpJob j2 = jobs2[p];
-        if(bestI == 0x7fffffff || bestMn == kNoDiagonalStep) j2.state = kStateEmpty;        // :185-191
+        if(bestI == kEndCellNone || bestMn == kNoDiagonalStep) j2.state = kStateEmpty;        // :185-191
         else {
             const int32_t offsetMin = (bestMn == kNoMatchingStep) ? INT32_MAX : bestMn, offsetMax = bestMx;
             // 32-bit wrap-around like the compiled reference (:222-239)
@@ -733,15 +783,16 @@ tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __r
     if(job.state == kStateRun && i > 0 && j > 0) {
         const uint32_t Wpad = dpPaddedWidth(job.lo, job.hi);
         const uint32_t C = dpWavefrontC(Wpad);
-        // By-step layout: the code of cell (i, e) sits in step t = (i - iFirst) + e / (2C); by-column layout: t = i.
+        // By-step layout: the code of cell (i, p) sits in step t = (i - iFirst) + p / (2C); by-column layout: t = i.
         const int32_t iFirst = C ? dpFirstColumn(job.lo) : 0;
-        const uint32_t reciprocal = C ? (65536u + 2u * C - 1u) / (2u * C) : 0u;      // e / (2C) == (e * reciprocal) >> 16 for e < 1024
+        const uint32_t reciprocal = C ? (65536u + 2u * C - 1u) / (2u * C) : 0u;      // p / (2C) == (p * reciprocal) >> 16 for p < 1024
+        const uint32_t shift = C ? 1u : 0u;                                          // physical offset p = e + 1 (barrier at p = 0)
         const uint32_t* __restrict__ tr = trace + job.traceOffset;
         uint2* __restrict__ out = runs + job.outOffset;
         const int32_t hi = job.hi;
         // One dependent load per iteration; the threads of a warp stay in step (one run or one gap step per iteration).
         while(i > 0 && j > 0) {
-            const uint32_t e = uint32_t(j - i + hi);
+            const uint32_t e = uint32_t(j - i + hi) + shift;
             const uint32_t t = uint32_t(i - iFirst) + ((e * reciprocal) >> 16);
             const uint32_t word = tr[uint64_t(t >> 4) * Wpad + e];
             // Diagonal steps stay on the same offset: a run of them is a run of "01" codes going down this word.
@@ -1018,27 +1069,43 @@ namespace shb {
 
 // Per-candidate job setup (src/AssemblerAlign.cpp:376-382): oriented reads (readId0, strand 0) and
 // (readId1, sameStrand ? 0 : 1); stage-1 job on the downsampled rows, stage-2 job skeleton on the full rows.
+// maxWidth: widest padded band the DP kernels take (kMaxBandWidth); a candidate whose unbanded stage needs more is
+// skipped and counted (tooWide), not the whole call (the reference has no such limit: documented deviation).
+// dsToc == nullptr: method 1 (src/AssemblerAlign1.cpp:129-148), no stage 1, the stage-2 job covers the whole matrix.
 static __global__ void method3SetupKernel(const uint32_t* __restrict__ candidates, uint32_t n,
                                           const uint64_t* __restrict__ toc, const uint64_t* __restrict__ dsToc,
                                           DpJob* __restrict__ jobs1, DpJob* __restrict__ jobs2,
                                           unsigned long long* __restrict__ traceWords1, unsigned long long* __restrict__ outCount,
-                                          unsigned long long* __restrict__ forwardCells)
+                                          unsigned long long* __restrict__ forwardCells, uint32_t maxWidth,
+                                          unsigned long long* __restrict__ tooWide)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n) return;
-    const uint32_t r0 = candidates[3ull * p], r1 = candidates[3ull * p + 1];
-    const bool same = (candidates[3ull * p + 2] & 0xffu) != 0;
-    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    uint64_t o0, o1;
+    candidateOrientedReads(candidates, p, o0, o1);
     DpJob j1, j2;
+    if(dsToc == nullptr) {
+        j2.aOffset = toc[o0]; j2.nx = uint32_t(toc[o0 + 1] - toc[o0]);
+        j2.bOffset = toc[o1]; j2.ny = uint32_t(toc[o1 + 1] - toc[o1]);
+        j2.lo = -int32_t(j2.ny); j2.hi = int32_t(j2.nx); j2.traceOffset = 0; j2.outOffset = 0; j2.pad = 0;
+        j2.state = (j2.nx == 0 || j2.ny == 0) ? kStateEmpty : kStateRun;
+        if(j2.state == kStateRun && dpPaddedWidth(j2.lo, j2.hi) > maxWidth) { j2.state = kStateSkipped; atomicAdd(tooWide, 1ull); }
+        jobs2[p] = j2;
+        outCount[p] = min(j2.nx, j2.ny);
+        return;
+    }
     j1.aOffset = dsToc[o0]; j1.nx = uint32_t(dsToc[o0 + 1] - dsToc[o0]);
     j1.bOffset = dsToc[o1]; j1.ny = uint32_t(dsToc[o1 + 1] - dsToc[o1]);
     j1.lo = -int32_t(j1.ny); j1.hi = int32_t(j1.nx);
     j1.traceOffset = 0; j1.outOffset = 0; j1.pad = 0;
     j1.state = (j1.nx == 0 || j1.ny == 0) ? kStateEmpty : kStateRun;       // src/AssemblerAlign3.cpp:100-106
+    if(j1.state == kStateRun && j1.ny > kStage1ForwardMaxRows && dpPaddedWidth(j1.lo, j1.hi) > maxWidth) {
+        j1.state = kStateSkipped; atomicAdd(tooWide, 1ull);
+    }
     j2.aOffset = toc[o0]; j2.nx = uint32_t(toc[o0 + 1] - toc[o0]);
     j2.bOffset = toc[o1]; j2.ny = uint32_t(toc[o1 + 1] - toc[o1]);
     j2.lo = 0; j2.hi = 0; j2.traceOffset = 0; j2.outOffset = 0; j2.pad = 0;
-    j2.state = (j1.state == kStateRun) ? kStateSkipped : kStateEmpty;       // stage 1 overwrites it when it runs
+    j2.state = (j1.state == kStateEmpty) ? kStateEmpty : kStateSkipped;     // stage 1 overwrites it when it runs
     jobs1[p] = j1; jobs2[p] = j2;
     // Only the jobs that are too long for the forward kernel need a trace.
     const bool forward = j1.ny <= kStage1ForwardMaxRows;
@@ -1099,6 +1166,27 @@ static __global__ void stage2TraceWordsKernel(const DpJob* __restrict__ jobs, ui
     traceWords[p] = (j.state == kStateRun) ? dpTraceWords(j.nx, j.ny, j.lo, j.hi) : 0ull;
 }
 
+// In-band, in-matrix cells of the banded jobs (what the reference's DP fills): per column i the rows max(0, i - hi) ..
+// min(ny, i - lo). counter += the total over the runnable jobs.
+static __global__ void bandCellsKernel(const DpJob* __restrict__ jobs, uint32_t n, unsigned long long* __restrict__ counter)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cells = 0;
+    if(p < n) {
+        const DpJob j = jobs[p];
+        if(j.state == kStateRun) {
+            const long long nx = j.nx, ny = j.ny, lo = j.lo, hi = j.hi;
+            for(long long i = max(0ll, lo); i <= min(nx, ny + hi); i++) {
+                const long long rows = min(ny, i - lo) - max(0ll, i - hi) + 1;
+                if(rows > 0) cells += (unsigned long long)rows;
+            }
+        }
+    }
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
+    if((threadIdx.x & 31u) == 0 && cells) atomicAdd(counter, cells);
+}
+
 static __global__ void widenBytesKernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* __restrict__ out)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1146,9 +1234,8 @@ static __global__ void align4CellCountKernel(const uint32_t* __restrict__ candid
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n) return;
-    const uint32_t r0 = candidates[3ull * p], r1 = candidates[3ull * p + 1];
-    const bool same = (candidates[3ull * p + 2] & 0xffu) != 0;
-    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    uint64_t o0, o1;
+    candidateOrientedReads(candidates, p, o0, o1);
     uint32_t nIX, nIY;
     align4GridSize(uint32_t(toc[o0 + 1] - toc[o0]), uint32_t(toc[o1 + 1] - toc[o1]), deltaX, deltaY, nIX, nIY);
     cellCounts[p] = (unsigned long long)nIX * nIY + 2;      // +2: room for one degenerate band
@@ -1165,9 +1252,8 @@ static __global__ void __launch_bounds__(128) align4FrontEndKernel(Align4Args g)
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if(p >= g.n) return;
-    const uint32_t r0 = g.candidates[3ull * p], r1 = g.candidates[3ull * p + 1];
-    const bool same = (g.candidates[3ull * p + 2] & 0xffu) != 0;
-    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    uint64_t o0, o1;
+    candidateOrientedReads(g.candidates, p, o0, o1);
     const uint64_t aBegin = g.toc[o0], bBegin = g.toc[o1];
     const uint32_t nx = uint32_t(g.toc[o0 + 1] - aBegin), ny = uint32_t(g.toc[o1 + 1] - bBegin);
     uint32_t nIX, nIY;
@@ -1364,9 +1450,8 @@ static __global__ void align4MakeJobsKernel(const uint32_t* __restrict__ candida
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if(p >= n) return;
-    const uint32_t r0 = candidates[3ull * p], r1 = candidates[3ull * p + 1];
-    const bool same = (candidates[3ull * p + 2] & 0xffu) != 0;
-    const uint64_t o0 = 2ull * r0, o1 = 2ull * r1 + (same ? 0 : 1);
+    uint64_t o0, o1;
+    candidateOrientedReads(candidates, p, o0, o1);
     DpJob j;
     j.aOffset = toc[o0]; j.nx = uint32_t(toc[o0 + 1] - toc[o0]);
     j.bOffset = toc[o1]; j.ny = uint32_t(toc[o1 + 1] - toc[o1]);

@@ -2,6 +2,7 @@
 #include "context.cuh"
 #include "lowhash_kernels.cuh"
 #include "hostpool.cuh"
+#include "digest.cuh"
 
 #include <cstring>
 #include <string>
@@ -16,7 +17,8 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p, void** candidatesOut,
 
 void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, const shb_align_options& o,
                        void** alignmentDataOut, uint64_t* alignmentCountOut,
-                       uint64_t** compressedTocOut, uint8_t** compressedDataOut, shb_align_result* result);
+                       uint64_t** compressedTocOut, uint8_t** compressedDataOut, shb_align_result* result,
+                       bool explicitOrientation);
 void destroyAlignCache(shb_context* c);
 void destroyLowhashState(shb_context* c);
 LowHashState& lowhashState(shb_context* c);
@@ -29,6 +31,7 @@ void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountO
 void devicePartition(shb_context* c, uint64_t* keys, uint32_t* vals, uint64_t n, uint32_t shift, uint32_t bits,
                      uint64_t* counts, uint64_t** keysOut, uint32_t** valsOut);
 void computeAlignmentTable(shb_context* c, const void* alignmentData, uint64_t n, uint64_t readCount, uint32_t** tocOut, uint32_t** dataOut);
+void computeCandidateTable(shb_context* c, const void* candidates, uint64_t n, uint64_t readCount, uint64_t** tocOut, uint64_t** dataOut);
 
 template<class F> shb_status guarded(F&& f)
 {
@@ -293,6 +296,7 @@ shb_status shb_lowhash_counters(shb_context* c, shb_lowhash_result* result)
         memset(result, 0, sizeof(*result));
         result->log2BucketCount = S.log2BucketCount; result->lowHashCount = S.lowHashCount; result->pairCount = S.pairCount;
         result->sweepMs = S.sweepMs; result->sweepLaunches = S.sweepLaunches; result->kernelLaunches = g_launchCount;
+        result->candidateCount = S.emittedCount; result->candidateDigest = S.candidateDigest;
     });
 }
 
@@ -302,7 +306,58 @@ shb_status shb_compute_alignments(shb_context* c, const void* candidates, uint64
 {
     return guarded([&] {
         SHB_REQUIRE(c && options && alignmentData && alignmentCount && compressedToc && compressedData, SHB_ERR_INVALID, "Null argument.");
-        computeAlignments(c, candidates, candidateCount, *options, alignmentData, alignmentCount, compressedToc, compressedData, result);
+        computeAlignments(c, candidates, candidateCount, *options, alignmentData, alignmentCount, compressedToc, compressedData, result, false);
+    });
+}
+
+// shasta::decompress (src/compressAlignment.cpp:73-137): streaks (skip0, skip1, n) in the 1/2/4/8/16-byte formats of
+// src/compressAlignment.hpp:102-320 -> ordinal pairs. Returns the number of pairs; writes at most cap of them.
+static uint64_t decompressAlignment(const uint8_t* s, uint64_t bytes, uint32_t* out, uint64_t cap)
+{
+    uint64_t pos = 0, n = 0;
+    uint32_t ordinal0 = 0, ordinal1 = 0;
+    auto sext = [](uint64_t v, int bits) { const uint64_t m = 1ull << (bits - 1); return int32_t(int64_t((v ^ m) - m)); };
+    while(pos < bytes) {
+        int32_t skip0, skip1; uint32_t len;
+        const uint8_t c0 = s[pos];
+        if((c0 & 1u) == 0) { skip0 = (c0 >> 1) & 3; skip1 = (c0 >> 3) & 3; len = ((c0 >> 5) & 7u) + 1; pos += 1; }
+        else if((c0 & 7u) == 1) { uint16_t v; memcpy(&v, s + pos, 2); pos += 2; skip0 = sext((v >> 3) & 0xF, 4); skip1 = sext((v >> 7) & 0xF, 4); len = uint32_t(v >> 11) + 1; }
+        else if((c0 & 7u) == 3) { uint32_t v; memcpy(&v, s + pos, 4); pos += 4; skip0 = sext((v >> 3) & 0x3FF, 10); skip1 = sext((v >> 13) & 0x3FF, 10); len = (v >> 23) + 1; }
+        else if((c0 & 7u) == 5) { uint64_t v; memcpy(&v, s + pos, 8); pos += 8; skip0 = sext((v >> 3) & 0xFFFFF, 20); skip1 = sext((v >> 23) & 0xFFFFF, 20); len = uint32_t(v >> 43) + 1; }
+        else { uint32_t v[4]; memcpy(v, s + pos, 16); pos += 16; skip0 = int32_t(v[1]); skip1 = int32_t(v[2]); len = v[3] + 1; }
+        ordinal0 += uint32_t(skip0); ordinal1 += uint32_t(skip1);
+        for(uint32_t i = 0; i < len; i++, n++) if(n < cap) { out[2*n] = ordinal0 + i; out[2*n+1] = ordinal1 + i; }
+        ordinal0 += len - 1; ordinal1 += len - 1;
+    }
+    return n;
+}
+
+shb_status shb_align_oriented_reads(shb_context* c, uint32_t orientedReadId0, uint32_t orientedReadId1,
+                                    const shb_align_options* options, uint32_t** ordinals, uint64_t* markerCount,
+                                    uint32_t* alignmentInfo13)
+{
+    return guarded([&] {
+        SHB_REQUIRE(c && options && ordinals && markerCount, SHB_ERR_INVALID, "Null argument.");
+        SHB_REQUIRE(orientedReadId0 != orientedReadId1, SHB_ERR_INVALID, "alignOrientedReads needs two different oriented reads.");
+        const uint32_t strand0 = orientedReadId0 & 1u, strand1 = orientedReadId1 & 1u;
+        const uint32_t cand[3] = {orientedReadId0 >> 1, orientedReadId1 >> 1, (strand0 == strand1 ? 1u : 0u) | (strand0 ? 0x100u : 0u)};
+        void* rec = nullptr; uint64_t count = 0; uint64_t* toc = nullptr; uint8_t* data = nullptr;
+        computeAlignments(c, cand, 1, *options, &rec, &count, &toc, &data, nullptr, true);
+        HostResult recHold(rec), tocHold(toc), dataHold(data);
+        *markerCount = 0;
+        *ordinals = nullptr;
+        if(alignmentInfo13) memset(alignmentInfo13, 0, 13 * sizeof(uint32_t));
+        if(count == 1) {
+            const uint32_t* w = static_cast<const uint32_t*>(rec);
+            const uint64_t n = w[9];
+            HostResult out(allocHostResult(8 * n + 8));
+            SHB_REQUIRE(out.p != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment.");
+            const uint64_t got = decompressAlignment(data, toc[1] - toc[0], static_cast<uint32_t*>(out.p), n);
+            SHB_REQUIRE(got == n, SHB_ERR_CUDA, "Internal error: the compressed alignment does not decode to markerCount pairs.");
+            if(alignmentInfo13) memcpy(alignmentInfo13, w + 3, 13 * sizeof(uint32_t));
+            *markerCount = n;
+            *ordinals = static_cast<uint32_t*>(out.take());
+        }
     });
 }
 
@@ -313,6 +368,39 @@ shb_status shb_compute_alignment_table(shb_context* c, const void* alignmentData
         SHB_REQUIRE(c && tableToc && tableData && (alignmentData || alignmentCount == 0), SHB_ERR_INVALID, "Null argument.");
         computeAlignmentTable(c, alignmentData, alignmentCount, readCount, tableToc, tableData);
     });
+}
+
+shb_status shb_compute_candidate_table(shb_context* c, const void* candidates, uint64_t candidateCount, uint64_t readCount,
+                                       uint64_t** tableToc, uint64_t** tableData)
+{
+    return guarded([&] {
+        SHB_REQUIRE(c && tableToc && tableData && (candidates || candidateCount == 0), SHB_ERR_INVALID, "Null argument.");
+        computeCandidateTable(c, candidates, candidateCount, readCount, tableToc, tableData);
+    });
+}
+
+uint64_t shb_digest_records(const uint32_t* records, uint64_t count, uint32_t words)
+{
+    uint64_t sum = 0;
+    for(uint64_t i = 0; i < count; i++) {
+        uint64_t h = kFnvOffset;
+        for(uint32_t k = 0; k < words; k++) h = fnvWord(h, records[i * words + k]);
+        sum += fnvFinish(h);
+    }
+    return sum;
+}
+
+uint64_t shb_digest_compressed(const uint32_t* alignmentData, uint64_t count, const uint64_t* compressedToc,
+                               const uint8_t* compressedData)
+{
+    uint64_t sum = 0;
+    for(uint64_t i = 0; i < count; i++) {
+        uint64_t h = kFnvOffset;
+        h = fnvWord(h, alignmentData[16 * i]); h = fnvWord(h, alignmentData[16 * i + 1]); h = fnvWord(h, alignmentData[16 * i + 2] & 0xffu);
+        for(uint64_t p = compressedToc[i]; p < compressedToc[i + 1]; p++) h = fnvWord(h, compressedData[p]);
+        sum += fnvFinish(h);
+    }
+    return sum;
 }
 
 } // extern "C"

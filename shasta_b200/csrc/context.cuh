@@ -19,6 +19,7 @@ struct LowHashState {
     uint32_t readBits = 1, slabGroup = 0;
     LowHashAccumulator acc;
     uint64_t lowHashCount = 0, pairCount = 0, sweepLaunches = 0;
+    uint64_t emittedCount = 0, candidateDigest = 0;     // of the last shb_lowhash_emit
     double sweepMs = 0.;
 };
 }

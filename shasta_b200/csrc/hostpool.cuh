@@ -97,4 +97,14 @@ private:
 
 inline void* allocHostResult(uint64_t bytes) { return HostPool::instance().allocate(bytes); }
 
+// Owns a host result block until it is handed to the caller: an exception on the way out releases it.
+struct HostResult {
+    void* p = nullptr;
+    explicit HostResult(void* q = nullptr) : p(q) {}
+    HostResult(const HostResult&) = delete;
+    HostResult& operator=(const HostResult&) = delete;
+    ~HostResult() { if(p) HostPool::instance().release(p); }
+    void* take() { void* q = p; p = nullptr; return q; }
+};
+
 } // namespace shb

@@ -4,6 +4,7 @@
 #include "context.cuh"
 #include "lowhash_kernels.cuh"
 #include "hostpool.cuh"
+#include "digest.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -330,17 +331,23 @@ void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountO
     cudaStream_t st = c->stream;
     mergeAccumulator(c, S.acc, S.readBits);
     const uint64_t nOut = countHighFrequency(c, S.acc, S.p.minFrequency, true);
-    void* host = allocHostResult(nOut * 12);
-    SHB_REQUIRE(host != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment candidates.");
+    HostResult host(allocHostResult(nOut * 12));
+    SHB_REQUIRE(host.p != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment candidates.");
+    unsigned long long* digestDev = c->scalars.get() + 41;
+    unsigned long long digest = 0;
     if(nOut) {
         c->candidatesDev.reserve(3 * nOut);
         SHB_LAUNCH(emitCandidatesKernel, ceilDiv(S.acc.count, 256), 256, 0, st, (const uint64_t*)accKeys(c, S.acc),
                    (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(), uint32_t(S.acc.count),
                    c->candidatesDev.get());
-        SHB_CUDA(cudaMemcpyAsync(host, c->candidatesDev.get(), nOut * 12, cudaMemcpyDeviceToHost, st));
+        SHB_CUDA(cudaMemcpyAsync(host.p, c->candidatesDev.get(), nOut * 12, cudaMemcpyDeviceToHost, st));
+        SHB_CUDA(cudaMemsetAsync(digestDev, 0, sizeof(unsigned long long), st));
+        SHB_LAUNCH(digestRecordsKernel, ceilDiv(nOut, 256), 256, 0, st, (const uint32_t*)c->candidatesDev.get(), nOut, 3u, digestDev);
+        SHB_CUDA(cudaMemcpyAsync(&digest, digestDev, sizeof(digest), cudaMemcpyDeviceToHost, st));
     }
     SHB_CUDA(cudaStreamSynchronize(st));
-    *candidatesOut = host;
+    S.emittedCount = nOut; S.candidateDigest = digest;
+    *candidatesOut = host.take();
     *candidateCountOut = nOut;
 }
 
@@ -445,6 +452,7 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
         result->lowHashCount = S.lowHashCount;
         result->pairCount = S.pairCount;
         result->candidateCount = *candidateCountOut;
+        result->candidateDigest = S.candidateDigest;
         result->sweepMs = S.sweepMs;
         result->totalMs = totalMs;
         result->sweepLaunches = S.sweepLaunches;

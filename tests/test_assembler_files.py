@@ -90,29 +90,25 @@ def test_companion_accessors_with_stubbed_device(tmp_path, golden_dir, monkeypat
         def set_markers(self, toc, data, flags):
             seen["markers"] = len(flags)
 
-    def stub_compute_alignments(ctx, cand, opts):
-        seen["cand"] = np.asarray(cand).copy()
+    def stub_align_oriented_reads(ctx, o0, o1, opts):
+        seen["pair"] = (o0, o1)
         seen["opts"] = opts
-        rec = np.zeros((1, 16), np.uint32)
-        rec[0, 9] = 321
-        return rec, np.zeros(2, np.uint64), np.zeros(0, np.uint8), None
+        return np.zeros((321, 2), np.uint32), np.zeros(13, np.uint32)
 
     monkeypatch.setattr(a, "_context", lambda: StubContext())
     a._markers_on_device = False
-    monkeypatch.setattr(capi, "compute_alignments", stub_compute_alignments)
+    monkeypatch.setattr(capi, "align_oriented_reads", stub_align_oriented_reads)
     kw = dict(deltaX=200, deltaY=10, minEntryCountPerCell=10, maxDistanceFromBoundary=100, minAlignedMarkerCount=10,
               minAlignedFraction=0.1, maxSkip=100, maxDrift=100, maxTrim=100, maxBand=1000, matchScore=6, mismatchScore=-1, gapScore=-1)
     n = a.alignOrientedReads4(readId0=7, strand0=1, readId1=3, strand1=0, **kw)
     assert n == 321 and "The alignment has 321 markers." in capsys.readouterr().out
     assert seen["markers"] == 20
-    assert seen["cand"].tolist() == [[3, 7, 0]]            # lower read id first, opposite strands
+    assert seen["pair"] == (15, 6)            # the orientation and order the caller gave: (7,1) horizontal, (3,0) vertical
     o = seen["opts"]
     assert (o.alignMethod, o.k, o.align4DeltaX, o.align4DeltaY, o.align4MinEntryCountPerCell, o.align4MaxDistanceFromBoundary) == (4, 10, 200, 10, 10, 100)
     assert (o.maxSkip, o.maxDrift, o.maxTrim, o.maxBand, o.minAlignedMarkerCount, o.suppressContainments) == (100, 100, 100, 1000, 10, 0)
     a.alignOrientedReads4(readId0=2, strand0=1, readId1=5, strand1=1, **kw)
-    assert seen["cand"].tolist() == [[2, 5, 1]]
-    with pytest.raises(RuntimeError, match="two different reads"):
-        a.alignOrientedReads4(readId0=4, strand0=0, readId1=4, strand1=1, **kw)
+    assert seen["pair"] == (5, 11)
 
 
 @pytest.mark.gpu
@@ -155,6 +151,25 @@ def test_script_sequence_on_reference_data_dir(tmp_path, golden_dir):
     assert np.array_equal(rec, orec) and np.array_equal(toc, otoc) and np.array_equal(data, odata)
     table_toc = A.mm_read_vector(prefix + "AlignmentTable.toc", np.uint32, object_size=4)
     assert len(table_toc) == 2 * 20 + 1 and int(table_toc[-1]) == 4 * len(rec)
+    # srcMain/main.cpp:706: computeCandidateTable after the candidates are known
+    b.computeCandidateTable()
+    ct_toc = np.asarray(A.mm_read_vector(prefix + "CandidateTable.toc", np.uint64, object_size=8))
+    ct_data = np.asarray(A.mm_read_vector(prefix + "CandidateTable.data", np.uint64, object_size=8))
+    otoc2, otable2 = B.oracle_compute_candidate_table(b._candidates, 20)
+    assert np.array_equal(ct_toc, otoc2) and np.array_equal(ct_data, otable2)
+    # single pair, in the orientation given (scripts/AlignOrientedReads4.py): against the oracle's Align4 on the same rows
+    toc0 = np.asarray(z["toc"])
+    r0, r1, same = [int(x) for x in b._candidates[0]]
+    for (s0, s1) in ((0, 0 if same else 1), (1, 1 if same else 0)):
+        for (ra, sa, rb, sb) in ((r0, s0, r1, s1), (r1, s1, r0, s0)):
+            n4 = b.alignOrientedReads4(ra, sa, rb, sb, deltaX=200, deltaY=10, minEntryCountPerCell=10, maxDistanceFromBoundary=100,
+                                       minAlignedMarkerCount=10, minAlignedFraction=0.1, maxSkip=100, maxDrift=100, maxTrim=100,
+                                       maxBand=1000, matchScore=6, mismatchScore=-1, gapScore=-1)
+            oa, ob = 2 * ra + sa, 2 * rb + sb
+            o4 = B.make_align_options(alignMethod=4, k=10, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
+                                      minAlignedFraction=0.1, maxBand=1000)
+            _, want, _ = B.oracle_align_pair(kmer[int(toc0[oa]):int(toc0[oa + 1])], kmer[int(toc0[ob]):int(toc0[ob + 1])], o4)
+            assert n4 == len(want) and np.array_equal(b._last_alignment, want)
     with pytest.raises(RuntimeError, match="unreasonably small"):
         b.findAlignmentCandidatesLowHash0(m=4, hashFraction=0.01, minHashIterationCount=10, alignmentCandidatesPerRead=20.,
                                           minBucketSize=0, maxBucketSize=10, minFrequency=2, log2MinHashBucketCount=3)

@@ -39,6 +39,10 @@ def _compare(ctx, d, cand, **opts):
     assert np.array_equal(rec, orec)
     assert np.array_equal(ctoc, otoc)
     assert np.array_equal(cdata, odata)
+    # the device-side digests carried by every bench line are those of exactly these bytes
+    assert res.alignmentDataDigest == capi.digest_records(orec, 16)
+    assert res.compressedDigest == capi.digest_compressed(orec, otoc, odata)
+    assert res.dpUsefulCells <= res.dpCells
     return rec, res
 
 
@@ -78,6 +82,15 @@ def test_method3_random_pairs_and_scores(ctx):
     _compare(ctx, d, cand, alignMethod=3, k=10, maxSkip=50, maxDrift=50, maxTrim=1000, minAlignedMarkerCount=3,
              minAlignedFraction=0.0, matchScore=3, mismatchScore=-2, gapScore=-1, downsamplingFactor=0.3,
              bandExtend=3, maxBand=200)
+
+
+def test_method1_unbanded_all_markers(ctx):
+    # Align.alignMethod 1 (src/AssemblerAlign1.cpp:129-148): one unbanded DP on all markers; the bands are as wide as
+    # nx + ny + 1, i.e. the widest wavefront classes and the scan kernel.
+    d, cand = _dataset(60, 10, 7, genome_markers=4000, n50=6000, min_bases=4000)
+    rec, res = _compare(ctx, d, cand[:150], alignMethod=1, k=10, maxSkip=30, maxDrift=30, maxTrim=30,
+                        minAlignedMarkerCount=50, minAlignedFraction=0.3)
+    assert len(rec) > 10 and res.tooWideCount == 0
 
 
 def test_alignment_properties(ctx):
@@ -139,6 +152,19 @@ def test_alignment_table(ctx):
     # every alignment appears exactly 4 times
     assert np.array_equal(np.bincount(table, minlength=len(rec)), np.full(len(rec), 4))
     toc0, table0 = capi.compute_alignment_table(ctx, rec[:0], 200)
+    assert toc0.sum() == 0 and len(table0) == 0
+
+
+def test_candidate_table(ctx):
+    from shasta_b200 import capi
+    d, cand = _dataset(200, 10, 33)
+    toc, table = capi.compute_candidate_table(ctx, cand, 200)
+    otoc, otable = B.oracle_compute_candidate_table(cand, 200)
+    assert len(cand) > 500
+    assert toc.dtype == np.uint64 and table.dtype == np.uint64
+    assert np.array_equal(toc, otoc) and np.array_equal(table, otable)
+    assert np.array_equal(np.bincount(table.astype(np.int64), minlength=len(cand)), np.full(len(cand), 4))
+    toc0, table0 = capi.compute_candidate_table(ctx, cand[:0], 200)
     assert toc0.sum() == 0 and len(table0) == 0
 
 

@@ -71,6 +71,20 @@ def test_small_batches_and_chunks_match_oracle(ctx, dataset, batch, chunk):
     assert np.array_equal(rec, orec) and np.array_equal(ctoc, otoc) and np.array_equal(cdata, odata)
 
 
+@pytest.mark.parametrize("workers", [1, 2, 3])
+def test_worker_threads_match_oracle(ctx, dataset, workers):
+    # The batches of one call are spread over host worker threads, each with its own streams and scratch; the kept
+    # alignments land in a shared arena in completion order and are put back into candidate order at the end.
+    d, cand = dataset
+    oo = B.make_align_options(**{k: v for k, v in OPTS.items() if k in B.ALIGN_DEFAULTS})
+    orec, otoc, odata, _ = B.oracle_compute_alignments(d["toc"], d["kmer"], cand, oo, threads=8)
+    with _Hooks(SHB_ALIGN_BATCH=211, SHB_ALIGN_CHUNK=70, SHB_ALIGN_WORKERS=workers):
+        for _ in range(2):
+            rec, ctoc, cdata, res = _run(ctx, d, cand, **OPTS)
+            assert res.workers == workers
+            assert np.array_equal(rec, orec) and np.array_equal(ctoc, otoc) and np.array_equal(cdata, odata)
+
+
 def test_method4_small_batches_match_oracle(ctx, dataset):
     d, cand = dataset
     opts = dict(OPTS, alignMethod=4)
