@@ -282,6 +282,11 @@ shb_status shb_synth_generate(shb_context* ctx, uint64_t seed, uint32_t k, doubl
                               const uint8_t* revHost, uint64_t* tocOut /* 2*readCount+1, relative */,
                               uint32_t** kmerIdsDevice, uint8_t** data7Device /* may be NULL */);
 shb_status shb_device_free(void* devicePtr);
+/* Test hook for the library's radix sort (csrc/radix_sort.cuh): sorts n host (key, value) items in place, stably, on the
+ * key bits [lowBegin, lowEnd) and then [highBegin, highEnd) (pass highEnd <= highBegin for a single range); values may be
+ * NULL. */
+shb_status shb_test_radix_sort(shb_context* ctx, uint64_t* keys, uint32_t* values, uint64_t n,
+                               int lowBegin, int lowEnd, int highBegin, int highEnd);
 /* Device pointer and length of the uint32 k-mer id SoA held by ctx (for the all-gather that replicates the
  * markers on every GPU before the alignment step). */
 shb_status shb_markers_device(shb_context* ctx, void** kmerIdsDevice, uint64_t* localMarkerCount);

@@ -827,7 +827,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                        seg.kept, 16u, digests);
             SHB_LAUNCH(digestCompressedKernel, ceilDiv(seg.kept, 256), 256, 0, st, (const uint32_t*)ac.outRecords.get() + 16 * seg.recordBase,
                        seg.kept, (const unsigned long long*)segToc, finalBytes + seg.bytes,
-                       (const uint8_t*)ac.outData.get() + seg.byteBase - finalBytes, digests);
+                       (const uint8_t*)ac.outData.get() + seg.byteBase - finalBytes, digests + 1);
             copyToHostPipelined(c, static_cast<uint8_t*>(recOut.p) + 64 * finalRecords, ac.outRecords.get() + 16 * seg.recordBase, 64 * seg.kept, lockedRec);
             copyToHostPipelined(c, static_cast<uint8_t*>(tocOut.p) + 8 * finalRecords, segToc, 8 * seg.kept, lockedToc);
             copyToHostPipelined(c, static_cast<uint8_t*>(dataOut.p) + finalBytes, ac.outData.get() + seg.byteBase, seg.bytes, lockedData);

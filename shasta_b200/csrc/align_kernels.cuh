@@ -1175,10 +1175,18 @@ static __global__ void bandCellsKernel(const DpJob* __restrict__ jobs, uint32_t 
     if(p < n) {
         const DpJob j = jobs[p];
         if(j.state == kStateRun) {
+            // Sum over the columns a..b of  min(ny, i - lo) - max(0, i - hi) + 1  (positive for every such column), as two
+            // arithmetic series: the bottom edge grows with i up to column ny + lo, the top edge from column hi + 1 on.
             const long long nx = j.nx, ny = j.ny, lo = j.lo, hi = j.hi;
-            for(long long i = max(0ll, lo); i <= min(nx, ny + hi); i++) {
-                const long long rows = min(ny, i - lo) - max(0ll, i - hi) + 1;
-                if(rows > 0) cells += (unsigned long long)rows;
+            const long long a = max(0ll, lo), b = min(nx, ny + hi);
+            if(b >= a) {
+                long long total = b - a + 1;                                    // the "+ 1" of every column
+                const long long c = min(b, ny + lo);                            // last column whose bottom edge is i - lo
+                if(c >= a) total += (c - a + 1) * (a + c) / 2 - lo * (c - a + 1);
+                total += (b - max(c, a - 1)) * ny;                               // columns with bottom edge ny
+                const long long d = max(a, hi + 1);                             // first column whose top edge is i - hi
+                if(d <= b) total -= (b - d + 1) * (d + b) / 2 - hi * (b - d + 1);
+                cells = (unsigned long long)total;
             }
         }
     }

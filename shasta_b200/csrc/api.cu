@@ -379,6 +379,28 @@ shb_status shb_compute_candidate_table(shb_context* c, const void* candidates, u
     });
 }
 
+shb_status shb_test_radix_sort(shb_context* c, uint64_t* keys, uint32_t* values, uint64_t n,
+                               int lowBegin, int lowEnd, int highBegin, int highEnd)
+{
+    return guarded([&] {
+        SHB_REQUIRE(c && (keys || n == 0), SHB_ERR_INVALID, "Null argument.");
+        SHB_CUDA(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        DeviceBuffer<uint64_t> kA, kB;
+        DeviceBuffer<uint32_t> vA, vB;
+        kA.reserve(n + 1); kB.reserve(n + 1); vA.reserve(n + 1); vB.reserve(n + 1);
+        SHB_CUDA(cudaMemcpyAsync(kA.get(), keys, 8 * n, cudaMemcpyHostToDevice, st));
+        if(values) SHB_CUDA(cudaMemcpyAsync(vA.get(), values, 4 * n, cudaMemcpyHostToDevice, st));
+        const int ranges[2][2] = {{lowBegin, lowEnd}, {highBegin, highEnd}};
+        const int rangeCount = (highEnd > highBegin) ? 2 : 1;
+        const bool inB = values ? radixSort<true>(kA.get(), kB.get(), vA.get(), vB.get(), n, ranges, rangeCount, c->sortWs, st)
+                                : radixSort<false>(kA.get(), kB.get(), nullptr, nullptr, n, ranges, rangeCount, c->sortWs, st);
+        SHB_CUDA(cudaMemcpyAsync(keys, inB ? kB.get() : kA.get(), 8 * n, cudaMemcpyDeviceToHost, st));
+        if(values) SHB_CUDA(cudaMemcpyAsync(values, inB ? vB.get() : vA.get(), 4 * n, cudaMemcpyDeviceToHost, st));
+        SHB_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
 uint64_t shb_digest_records(const uint32_t* records, uint64_t count, uint32_t words)
 {
     uint64_t sum = 0;

@@ -39,24 +39,45 @@ template<class T> T readScalar(const T* dev, cudaStream_t stream)
     return v;
 }
 
+// Sizes of the fused-iteration groups the default feature length (m = 4, every shipped configuration) has a fully
+// unrolled kernel for; the iteration loop of lowhash0 cuts the iterations into groups of these sizes.
+const uint32_t kUnrolledGroups[] = {16, 10, 8, 4, 2, 1};
+
+uint32_t nextSweepGroup(uint64_t remaining)
+{
+    for(uint32_t g : kUnrolledGroups) if(g <= remaining) return g;
+    return 1;
+}
+
 void launchSweep(const SweepArgs& a, uint32_t blocks, cudaStream_t stream)
 {
+    if(a.m == 4) {
+        switch(a.iterationCount) {
+        case 16: SHB_LAUNCH((lowhashSweepKernel<4, 16>), blocks, kSweepThreads, 0, stream, a); return;
+        case 10: SHB_LAUNCH((lowhashSweepKernel<4, 10>), blocks, kSweepThreads, 0, stream, a); return;
+        case 8: SHB_LAUNCH((lowhashSweepKernel<4, 8>), blocks, kSweepThreads, 0, stream, a); return;
+        case 4: SHB_LAUNCH((lowhashSweepKernel<4, 4>), blocks, kSweepThreads, 0, stream, a); return;
+        case 2: SHB_LAUNCH((lowhashSweepKernel<4, 2>), blocks, kSweepThreads, 0, stream, a); return;
+        case 1: SHB_LAUNCH((lowhashSweepKernel<4, 1>), blocks, kSweepThreads, 0, stream, a); return;
+        default: break;
+        }
+    }
     switch(a.m) {
-    case 1: SHB_LAUNCH(lowhashSweepKernel<1>, blocks, kSweepThreads, 0, stream, a); break;
-    case 2: SHB_LAUNCH(lowhashSweepKernel<2>, blocks, kSweepThreads, 0, stream, a); break;
-    case 3: SHB_LAUNCH(lowhashSweepKernel<3>, blocks, kSweepThreads, 0, stream, a); break;
-    case 4: SHB_LAUNCH(lowhashSweepKernel<4>, blocks, kSweepThreads, 0, stream, a); break;
-    case 5: SHB_LAUNCH(lowhashSweepKernel<5>, blocks, kSweepThreads, 0, stream, a); break;
-    case 6: SHB_LAUNCH(lowhashSweepKernel<6>, blocks, kSweepThreads, 0, stream, a); break;
-    case 7: SHB_LAUNCH(lowhashSweepKernel<7>, blocks, kSweepThreads, 0, stream, a); break;
-    case 8: SHB_LAUNCH(lowhashSweepKernel<8>, blocks, kSweepThreads, 0, stream, a); break;
-    default: SHB_LAUNCH(lowhashSweepKernel<0>, blocks, kSweepThreads, 0, stream, a); break;
+    case 1: SHB_LAUNCH((lowhashSweepKernel<1, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 2: SHB_LAUNCH((lowhashSweepKernel<2, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 3: SHB_LAUNCH((lowhashSweepKernel<3, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 4: SHB_LAUNCH((lowhashSweepKernel<4, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 5: SHB_LAUNCH((lowhashSweepKernel<5, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 6: SHB_LAUNCH((lowhashSweepKernel<6, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 7: SHB_LAUNCH((lowhashSweepKernel<7, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 8: SHB_LAUNCH((lowhashSweepKernel<8, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    default: SHB_LAUNCH((lowhashSweepKernel<0, 0>), blocks, kSweepThreads, 0, stream, a); break;
     }
 }
 
 // Sorted-by-key (keys[,vals]) -> head flags, exclusive segment index, segment starts.
-// Returns the number of segments (one host sync).
-uint32_t buildSegments(shb_context* c, const uint64_t* sortedKeys, uint32_t n, int shift)
+// Returns the number of segments (one host sync) unless wantCount is false (then 0, no sync).
+uint32_t buildSegments(shb_context* c, const uint64_t* sortedKeys, uint32_t n, int shift, bool wantCount = true)
 {
     cudaStream_t st = c->stream;
     c->flagsBuf.reserve(n);
@@ -69,7 +90,7 @@ uint32_t buildSegments(shb_context* c, const uint64_t* sortedKeys, uint32_t n, i
     exclusiveScan<uint32_t>(c->flagsBuf.get(), c->indexBuf.get(), n, total, c->scanWs.get(), st);
     SHB_LAUNCH(segmentStartsKernel, ceilDiv(n, 256), 256, 0, st,
                (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(), n, c->segStartBuf.get());
-    return readScalar<uint32_t>(total, st);
+    return wantCount ? readScalar<uint32_t>(total, st) : 0u;
 }
 
 using Accumulator = LowHashAccumulator;
@@ -258,7 +279,7 @@ void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uin
     const uint64_t* keys = inTmp ? c->entryKeysTmp.get() : keysA;
     const uint32_t* vals = inTmp ? c->entryValsTmp.get() : valsA;
 
-    buildSegments(c, keys, n, 32);
+    buildSegments(c, keys, n, 32, false);
 
     // Count pass (also per-read statistics), scan, emit pass.
     c->countsBuf.reserve(n);
@@ -421,7 +442,7 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
                         "MinHash.alignmentCandidatesPerRead was not reached after 4096 LowHash iterations.");
         } else {
             if(iteration == p.minHashIterationCount) break;
-            if(!perIteration) group = uint32_t(std::min<uint64_t>(kMaxFusedIterations, p.minHashIterationCount - iteration));
+            if(!perIteration) group = nextSweepGroup(p.minHashIterationCount - iteration);
         }
         unsigned long long counts[kMaxFusedIterations];
         lowhashSweep(c, iteration, group, counts);

@@ -55,7 +55,8 @@ constexpr int kSweepThreads = 256;
 constexpr int kSweepPositionsPerThread = 8;
 constexpr int kSweepTile = kSweepThreads * kSweepPositionsPerThread;      // 2048 positions per block
 constexpr int kMaxFusedIterations = 16;
-constexpr int kSweepQueue = 2048;         // low hashes queued per block before the (rare) inline path
+constexpr int kSweepQueue = 768;          // low hashes queued per block (expected 2048 * K * hashFraction ~ 205 for K = 10,
+                                          // hashFraction 0.01); beyond that the rare path runs inline
 constexpr int kMaxTemplatedM = 8;
 
 struct SweepArgs {
@@ -76,40 +77,48 @@ struct SweepArgs {
     unsigned long long* counts;     // [iterationCount]
 };
 
-// x * 0xc6a4a7935bd1e995 (mod 2^64) as one wide multiply and two multiply-adds chained through the high word.
-__device__ __forceinline__ uint64_t mulM(uint64_t x)
+// 64-bit values as two 32-bit halves: the hash is pure 32-bit integer work on this machine, and keeping the halves apart
+// stops the compiler from routing them through 64-bit adds with carry chains.
+struct U64Halves { uint32_t lo, hi; };
+__device__ __forceinline__ U64Halves halves(uint64_t x) { return U64Halves{uint32_t(x), uint32_t(x >> 32)}; }
+__device__ __forceinline__ uint64_t whole(U64Halves x) { return (uint64_t(x.hi) << 32) | x.lo; }
+
+// x * 0xc6a4a7935bd1e995 (mod 2^64): one wide multiply and two multiply-adds into the high word.
+__device__ __forceinline__ U64Halves mulM(U64Halves x)
 {
-    const uint32_t MLO = 0x5bd1e995u, MHI = 0xc6a4a793u;
-    const uint32_t lo = uint32_t(x), hi = uint32_t(x >> 32);
-    const uint64_t wide = uint64_t(lo) * MLO;
-    const uint32_t plo = uint32_t(wide);
-    uint32_t phi = uint32_t(wide >> 32);
-    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(lo), "r"(MHI));
-    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(hi), "r"(MLO));
-    return (uint64_t(phi) << 32) | plo;
+    U64Halves r;
+    asm("{\n\t.reg .u64 w;\n\tmul.wide.u32 w, %2, 0x5bd1e995;\n\tmov.b64 {%0, %1}, w;\n\t"
+        "mad.lo.u32 %1, %2, 0xc6a4a793, %1;\n\tmad.lo.u32 %1, %3, 0x5bd1e995, %1;\n\t}"
+        : "=r"(r.lo), "=&r"(r.hi) : "r"(x.lo), "r"(x.hi));
+    return r;
 }
+__device__ __forceinline__ uint64_t mulM(uint64_t x) { return whole(mulM(halves(x))); }
 
 __device__ __forceinline__ uint64_t murmurMix(uint64_t k)
 {
-    k = mulM(k);
-    k ^= k >> 47;
-    k = mulM(k);
-    return k;
+    U64Halves h = mulM(halves(k));
+    h.lo ^= h.hi >> 15;                 // k ^= k >> 47
+    return whole(mulM(h));
 }
 
-// MurmurHash64A of one feature for one seed, given the seed-independent mixed blocks and tail.
-template<int MM> __device__ __forceinline__ uint64_t murmurFinish(uint64_t h, const uint64_t* mixed, uint32_t blocks, bool hasTail, uint64_t tail)
+// MurmurHash64A of one feature for one seed, given the seed-independent mixed blocks and tail, up to but NOT including
+// the final `h ^= h >> 47`: that last step only touches the low 17 bits, so the high word — all the threshold test of the
+// hot loop looks at — is already final. h0 = (seed ^ len*M) ^ mixed[0] when the feature has at least one block.
+template<int MM> __device__ __forceinline__ U64Halves murmurAlmost(U64Halves h, const uint64_t* mixed, uint32_t blocks, bool hasTail, uint64_t tail)
 {
-    if(MM > 0) {
+    if(MM >= 2) {
+        h = mulM(h);
 #pragma unroll
-        for(int b = 0; b < MM / 2; b++) { h ^= mixed[b]; h = mulM(h); }
-    } else {
-        for(uint32_t b = 0; b < blocks; b++) { h ^= mixed[b]; h = mulM(h); }
+        for(int b = 1; b < MM / 2; b++) { h.lo ^= uint32_t(mixed[b]); h.hi ^= uint32_t(mixed[b] >> 32); h = mulM(h); }
+    } else if(MM == 0) {
+        if(blocks) {
+            h = mulM(h);
+            for(uint32_t b = 1; b < blocks; b++) { h.lo ^= uint32_t(mixed[b]); h.hi ^= uint32_t(mixed[b] >> 32); h = mulM(h); }
+        }
     }
-    if(hasTail) { h ^= tail; h = mulM(h); }
-    h ^= h >> 47;
+    if(hasTail) { h.lo ^= uint32_t(tail); h.hi ^= uint32_t(tail >> 32); h = mulM(h); }
+    h.lo ^= h.hi >> 15;                 // h ^= h >> 47
     h = mulM(h);
-    h ^= h >> 47;
     return h;
 }
 
@@ -128,24 +137,25 @@ __device__ __forceinline__ uint32_t resolveFeature(const SweepArgs& a, uint64_t 
     return (inside && !palindromic) ? lo : 0xffffffffu;
 }
 
-// The hot loop only hashes and queues the (about hashFraction) low hashes in shared memory; the
-// divergent work (toc binary search, validity, output slot) is done afterwards by all threads of the
-// block over the queue, so a warp never serialises behind one lane's rare path.
-template<int MM> __global__ void __launch_bounds__(kSweepThreads)
+// The hot loop hashes every position for every seed of the launch and tests only the HIGH word of the hash against the
+// threshold (one compare). The few hashes that pass (about hashFraction of them) finish the hash, make the exact test and
+// are queued in shared memory; the divergent work on them (toc binary search, validity, output slot) is done afterwards by
+// all threads of the block over the queue, so a warp never serialises behind one lane's rare path.
+// KK > 0: the number of fused iterations is a compile-time constant (fully unrolled seed loop); KK == 0: a.iterationCount.
+template<int MM, int KK> __global__ void __launch_bounds__(kSweepThreads)
 lowhashSweepKernel(const SweepArgs a)
 {
     constexpr int kHalo = 2 * kMaxFusedIterations;       // >= any supported m (generic path caps m at 32)
     __shared__ uint32_t sk[kSweepTile + kHalo];
     __shared__ uint64_t queueHash[kSweepQueue];
-    __shared__ uint32_t queueMeta[kSweepQueue];          // in: local | s<<16   out: orientedRead (global) or ~0
-    __shared__ uint32_t queueRank[kSweepQueue];
+    __shared__ uint32_t queueMeta[kSweepQueue];          // in: local | s<<16   out: rank within (block, seed) | s<<24, or ~0
+    __shared__ uint32_t queueRead[kSweepQueue];          // oriented read (global)
     __shared__ uint32_t queueCount;
     __shared__ uint32_t seedCount[kMaxFusedIterations];
     __shared__ unsigned long long seedBase[kMaxFusedIterations];
 
     const uint64_t M = 0xc6a4a7935bd1e995ull;
     const uint32_t m = (MM > 0) ? uint32_t(MM) : a.m;
-    static_assert(kMaxFusedIterations <= 32, "the per-position hit mask has 32 bits");
     const uint64_t tileBase = uint64_t(blockIdx.x) * kSweepTile;
 
     if(threadIdx.x < kMaxFusedIterations) seedCount[threadIdx.x] = 0;
@@ -156,9 +166,11 @@ lowhashSweepKernel(const SweepArgs a)
     }
     __syncthreads();
 
-    const uint32_t K = a.iterationCount;
+    const uint32_t K = (KK > 0) ? uint32_t(KK) : a.iterationCount;
     const uint64_t lenTimesM = uint64_t(4u * m) * M;
     const uint64_t threshold = a.hashThreshold;
+    const uint32_t thresholdHigh = uint32_t(threshold >> 32);
+    const uint32_t seed0 = a.iterationBegin * 37u;                    // iteration * 37 fits 32 bits
 
 #pragma unroll 1
     for(int slot = 0; slot < kSweepPositionsPerThread; slot++) {
@@ -183,32 +195,29 @@ lowhashSweepKernel(const SweepArgs a)
         }
         const bool hasTail = (m & 1u) != 0;
         const uint64_t tail = hasTail ? uint64_t(sk[local + m - 1]) : 0ull;
+        // h after the first block's xor = (seed ^ len*M) ^ mixed[0]; the seed only reaches the low word.
+        const uint64_t x0 = blocks ? (lenTimesM ^ mixed[0]) : lenTimesM;
 
-        // Hot loop: hash for every seed, remember WHICH seeds gave a low hash in a bit mask (no divergent work here).
-        uint32_t hitMask = 0;
-        const uint32_t seedBase = a.iterationBegin * 37u;              // iteration * 37 fits 32 bits
-#pragma unroll 2
-        for(uint32_t s = 0; s < K; s++) {
-            const uint64_t h = murmurFinish<MM>(uint64_t(seedBase + 37u * s) ^ lenTimesM, mixed, blocks, hasTail, tail);
-            hitMask |= (h < threshold) ? (1u << s) : 0u;
-        }
-        // Rare path (about hashFraction of the hashes): recompute the few low hashes and queue them.
-        while(hitMask) {
-            const uint32_t s = uint32_t(__ffs(int(hitMask))) - 1u;
-            hitMask &= hitMask - 1u;
-            const uint64_t h = murmurFinish<MM>(uint64_t(seedBase + 37u * s) ^ lenTimesM, mixed, blocks, hasTail, tail);
-            const uint32_t q = atomicAdd(&queueCount, 1u);
-            if(q < (uint32_t)kSweepQueue) {
-                queueHash[q] = h;
-                queueMeta[q] = uint32_t(local) | (s << 16);
-            } else {
-                // Queue full (pathological hashFraction): do the rare path inline.
-                const uint32_t o = resolveFeature(a, p, m);
-                if(o != 0xffffffffu) {
-                    const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
-                    if(gi < a.capacity) {
-                        a.keys[uint64_t(s) * a.capacity + gi] = ((h & a.bucketMask) << 32) | (h >> 32);
-                        a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
+#pragma unroll
+        for(uint32_t s = 0; s < ((KK > 0) ? uint32_t(KK) : K); s++) {
+            const U64Halves h = murmurAlmost<MM>(U64Halves{uint32_t(x0) ^ (seed0 + 37u * s), uint32_t(x0 >> 32)}, mixed, blocks, hasTail, tail);
+            if(h.hi <= thresholdHigh) {                                // rare (about hashFraction + 2^-32)
+                const uint64_t hash = whole(U64Halves{h.lo ^ (h.hi >> 15), h.hi});
+                if(hash < threshold) {
+                    const uint32_t q = atomicAdd(&queueCount, 1u);
+                    if(q < (uint32_t)kSweepQueue) {
+                        queueHash[q] = hash;
+                        queueMeta[q] = uint32_t(local) | (s << 16);
+                    } else {
+                        // Queue full (pathological hashFraction): do the rare path inline.
+                        const uint32_t o = resolveFeature(a, p, m);
+                        if(o != 0xffffffffu) {
+                            const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
+                            if(gi < a.capacity) {
+                                a.keys[uint64_t(s) * a.capacity + gi] = ((hash & a.bucketMask) << 32) | (hash >> 32);
+                                a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
+                            }
+                        }
                     }
                 }
             }
@@ -223,8 +232,8 @@ lowhashSweepKernel(const SweepArgs a)
         const uint32_t local = meta & 0xffffu, s = meta >> 16;
         const uint32_t o = resolveFeature(a, tileBase + local, m);
         if(o != 0xffffffffu) {
-            queueRank[q] = atomicAdd(&seedCount[s], 1u) | (s << 24);
-            queueMeta[q] = a.orientedReadBase + o;
+            queueMeta[q] = atomicAdd(&seedCount[s], 1u) | (s << 24);
+            queueRead[q] = a.orientedReadBase + o;
         } else {
             queueMeta[q] = 0xffffffffu;
         }
@@ -237,14 +246,14 @@ lowhashSweepKernel(const SweepArgs a)
     __syncthreads();
     // Queue pass B: write (bucketId<<32 | hashHigh, orientedReadId) to the iteration's slab.
     for(uint32_t q = threadIdx.x; q < nq; q += kSweepThreads) {
-        const uint32_t oread = queueMeta[q];
-        if(oread == 0xffffffffu) continue;
-        const uint32_t s = queueRank[q] >> 24;
-        const unsigned long long gi = seedBase[s] + (queueRank[q] & 0xffffffu);
+        const uint32_t meta = queueMeta[q];
+        if(meta == 0xffffffffu) continue;
+        const uint32_t s = meta >> 24;
+        const unsigned long long gi = seedBase[s] + (meta & 0xffffffu);
         if(gi < a.capacity) {
             const uint64_t h = queueHash[q];
             a.keys[uint64_t(s) * a.capacity + gi] = ((h & a.bucketMask) << 32) | (h >> 32);
-            a.vals[uint64_t(s) * a.capacity + gi] = oread;
+            a.vals[uint64_t(s) * a.capacity + gi] = queueRead[q];
         }
     }
 }

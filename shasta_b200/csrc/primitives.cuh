@@ -1,5 +1,5 @@
 // Hand-written device-wide primitives used by the LowHash and alignment pipelines:
-// exclusive scan, LSD radix sort (64-bit keys, optional 32-bit payload), stream compaction helpers.
+// exclusive scan, stream compaction helpers, and (radix_sort.cuh) the LSD radix sort.
 // All are plain sm_100a CUDA (warp shuffles / match_any / shared-memory atomics); no CUB/Thrust.
 #pragma once
 
@@ -106,127 +106,11 @@ template<class T> void exclusiveScan(const T* in, T* out, uint64_t n, T* totalOu
     SHB_LAUNCH((scanDownsweepKernel<T>), (unsigned)blocks, kScanThreads, 0, stream, in, out, (const T*)sums, n, (T*)nullptr);
 }
 
-// ---------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, stable. Keys uint64; optional uint32 payload.
-constexpr int kSortThreads = 256;
-constexpr int kSortItemsPerThread = 16;
-constexpr int kSortTile = kSortThreads * kSortItemsPerThread;     // 4096 keys per block
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
+} // namespace shb
 
-// hist[digit * numBlocks + block] = number of keys of the block's tile with that digit.
-static __global__ void __launch_bounds__(kSortThreads)
-radixHistogramKernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t digitMask,
-                     uint32_t* __restrict__ hist, uint32_t numBlocks)
-{
-    __shared__ uint32_t counts[kRadix];
-    counts[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t base = blockIdx.x * kSortTile;
-#pragma unroll
-    for(int i = 0; i < kSortItemsPerThread; i++) {
-        const uint32_t idx = base + i * kSortThreads + threadIdx.x;
-        if(idx < n) {
-            const uint32_t d = uint32_t(keys[idx] >> shift) & digitMask;
-            atomicAdd(&counts[d], 1u);
-        }
-    }
-    __syncthreads();
-    hist[threadIdx.x * numBlocks + blockIdx.x] = counts[threadIdx.x];
-}
+#include "radix_sort.cuh"      // radixSort<HAS_VALUES>, SortWorkspace
 
-// Stable scatter. offsets = exclusive scan of hist (same indexing).
-template<bool HAS_VALUES> __global__ void __launch_bounds__(kSortThreads)
-radixScatterKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ keysOut,
-                   const uint32_t* __restrict__ valsIn, uint32_t* __restrict__ valsOut,
-                   uint32_t n, int shift, uint32_t digitMask,
-                   const uint32_t* __restrict__ offsets, uint32_t numBlocks)
-{
-    constexpr int kWarps = kSortThreads / 32;
-    __shared__ uint32_t digitBase[kRadix];               // next output slot per digit
-    __shared__ uint32_t warpCounts[kWarps][kRadix];      // per chunk: count, then start slot, per warp
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned warp = threadIdx.x >> 5;
-    digitBase[threadIdx.x] = offsets[threadIdx.x * numBlocks + blockIdx.x];
-    const uint32_t base = blockIdx.x * kSortTile;
-#pragma unroll 1
-    for(int i = 0; i < kSortItemsPerThread; i++) {
-        const uint32_t idx = base + i * kSortThreads + threadIdx.x;
-        const bool active = idx < n;
-#pragma unroll
-        for(int w = 0; w < kWarps; w++) warpCounts[w][threadIdx.x] = 0;
-        __syncthreads();
-        uint64_t key = 0;
-        uint32_t val = 0;
-        uint32_t d = kRadix;                             // sentinel digit for inactive lanes
-        if(active) {
-            key = keysIn[idx];
-            if(HAS_VALUES) val = valsIn[idx];
-            d = uint32_t(key >> shift) & digitMask;
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned rankInWarp = __popc(peers & ((1u << lane) - 1u));
-        if(active && rankInWarp == 0) warpCounts[warp][d] = __popc(peers);
-        __syncthreads();
-        {
-            // Thread t owns digit t: turn the per-warp counts into start slots.
-            uint32_t run = digitBase[threadIdx.x];
-#pragma unroll
-            for(int w = 0; w < kWarps; w++) {
-                const uint32_t c = warpCounts[w][threadIdx.x];
-                warpCounts[w][threadIdx.x] = run;
-                run += c;
-            }
-            digitBase[threadIdx.x] = run;
-        }
-        __syncthreads();
-        if(active) {
-            const uint32_t dst = warpCounts[warp][d] + rankInWarp;
-            keysOut[dst] = key;
-            if(HAS_VALUES) valsOut[dst] = val;
-        }
-        __syncthreads();
-    }
-}
-
-struct SortWorkspace {
-    DeviceBuffer<uint32_t> hist;
-    DeviceBuffer<uint32_t> scanWs;
-};
-
-// Sorts n (key[,value]) items on the bit ranges given (each range [begin,end) is processed in
-// 8-bit passes, least significant range first). Buffers ping-pong between (keysA,valsA) and
-// (keysB,valsB); returns true if the result ends up in the B buffers.
-template<bool HAS_VALUES>
-bool radixSort(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* valsB, uint64_t n,
-               const int (*bitRanges)[2], int rangeCount, SortWorkspace& ws, cudaStream_t stream)
-{
-    SHB_REQUIRE(n < (1ull << 32), SHB_ERR_INVALID, "radixSort: more than 2^32-1 items in one sort.");
-    if(n == 0) return false;
-    const uint32_t numBlocks = ceilDiv(n, kSortTile);
-    const uint64_t histSize = uint64_t(kRadix) * numBlocks;
-    ws.hist.reserve(histSize);
-    ws.scanWs.reserve(scanWorkspaceElements(histSize));
-    bool inB = false;
-    for(int r = 0; r < rangeCount; r++) {
-        for(int bit = bitRanges[r][0]; bit < bitRanges[r][1]; bit += kRadixBits) {
-            const int bits = (bitRanges[r][1] - bit < kRadixBits) ? (bitRanges[r][1] - bit) : kRadixBits;
-            const uint32_t digitMask = (1u << bits) - 1u;
-            uint64_t* kin = inB ? keysB : keysA;
-            uint64_t* kout = inB ? keysA : keysB;
-            uint32_t* vin = inB ? valsB : valsA;
-            uint32_t* vout = inB ? valsA : valsB;
-            SHB_LAUNCH(radixHistogramKernel, numBlocks, kSortThreads, 0, stream,
-                       (const uint64_t*)kin, (uint32_t)n, bit, digitMask, ws.hist.get(), numBlocks);
-            exclusiveScan<uint32_t>(ws.hist.get(), ws.hist.get(), histSize, nullptr, ws.scanWs.get(), stream);
-            SHB_LAUNCH((radixScatterKernel<HAS_VALUES>), numBlocks, kSortThreads, 0, stream,
-                       (const uint64_t*)kin, kout, (const uint32_t*)vin, vout, (uint32_t)n, bit, digitMask,
-                       (const uint32_t*)ws.hist.get(), numBlocks);
-            inB = !inB;
-        }
-    }
-    return inB;
-}
+namespace shb {
 
 // counts[digit] += 1 for every key (warp-aggregated atomics; the input is sorted by digit so runs are long).
 static __global__ void digitCountKernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t digitMask,
