@@ -272,6 +272,45 @@ shb_status shb_compute_candidate_table(shb_context* ctx, const void* candidates,
                                        uint64_t readCount, uint64_t** tableToc, uint64_t** tableData);
 
 /* ------------------------------------------------------------------------------------------
+ * Read-sharded multi-GPU runs (BASELINE.json configs[2..4]): one process (and one context) per GPU,
+ * NCCL over NVLink / NVSwitch for the two exchanges LowHash0 needs (bucket entries per iteration, pair counts once) and
+ * for replicating the k-mer ids before the alignment step. NCCL is loaded at run time (libnccl.so.2); a host that
+ * already has a communicator for these GPUs passes it with shb_dist_attach, otherwise rank 0 calls shb_dist_unique_id,
+ * ships the 128 bytes to the other ranks by any means (MPI, a file, torch.distributed ...) and every rank calls
+ * shb_dist_init (collective). The number of ranks must be a power of two. All shb_*_sharded calls are collective: every
+ * rank makes the same calls in the same order.
+ *   markers: each rank uploads the rows of its read range with shb_set_markers(readBegin, readEnd); the ranges must be
+ *            contiguous in rank order and cover all reads.
+ */
+#define SHB_DIST_UNIQUE_ID_BYTES 128
+shb_status shb_dist_unique_id(void* id128);
+shb_status shb_dist_init(shb_context* ctx, int worldSize, int rank, const void* id128);
+shb_status shb_dist_attach(shb_context* ctx, void* ncclComm /* ncclComm_t */, int worldSize, int rank);
+void shb_dist_finalize(shb_context* ctx);
+
+/* Assembler::findAlignmentCandidatesLowHash0 over the read shards (fixed minHashIterationCount). Rank g receives the g-th
+ * contiguous block of the candidate list in the reference's order (the blocks are evened out on the device), free with
+ * shb_free; stats (optional, uint64[readCountTotal*3]) receives the complete ReadLowHashStatistics on every rank;
+ * result->candidateDigest is the digest of the slice this rank emitted: the ranks' digests sum (mod 2^64) to the digest of
+ * the single-GPU run. */
+shb_status shb_lowhash0_sharded(shb_context* ctx, const shb_lowhash_params* params, void** candidates, uint64_t* candidateCount,
+                                uint64_t* stats, shb_lowhash_result* result);
+
+/* Assembler::computeAlignments on this rank's block of candidates: the k-mer id shards of all ranks are gathered into this
+ * GPU once per marker set (cached until shb_set_markers* is called again; collective only then), after which the call
+ * is local. Same outputs as shb_compute_alignments. */
+shb_status shb_compute_alignments_sharded(shb_context* ctx, const void* candidates, uint64_t candidateCount,
+                                          const shb_align_options* options, void** alignmentData, uint64_t* alignmentCount,
+                                          uint64_t** compressedToc, uint8_t** compressedData, shb_align_result* result);
+
+typedef struct {
+    double sweepSeconds, partitionSeconds, exchangeSeconds, processSeconds, finalSeconds, gatherSeconds, totalSeconds;
+    uint64_t entriesReceived, pairsReceived;
+} shb_dist_timing;
+/* Host wall-clock breakdown of the last shb_lowhash0_sharded / marker gather on this rank (diagnostics). */
+shb_status shb_dist_timing_get(shb_context* ctx, shb_dist_timing* timing);
+
+/* ------------------------------------------------------------------------------------------
  * Bench / test utilities (not part of the reference's interface): the marker-space synthetic read
  * generator of shasta_b200/synth.py on the device, and helpers for the device buffers it returns.
  */

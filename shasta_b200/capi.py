@@ -58,6 +58,15 @@ class AlignResult(C.Structure):
                 ("compressedDigest", C.c_uint64)]
 
 
+class DistTiming(C.Structure):
+    _fields_ = [("sweepSeconds", C.c_double), ("partitionSeconds", C.c_double), ("exchangeSeconds", C.c_double),
+                ("processSeconds", C.c_double), ("finalSeconds", C.c_double), ("gatherSeconds", C.c_double),
+                ("totalSeconds", C.c_double), ("entriesReceived", C.c_uint64), ("pairsReceived", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 # Defaults of src/AssemblerOptions.cpp:380-489
 ALIGN_DEFAULTS = dict(alignMethod=3, maxSkip=30, maxDrift=30, maxTrim=30, maxMarkerFrequency=10, minAlignedMarkerCount=100,
                       minAlignedFraction=0.4, matchScore=6, mismatchScore=-1, gapScore=-1, downsamplingFactor=0.1,
@@ -99,6 +108,17 @@ def lib():
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                              C.POINTER(AlignResult)]
         L.shb_compute_alignment_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_dist_unique_id.argtypes = [C.c_void_p]
+        L.shb_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.shb_dist_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.shb_dist_finalize.argtypes = [C.c_void_p]
+        L.shb_dist_finalize.restype = None
+        L.shb_lowhash0_sharded.argtypes = [C.c_void_p, C.POINTER(LowHashParams), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                           C.c_void_p, C.POINTER(LowHashResult)]
+        L.shb_compute_alignments_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(AlignOptions), C.POINTER(C.c_void_p),
+                                                     C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                     C.POINTER(AlignResult)]
+        L.shb_dist_timing_get.argtypes = [C.c_void_p, C.POINTER(DistTiming)]
         L.shb_align_oriented_reads.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(AlignOptions), C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_uint64), C.c_void_p]
         L.shb_compute_candidate_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -156,6 +176,31 @@ class Context:
         if self._h:
             lib().shb_context_destroy(self._h)
             self._h = C.c_void_p()
+
+    # ---- multi-GPU (one process per GPU; NCCL inside the library) -------------------------------------------------
+    def dist_init(self, world, rank, unique_id: bytes):
+        """Collective: joins the NCCL communicator described by unique_id (dist_unique_id() of rank 0)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().shb_dist_init(self._h, int(world), int(rank), buf))
+
+    def dist_finalize(self):
+        lib().shb_dist_finalize(self._h)
+
+    def lowhash0_sharded(self, params: LowHashParams, want_stats=True):
+        """Collective. Returns (this rank's block of the candidates uint32[n,3], stats uint64[R,3] | None, LowHashResult)."""
+        cand = C.c_void_p()
+        n = C.c_uint64()
+        res = LowHashResult()
+        stats = np.zeros((self.read_count, 3), np.uint64) if want_stats else None
+        _check(lib().shb_lowhash0_sharded(self._h, C.byref(params), C.byref(cand), C.byref(n), _ptr(stats), C.byref(res)))
+        out = _records_to_array(cand, n.value)
+        lib().shb_free(cand)
+        return out, stats, res
+
+    def dist_timing(self):
+        t = DistTiming()
+        _check(lib().shb_dist_timing_get(self._h, C.byref(t)))
+        return t
 
     def __del__(self):
         try:
@@ -316,6 +361,32 @@ def compute_alignments(ctx: Context, candidates, options: AlignOptions):
     res = AlignResult()
     _check(lib().shb_compute_alignments(ctx._h, _ptr(cand), len(cand), C.byref(options), C.byref(rec), C.byref(cnt),
                                         C.byref(toc), C.byref(data), C.byref(res)))
+    n = cnt.value
+    tocn = _owned_array(toc, n + 1, np.uint64)
+    nb = int(tocn[-1])
+    records = _owned_array(rec, 16 * n, np.uint32).reshape(n, 16)
+    datan = _owned_array(data, nb, np.uint8)
+    return records, tocn, datan, res
+
+
+def dist_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
+    buf = (C.c_uint8 * 128)()
+    _check(lib().shb_dist_unique_id(buf))
+    return bytes(buf)
+
+
+def compute_alignments_sharded(ctx: Context, candidates, options: AlignOptions):
+    """Assembler::computeAlignments on this rank's block of candidates; the k-mer ids of all ranks are gathered into this
+    GPU on the first call after the markers changed (collective then). Same returns as compute_alignments."""
+    cand = candidates_to_records(candidates)
+    rec = C.c_void_p()
+    cnt = C.c_uint64()
+    toc = C.c_void_p()
+    data = C.c_void_p()
+    res = AlignResult()
+    _check(lib().shb_compute_alignments_sharded(ctx._h, _ptr(cand), len(cand), C.byref(options), C.byref(rec), C.byref(cnt),
+                                                C.byref(toc), C.byref(data), C.byref(res)))
     n = cnt.value
     tocn = _owned_array(toc, n + 1, np.uint64)
     nb = int(tocn[-1])

@@ -21,6 +21,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
                        bool explicitOrientation);
 void destroyAlignCache(shb_context* c);
 void destroyLowhashState(shb_context* c);
+void destroyDistState(shb_context* c);
 LowHashState& lowhashState(shb_context* c);
 void lowhashBegin(shb_context* c, const shb_lowhash_params& p);
 void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsigned long long* counts);
@@ -108,6 +109,7 @@ void shb_context_destroy(shb_context* c)
     if(!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    destroyDistState(c);
     destroyAlignCache(c);
     destroyLowhashState(c);
     for(int i = 0; i < 2; i++) { if(c->pinnedStage[i]) cudaFreeHost(c->pinnedStage[i]); if(c->stageEvent[i]) cudaEventDestroy(c->stageEvent[i]); }

@@ -7,6 +7,7 @@
 #include <vector>
 
 namespace shb {
+constexpr int kMaxFusedIterations = 16;         // LowHash iterations hashed per pass over the k-mer ids (one slab each)
 struct LowHashAccumulator {
     uint64_t count = 0;
     bool inB = false;       // which of the acc ping-pong buffers holds the data
@@ -65,4 +66,6 @@ struct shb_context {
 
     // ---- alignment cache (downsampled markers; see align.cu) ------------------------------------
     void* alignCache = nullptr;
+    // ---- multi-GPU state (NCCL communicator, exchange buffers, gathered markers; see dist.cu) --------
+    void* dist = nullptr;
 };

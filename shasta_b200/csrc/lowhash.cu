@@ -43,35 +43,46 @@ template<class T> T readScalar(const T* dev, cudaStream_t stream)
 // unrolled kernel for; the iteration loop of lowhash0 cuts the iterations into groups of these sizes.
 const uint32_t kUnrolledGroups[] = {16, 10, 8, 4, 2, 1};
 
-uint32_t nextSweepGroup(uint64_t remaining)
+uint32_t nextSweepGroupImpl(uint64_t remaining)
 {
     for(uint32_t g : kUnrolledGroups) if(g <= remaining) return g;
     return 1;
+}
+
+template<int MM, int KK> void launchSweepKernel(const SweepArgs& a, uint32_t blocks, cudaStream_t stream)
+{
+    const size_t dynamicBytes = size_t(a.queueCapacity) * 16;
+    static size_t allowed = 0;          // per instantiation; the static part (tile + counters) is ~8.5 KB
+    if(dynamicBytes > allowed) {
+        SHB_CUDA(cudaFuncSetAttribute(lowhashSweepKernel<MM, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dynamicBytes)));
+        allowed = dynamicBytes;
+    }
+    SHB_LAUNCH((lowhashSweepKernel<MM, KK>), blocks, kSweepThreads, dynamicBytes, stream, a);
 }
 
 void launchSweep(const SweepArgs& a, uint32_t blocks, cudaStream_t stream)
 {
     if(a.m == 4) {
         switch(a.iterationCount) {
-        case 16: SHB_LAUNCH((lowhashSweepKernel<4, 16>), blocks, kSweepThreads, 0, stream, a); return;
-        case 10: SHB_LAUNCH((lowhashSweepKernel<4, 10>), blocks, kSweepThreads, 0, stream, a); return;
-        case 8: SHB_LAUNCH((lowhashSweepKernel<4, 8>), blocks, kSweepThreads, 0, stream, a); return;
-        case 4: SHB_LAUNCH((lowhashSweepKernel<4, 4>), blocks, kSweepThreads, 0, stream, a); return;
-        case 2: SHB_LAUNCH((lowhashSweepKernel<4, 2>), blocks, kSweepThreads, 0, stream, a); return;
-        case 1: SHB_LAUNCH((lowhashSweepKernel<4, 1>), blocks, kSweepThreads, 0, stream, a); return;
+        case 16: launchSweepKernel<4, 16>(a, blocks, stream); return;
+        case 10: launchSweepKernel<4, 10>(a, blocks, stream); return;
+        case 8: launchSweepKernel<4, 8>(a, blocks, stream); return;
+        case 4: launchSweepKernel<4, 4>(a, blocks, stream); return;
+        case 2: launchSweepKernel<4, 2>(a, blocks, stream); return;
+        case 1: launchSweepKernel<4, 1>(a, blocks, stream); return;
         default: break;
         }
     }
     switch(a.m) {
-    case 1: SHB_LAUNCH((lowhashSweepKernel<1, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    case 2: SHB_LAUNCH((lowhashSweepKernel<2, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    case 3: SHB_LAUNCH((lowhashSweepKernel<3, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    case 4: SHB_LAUNCH((lowhashSweepKernel<4, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    case 5: SHB_LAUNCH((lowhashSweepKernel<5, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    case 6: SHB_LAUNCH((lowhashSweepKernel<6, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    case 7: SHB_LAUNCH((lowhashSweepKernel<7, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    case 8: SHB_LAUNCH((lowhashSweepKernel<8, 0>), blocks, kSweepThreads, 0, stream, a); break;
-    default: SHB_LAUNCH((lowhashSweepKernel<0, 0>), blocks, kSweepThreads, 0, stream, a); break;
+    case 1: launchSweepKernel<1, 0>(a, blocks, stream); break;
+    case 2: launchSweepKernel<2, 0>(a, blocks, stream); break;
+    case 3: launchSweepKernel<3, 0>(a, blocks, stream); break;
+    case 4: launchSweepKernel<4, 0>(a, blocks, stream); break;
+    case 5: launchSweepKernel<5, 0>(a, blocks, stream); break;
+    case 6: launchSweepKernel<6, 0>(a, blocks, stream); break;
+    case 7: launchSweepKernel<7, 0>(a, blocks, stream); break;
+    case 8: launchSweepKernel<8, 0>(a, blocks, stream); break;
+    default: launchSweepKernel<0, 0>(a, blocks, stream); break;
     }
 }
 
@@ -156,6 +167,8 @@ uint64_t countHighFrequency(shb_context* c, const Accumulator& acc, uint64_t min
 
 } // namespace
 
+uint32_t nextSweepGroup(uint64_t remaining) { return nextSweepGroupImpl(remaining); }
+
 
 // ---------------------------------------------------------------------------------------------
 // Staged LowHash0. The single-GPU call is begin -> { sweep -> processEntries per slab } -> finish;
@@ -237,6 +250,10 @@ void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsig
         a.vals = c->sweepVals.get();
         a.capacity = S.capacity;
         a.counts = c->scalars.get();
+        {
+            const double expected = double(kSweepTile) * double(group) * S.p.hashFraction;
+            a.queueCapacity = uint32_t(std::min<double>(kSweepQueueMax, std::max<double>(kSweepQueueMin, 1.5 * expected + 64.)));
+        }
         const bool run = M >= S.p.m && M > 0;
         if(run) {
             SHB_CUDA(cudaEventRecord(sweepTimer.a, st));
@@ -343,8 +360,9 @@ void lowhashSetPairs(shb_context* c, const uint64_t* keys, const uint32_t* count
     S.acc.count = n;
 }
 
-// Final merge + emission, src/LowHash0.cpp:204-214. Returns a host buffer (shb_free) of 12-byte records.
-void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountOut)
+// Final merge + emission, src/LowHash0.cpp:204-214, left on the device: c->candidatesDev holds nOut 12-byte records.
+// The digest of the emitted records is computed asynchronously into S.candidateDigest's device slot (scalars[41]).
+uint64_t lowhashEmitDevice(shb_context* c)
 {
     LowHashState& S = lowhashState(c);
     SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
@@ -352,22 +370,32 @@ void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountO
     cudaStream_t st = c->stream;
     mergeAccumulator(c, S.acc, S.readBits);
     const uint64_t nOut = countHighFrequency(c, S.acc, S.p.minFrequency, true);
-    HostResult host(allocHostResult(nOut * 12));
-    SHB_REQUIRE(host.p != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment candidates.");
     unsigned long long* digestDev = c->scalars.get() + 41;
-    unsigned long long digest = 0;
+    SHB_CUDA(cudaMemsetAsync(digestDev, 0, sizeof(unsigned long long), st));
     if(nOut) {
         c->candidatesDev.reserve(3 * nOut);
         SHB_LAUNCH(emitCandidatesKernel, ceilDiv(S.acc.count, 256), 256, 0, st, (const uint64_t*)accKeys(c, S.acc),
                    (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(), uint32_t(S.acc.count),
                    c->candidatesDev.get());
-        SHB_CUDA(cudaMemcpyAsync(host.p, c->candidatesDev.get(), nOut * 12, cudaMemcpyDeviceToHost, st));
-        SHB_CUDA(cudaMemsetAsync(digestDev, 0, sizeof(unsigned long long), st));
         SHB_LAUNCH(digestRecordsKernel, ceilDiv(nOut, 256), 256, 0, st, (const uint32_t*)c->candidatesDev.get(), nOut, 3u, digestDev);
-        SHB_CUDA(cudaMemcpyAsync(&digest, digestDev, sizeof(digest), cudaMemcpyDeviceToHost, st));
     }
+    S.emittedCount = nOut;
+    return nOut;
+}
+
+// ... and copied to a host buffer (shb_free) of 12-byte records.
+void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountOut)
+{
+    LowHashState& S = lowhashState(c);
+    const uint64_t nOut = lowhashEmitDevice(c);
+    cudaStream_t st = c->stream;
+    HostResult host(allocHostResult(nOut * 12));
+    SHB_REQUIRE(host.p != nullptr, SHB_ERR_OOM, "Out of host memory for the alignment candidates.");
+    unsigned long long digest = 0;
+    if(nOut) SHB_CUDA(cudaMemcpyAsync(host.p, c->candidatesDev.get(), nOut * 12, cudaMemcpyDeviceToHost, st));
+    SHB_CUDA(cudaMemcpyAsync(&digest, c->scalars.get() + 41, sizeof(digest), cudaMemcpyDeviceToHost, st));
     SHB_CUDA(cudaStreamSynchronize(st));
-    S.emittedCount = nOut; S.candidateDigest = digest;
+    S.candidateDigest = digest;
     *candidatesOut = host.take();
     *candidateCountOut = nOut;
 }

@@ -7,6 +7,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "context.cuh"
 
 namespace shb {
 
@@ -54,9 +55,9 @@ extractKmerIdsKernel(const uint32_t* __restrict__ words, uint64_t wordCount, uin
 constexpr int kSweepThreads = 256;
 constexpr int kSweepPositionsPerThread = 8;
 constexpr int kSweepTile = kSweepThreads * kSweepPositionsPerThread;      // 2048 positions per block
-constexpr int kMaxFusedIterations = 16;
-constexpr int kSweepQueue = 768;          // low hashes queued per block (expected 2048 * K * hashFraction ~ 205 for K = 10,
-                                          // hashFraction 0.01); beyond that the rare path runs inline
+// Low hashes queued per block before the (slow) inline path: sized by the host from the expected 2048 * K * hashFraction
+// (205 for K = 10 and hashFraction 0.01; 1640 for K = 16 and the HiFi configuration's 0.05) with 50 % slack.
+constexpr uint32_t kSweepQueueMin = 256, kSweepQueueMax = 6144;
 constexpr int kMaxTemplatedM = 8;
 
 struct SweepArgs {
@@ -75,6 +76,7 @@ struct SweepArgs {
     uint32_t* vals;
     uint64_t capacity;
     unsigned long long* counts;     // [iterationCount]
+    uint32_t queueCapacity;         // entries of the shared-memory low-hash queue (16 bytes each, dynamic shared memory)
 };
 
 // 64-bit values as two 32-bit halves: the hash is pure 32-bit integer work on this machine, and keeping the halves apart
@@ -89,7 +91,7 @@ __device__ __forceinline__ U64Halves mulM(U64Halves x)
     U64Halves r;
     asm("{\n\t.reg .u64 w;\n\tmul.wide.u32 w, %2, 0x5bd1e995;\n\tmov.b64 {%0, %1}, w;\n\t"
         "mad.lo.u32 %1, %2, 0xc6a4a793, %1;\n\tmad.lo.u32 %1, %3, 0x5bd1e995, %1;\n\t}"
-        : "=r"(r.lo), "=&r"(r.hi) : "r"(x.lo), "r"(x.hi));
+        : "=&r"(r.lo), "=&r"(r.hi) : "r"(x.lo), "r"(x.hi));       // early clobber: x.lo is read again after r.lo is written
     return r;
 }
 __device__ __forceinline__ uint64_t mulM(uint64_t x) { return whole(mulM(halves(x))); }
@@ -147,9 +149,9 @@ lowhashSweepKernel(const SweepArgs a)
 {
     constexpr int kHalo = 2 * kMaxFusedIterations;       // >= any supported m (generic path caps m at 32)
     __shared__ uint32_t sk[kSweepTile + kHalo];
-    __shared__ uint64_t queueHash[kSweepQueue];
-    __shared__ uint32_t queueMeta[kSweepQueue];          // in: local | s<<16   out: rank within (block, seed) | s<<24, or ~0
-    __shared__ uint32_t queueRead[kSweepQueue];          // oriented read (global)
+    extern __shared__ uint64_t queueHash[];              // a.queueCapacity low hashes queued per block, then per entry:
+    uint32_t* queueMeta = reinterpret_cast<uint32_t*>(queueHash + a.queueCapacity);   // in: local | s<<16   out: rank within (block, seed) | s<<24, or ~0
+    uint32_t* queueRead = queueMeta + a.queueCapacity;                               // oriented read (global)
     __shared__ uint32_t queueCount;
     __shared__ uint32_t seedCount[kMaxFusedIterations];
     __shared__ unsigned long long seedBase[kMaxFusedIterations];
@@ -198,26 +200,35 @@ lowhashSweepKernel(const SweepArgs a)
         // h after the first block's xor = (seed ^ len*M) ^ mixed[0]; the seed only reaches the low word.
         const uint64_t x0 = blocks ? (lenTimesM ^ mixed[0]) : lenTimesM;
 
+        // Hot loop: hash for every seed and remember WHICH seeds passed the high-word test in a bit mask (no divergent work
+        // here: a warp step in which one of the 32 lanes has a hit would otherwise drag the whole warp through the rare path,
+        // and with hashFraction 0.01 that is one step in four).
+        uint32_t hitMask = 0;
 #pragma unroll
         for(uint32_t s = 0; s < ((KK > 0) ? uint32_t(KK) : K); s++) {
             const U64Halves h = murmurAlmost<MM>(U64Halves{uint32_t(x0) ^ (seed0 + 37u * s), uint32_t(x0 >> 32)}, mixed, blocks, hasTail, tail);
-            if(h.hi <= thresholdHigh) {                                // rare (about hashFraction + 2^-32)
-                const uint64_t hash = whole(U64Halves{h.lo ^ (h.hi >> 15), h.hi});
-                if(hash < threshold) {
-                    const uint32_t q = atomicAdd(&queueCount, 1u);
-                    if(q < (uint32_t)kSweepQueue) {
-                        queueHash[q] = hash;
-                        queueMeta[q] = uint32_t(local) | (s << 16);
-                    } else {
-                        // Queue full (pathological hashFraction): do the rare path inline.
-                        const uint32_t o = resolveFeature(a, p, m);
-                        if(o != 0xffffffffu) {
-                            const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
-                            if(gi < a.capacity) {
-                                a.keys[uint64_t(s) * a.capacity + gi] = ((hash & a.bucketMask) << 32) | (hash >> 32);
-                                a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
-                            }
-                        }
+            hitMask |= (h.hi <= thresholdHigh) ? (1u << s) : 0u;
+        }
+        // Rare path (about hashFraction of the hashes): recompute the few candidates, make the exact test and queue them.
+        while(hitMask) {
+            const uint32_t s = uint32_t(__ffs(int(hitMask))) - 1u;
+            hitMask &= hitMask - 1u;
+            const U64Halves h = murmurAlmost<MM>(U64Halves{uint32_t(x0) ^ (seed0 + 37u * s), uint32_t(x0 >> 32)}, mixed, blocks, hasTail, tail);
+            const uint64_t hash = whole(U64Halves{h.lo ^ (h.hi >> 15), h.hi});
+            if(hash >= threshold) continue;
+            const uint32_t q = atomicAdd(&queueCount, 1u);
+            if(q < a.queueCapacity) {
+                queueHash[q] = hash;
+                queueMeta[q] = uint32_t(local) | (s << 16);
+            } else {
+                // Queue full (cannot happen for the sizes the host derives from hashFraction unless the data are pathological):
+                // do the rare path inline.
+                const uint32_t o = resolveFeature(a, p, m);
+                if(o != 0xffffffffu) {
+                    const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
+                    if(gi < a.capacity) {
+                        a.keys[uint64_t(s) * a.capacity + gi] = ((hash & a.bucketMask) << 32) | (hash >> 32);
+                        a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
                     }
                 }
             }
@@ -226,7 +237,7 @@ lowhashSweepKernel(const SweepArgs a)
     __syncthreads();
 
     // Queue pass A: resolve each queued low hash to its oriented read, rank it within (block, seed).
-    const uint32_t nq = min(queueCount, (uint32_t)kSweepQueue);
+    const uint32_t nq = min(queueCount, a.queueCapacity);
     for(uint32_t q = threadIdx.x; q < nq; q += kSweepThreads) {
         const uint32_t meta = queueMeta[q];
         const uint32_t local = meta & 0xffffu, s = meta >> 16;
