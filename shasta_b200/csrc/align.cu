@@ -444,7 +444,7 @@ void runBandedJobs(AlignWorker& w, uint32_t nJobs, const uint32_t* sequences, Dp
     std::vector<uint64_t> classCounts;
     buildClassOrder(w, b.jobs.get(), nJobs, classCounts);
     BandedArgs g;
-    g.kmerIds = sequences; g.scores = scores;
+    g.kmerIds = sequences; g.scores = scores; g.fma = FmaUnits{1, 2, 4};
     SHB_CUDA(cudaEventRecord(w.dp2a, st));
     // Per chunk: DP (warp per job) on its stream, then traceback (thread per job) and equal-k-mer filter (warp per job)
     // on a high-priority stream.
@@ -569,7 +569,7 @@ void processBatch(AlignCall& call, AlignWorker& w, uint64_t begin, uint32_t nb, 
             Method3Args g1;
             g1.candidates = b.cand.get(); g1.candidateBegin = begin; g1.n = nb;
             g1.toc = c->toc.get(); g1.dsToc = ac.dsToc.get(); g1.dsKmer = ac.dsKmer.get(); g1.dsOrdinal = ac.dsOrdinal.get();
-            g1.scores = call.scores; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
+            g1.scores = call.scores; g1.fma = FmaUnits{1, 2, 4}; g1.bandExtend = o.bandExtend; g1.maxBand = o.maxBand;
             std::vector<uint64_t> classCounts1;
             buildClassOrder(w, b.jobs1.get(), nb, classCounts1, kForwardClassCount);
             SHB_CUDA(cudaEventRecord(w.dp1a, st));

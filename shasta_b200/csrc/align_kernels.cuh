@@ -278,24 +278,60 @@ template<int C> __device__ __forceinline__ void initSubChunkLimits(SubChunkLimit
 // bounded drift), below the matrix their values are never read by an in-matrix cell, and their trace codes are never
 // visited by the traceback. bw[] = b[j-1] for the C offsets (sentinel outside the row).
 // Boundary = false leaves out the test for the boundary cell (i == 0 or j == 0): for columns past max(0, hi).
+// The wavefront kernels are bound by the integer-ALU pipe (compares, selects, min/max); the FMA pipe idles. The adds of
+// the recurrence and the trace bookkeeping are therefore written as integer multiply-adds with run-time multipliers
+// (a kernel argument the compiler cannot fold): IMAD issues on the FMA pipe. FmaUnits = {1, 2, 4}.
+struct FmaUnits { int32_t one, two, four; };
+__device__ __forceinline__ int32_t fmaPipeAdd(int32_t a, int32_t b, int32_t one)
+{
+    int32_t r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t fmaPipeMul(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// acc += v if x == y (compare on the ALU pipe, the predicated add on the FMA pipe)
+__device__ __forceinline__ void fmaPipeAddIfEqual(int32_t& acc, uint32_t x, uint32_t y, int32_t v, int32_t one)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %1, %2;\n\t@q mad.lo.s32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "r"(x), "r"(y), "r"(v), "r"(one));
+}
+// acc += a * b if x > y (x >= y when OrEqual), signed
+template<bool OrEqual> __device__ __forceinline__ void fmaPipeAddIfGreater(uint32_t& acc, int32_t x, int32_t y, int32_t a, int32_t b)
+{
+    if(OrEqual) asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %1, %2;\n\t@q mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "r"(x), "r"(y), "r"(a), "r"(b));
+    else asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %1, %2;\n\t@q mad.lo.u32 %0, %3, %4, %0;\n\t}" : "+r"(acc) : "r"(x), "r"(y), "r"(a), "r"(b));
+}
+
+// Trace words of the wavefront kernels: a shift register of 2-bit codes, newest step in the low bits:
+//   bit 0 = the cell took a gap move (its score is gapIn + gap, not the diagonal's), bit 1 = the horizontal input was the
+//   larger gap input (meaningful when bit 0 is set). After the 16 steps of a block, step s of the block sits at bits
+//   2 * (15 - s). (The scan kernel keeps the older code format: 0 none, 1 diagonal, 2 vertical, 3 horizontal.)
 template<int C, bool Boundary> __device__ __forceinline__ void systolicSubChunk(
     int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t i, uint32_t ai,
-    int32_t below /* H(i, p0-1) */, int32_t top /* H(i-1, p0+C) */, const uint32_t* bw, DpScores sc)
+    int32_t below /* H(i, p0-1) */, int32_t top /* H(i-1, p0+C) */, const uint32_t* bw, DpScores sc, FmaUnits u)
 {
     int32_t vertIn = below;
+    const int32_t matchBonus = sc.match - sc.mismatch;
 #pragma unroll
     for(int c = 0; c < C; c++) {
-        const int32_t diag = H[c] + ((ai == bw[c]) ? sc.match : sc.mismatch);   // from H(i-1, p)
+        int32_t diag = fmaPipeAdd(H[c], sc.mismatch, u.one);                    // from H(i-1, p)
+        fmaPipeAddIfEqual(diag, ai, bw[c], matchBonus, u.one);
         const int32_t horzIn = (c + 1 < C) ? H[c + 1] : top;                    // H(i-1, p+1); vertIn = H(i, p-1)
-        // max(diag, vert, horz) as one max and one add-max; the tie order (include/shb_dp_policy.h) only enters the code.
+        // max(diag, vert, horz) as one max and one add-max; the tie order (include/shb_dp_policy.h) only enters the trace.
         const int32_t gapIn = max(vertIn, horzIn);
         int32_t h = __viaddmax_s32(gapIn, lim.gap[c], diag);
-        const bool viaGap = SHB_DP_DIAG_WINS_TIES ? (h > diag) : (gapIn + lim.gap[c] >= diag);
-        const uint32_t code = viaGap ? (dpHorzWins(horzIn, vertIn) ? 3u : 2u) : 1u;
+        uint32_t tr = fmaPipeMul(Tr[c], uint32_t(u.four));                      // shift the older codes up by two bits
+        if(SHB_DP_DIAG_WINS_TIES) fmaPipeAddIfGreater<false>(tr, h, diag, u.one, u.one);
+        else fmaPipeAddIfGreater<true>(tr, fmaPipeAdd(gapIn, lim.gap[c], u.one), diag, u.one, u.one);
+        fmaPipeAddIfGreater<!SHB_DP_VERT_BEFORE_HORZ>(tr, horzIn, vertIn, u.one, u.two);
+        Tr[c] = tr;
         if(Boundary) h = (i == lim.first[c]) ? 0 : h;
         H[c] = h;
         vertIn = h;
-        Tr[c] = (Tr[c] >> 2) | (code << 30);        // always holds the codes of the last 16 steps
     }
 }
 
@@ -335,7 +371,7 @@ template<int C> struct SystolicState {
 // 16 steps. Checked = false: no boundary cell and no end cell can occur in these steps for any lane, and every k-mer
 // the lanes load lies inside its row (see the block ranges in bandedOverlapDpSystolic), so the loads are unconditional.
 template<int C, bool Checked> __device__ __forceinline__ void systolicBlock(
-    SystolicState<C>& s, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc)
+    SystolicState<C>& s, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc, FmaUnits fu)
 {
     constexpr int kUnroll = (C == 1) ? 16 : (C == 2) ? 8 : (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
 #pragma unroll kUnroll
@@ -352,11 +388,11 @@ template<int C, bool Checked> __device__ __forceinline__ void systolicBlock(
         // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i
         // (lane 0: its own value comes back, which only the barrier offset p = 0 reads).
         const int32_t below = __shfl_up_sync(0xffffffffu, s.HB[C - 1], 1);
-        systolicSubChunk<C, Checked>(s.HA, s.TA, s.limA, s.i, ai, below, s.HB[0], s.bw, sc);
+        systolicSubChunk<C, Checked>(s.HA, s.TA, s.limA, s.i, ai, below, s.HB[0], s.bw, sc, fu);
         // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1
         // (lane 31: its own value comes back, read only by barrier / padding offsets).
         const int32_t top = __shfl_down_sync(0xffffffffu, s.HA[0], 1);
-        systolicSubChunk<C, Checked>(s.HB, s.TB, s.limB, s.i, ai, s.HA[C - 1], top, s.bw + C, sc);
+        systolicSubChunk<C, Checked>(s.HB, s.TB, s.limB, s.i, ai, s.HA[C - 1], top, s.bw + C, sc, fu);
         if(Checked) {
             // End-cell bookkeeping for both sub-chunks: offsets eA + cStar (row ny) and, in column nx, all rows.
             const int32_t cStar = rowEndA - s.i;
@@ -375,7 +411,7 @@ template<int C, bool Checked> __device__ __forceinline__ void systolicBlock(
 
 template<int C> __device__ inline void bandedOverlapDpSystolic(
     const uint32_t* __restrict__ a, uint32_t nxU, const uint32_t* __restrict__ b, uint32_t nyU, int32_t lo, int32_t hi, DpScores sc,
-    uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
+    FmaUnits fu, uint32_t* __restrict__ trace, int32_t& bestScore, int32_t& bestI, int32_t& bestJ)
 {
     const int32_t lane = int32_t(threadIdx.x & 31u);
     const int32_t nx = int32_t(nxU), ny = int32_t(nyU);
@@ -419,8 +455,8 @@ template<int C> __device__ inline void bandedOverlapDpSystolic(
     const int32_t tailBlock = max(0, firstEndStep) >> 4;
     uint32_t* row = trace;
     for(int32_t blk = 0; blk < blocks; blk++, row += WpadJob) {
-        if(blk < headBlocks || blk >= tailBlock) systolicBlock<C, true>(s, eA, eB, rowEndA, nx, ny, sc);
-        else systolicBlock<C, false>(s, eA, eB, rowEndA, nx, ny, sc);
+        if(blk < headBlocks || blk >= tailBlock) systolicBlock<C, true>(s, eA, eB, rowEndA, nx, ny, sc, fu);
+        else systolicBlock<C, false>(s, eA, eB, rowEndA, nx, ny, sc, fu);
         // Warp-uniform, coalesced trace store of the block's 16 steps.
 #pragma unroll
         for(int c = 0; c < C; c++) {
@@ -469,7 +505,7 @@ __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, 
         const uint32_t sh = 2u * (skew & 15u);
         if(sh == 0) return w0;
         const uint32_t w1 = trace[(row + 1) * uint32_t(Wpad) + p];
-        return __funnelshift_r(w0, w1, sh);
+        return __funnelshift_l(w1, w0, sh);            // newest step in the low bits: column c of the block at bits 2 * (15 - c)
     };
     int32_t block = (i - iFirst) >> 4;
     int32_t eb = (j - i + hi) - 16;
@@ -489,18 +525,27 @@ __device__ inline uint32_t tracebackCollect(const uint32_t* __restrict__ trace, 
             cur = loadWindow(block, eb);
         }
         const uint32_t word = __shfl_sync(0xffffffffu, cur, e - eb);
-        // Diagonal steps stay on the same offset, so a run of them is a run of "01" codes going down this word:
+        // Diagonal steps stay on the same offset, so a run of them is a run of equal codes going down this word:
         // take the whole run at once (one lane per step writes it) instead of one step per iteration.
         const int32_t q = (i - iFirst) & 15;
-        const uint32_t x = word ^ 0x55555555u;
-        const uint32_t notDiag = (x | (x >> 1)) & 0x55555555u & ((2u << (2 * q)) - 1u);       // bit 2p: column p of the block, p <= q
-        int32_t run = notDiag ? q - ((31 - __clz(notDiag)) >> 1) : q + 1;
+        int32_t run;
+        uint32_t code;              // 2 = vertical, 3 = horizontal, anything else with run == 0 = stop
+        if(pairWidth == 0) {        // scan kernel: codes 0 none, 1 diagonal, 2 vertical, 3 horizontal; column p of the block at bits 2p
+            const uint32_t x = word ^ 0x55555555u;
+            const uint32_t notDiag = (x | (x >> 1)) & 0x55555555u & ((2u << (2 * q)) - 1u);       // bit 2p: column p of the block, p <= q
+            run = notDiag ? q - ((31 - __clz(notDiag)) >> 1) : q + 1;
+            code = (word >> (2 * q)) & 3u;
+        } else {                    // wavefront kernels: bit 0 gap move, bit 1 horizontal; column c of the block at bits 2 * (15 - c)
+            const uint32_t w = word >> (2 * (15 - q));
+            const uint32_t gaps = w & 0x55555555u & (q == 15 ? 0xffffffffu : ((1u << (2 * (q + 1))) - 1u));
+            run = gaps ? ((__ffs(int(gaps)) - 1) >> 1) : q + 1;
+            code = (w & 1u) ? ((w & 2u) ? 3u : 2u) : 1u;
+        }
         run = min(run, min(i, j));
         if(run > 0) {
             if(lane < run) steps[n + uint32_t(lane)] = make_uint2(uint32_t(i - 1 - lane), uint32_t(j - 1 - lane));
             n += uint32_t(run); i -= run; j -= run;
         } else {
-            const uint32_t code = (word >> (2 * q)) & 3u;
             if(code == 2u) j--;
             else if(code == 3u) i--;
             else break;
@@ -520,6 +565,7 @@ struct Method3Args {
     const uint64_t* toc;            // global rows (all reads)
     const uint64_t* dsToc; const uint32_t* dsKmer; const uint32_t* dsOrdinal;
     DpScores scores;
+    FmaUnits fma;                   // {1, 2, 4}: run-time multipliers of the FMA-pipe adds
     int32_t bandExtend, maxBand;
     uint32_t wMax;                  // widest padded band of this launch's class (sizes the scan kernel's shared memory)
 };
@@ -539,7 +585,7 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
     const uint32_t* b = g.dsKmer + job.bOffset;
     int32_t bestScore, bestI, bestJ;
     if constexpr(C > 0) {
-        bandedOverlapDpSystolic<C>(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, trace + job.traceOffset, bestScore, bestI, bestJ);
+        bandedOverlapDpSystolic<C>(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, g.fma, trace + job.traceOffset, bestScore, bestI, bestJ);
         (void)warp;
     } else {
         const uint32_t stride = g.wMax + 1;
@@ -726,6 +772,7 @@ struct BandedArgs {
     const uint32_t* order;          // job indices of this launch's band class, longest first; n = how many
     const uint32_t* kmerIds;
     DpScores scores;
+    FmaUnits fma;                   // {1, 2, 4}: run-time multipliers of the FMA-pipe adds
     uint32_t wMax;                  // widest padded band of this launch's class (sizes the scan kernel's shared memory)
 };
 
@@ -746,7 +793,7 @@ bandedAlignKernel(BandedArgs g, const DpJob* __restrict__ jobs, uint32_t* __rest
     const uint32_t* b = g.kmerIds + job.bOffset;
     int32_t bestScore, bestI, bestJ;
     if constexpr(C > 0) {
-        bandedOverlapDpSystolic<C>(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, trace + job.traceOffset, bestScore, bestI, bestJ);
+        bandedOverlapDpSystolic<C>(a, job.nx, b, job.ny, job.lo, job.hi, g.scores, g.fma, trace + job.traceOffset, bestScore, bestI, bestJ);
         (void)warp;
     } else {
         const uint32_t stride = g.wMax + 1;
@@ -795,13 +842,22 @@ tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __r
             const uint32_t e = uint32_t(j - i + hi) + shift;
             const uint32_t t = uint32_t(i - iFirst) + ((e * reciprocal) >> 16);
             const uint32_t word = tr[uint64_t(t >> 4) * Wpad + e];
-            // Diagonal steps stay on the same offset: a run of them is a run of "01" codes going down this word.
+            // Diagonal steps stay on the same offset: a run of them is a run of equal codes going down this word.
             const uint32_t q = t & 15u;
-            const uint32_t x = word ^ 0x55555555u;
-            const uint32_t notDiag = (x | (x >> 1)) & 0x55555555u & ((2u << (2u * q)) - 1u);      // bit 2s: step s of the word, s <= q
-            int32_t run = notDiag ? int32_t(q) - ((31 - __clz(notDiag)) >> 1) : int32_t(q) + 1;
+            int32_t run;
+            uint32_t code;
+            if(C == 0) {            // scan kernel: codes 0 none, 1 diagonal, 2 vertical, 3 horizontal; step s at bits 2s
+                const uint32_t x = word ^ 0x55555555u;
+                const uint32_t notDiag = (x | (x >> 1)) & 0x55555555u & ((2u << (2u * q)) - 1u);      // bit 2s: step s of the word, s <= q
+                run = notDiag ? int32_t(q) - ((31 - __clz(notDiag)) >> 1) : int32_t(q) + 1;
+                code = (word >> (2u * q)) & 3u;
+            } else {                // wavefront kernels: bit 0 gap move, bit 1 horizontal; step s at bits 2 * (15 - s)
+                const uint32_t w = word >> (2u * (15u - q));
+                const uint32_t gaps = w & 0x55555555u & (q == 15u ? 0xffffffffu : ((1u << (2u * (q + 1u))) - 1u));
+                run = gaps ? ((__ffs(int(gaps)) - 1) >> 1) : int32_t(q) + 1;
+                code = (w & 1u) ? ((w & 2u) ? 3u : 2u) : 1u;
+            }
             run = min(run, min(i, j));
-            const uint32_t code = (word >> (2u * q)) & 3u;
             if(run > 0) {
                 out[count++] = make_uint2(uint32_t(i - 1) | (uint32_t(run - 1) << kRunLengthShift), uint32_t(j - 1));
                 i -= run; j -= run;
