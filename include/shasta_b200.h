@@ -72,6 +72,33 @@ shb_status shb_set_markers_device(shb_context* ctx,
                                   const uint8_t* readFlagsHost, uint64_t totalMarkerCount);
 
 /* ------------------------------------------------------------------------------------------
+ * Marker finding (the producer of the path's input). Replaces Assembler::findMarkers ->
+ * MarkerFinder (src/MarkerFinder.cpp:16-127, src/AssemblerMarkers.cpp): the reads go to the device as the reference
+ * stores them (2 bits per base) and the markers of both strands are produced there, so the 7-byte records need not cross
+ * PCIe at all when only the hot path follows.
+ *   readWordOffsets : uint64[readCount+1], offsets in 64-bit words into readWords (the toc of Data/Reads)
+ *   readWords       : LongBaseSequences payload (src/LongBaseSequence.hpp:33-41): per read, per 64 bases, the low bit plane
+ *                     word then the high bit plane word, base 0 in the most significant bit; run-length encoded bases when the
+ *                     assembly uses the RLE read representation
+ *   baseCounts      : uint64[readCount]
+ *   kmerTable       : 4^k KmerInfo records of 24 bytes (Data/Kmers, src/Kmer.hpp:23-38; only isMarker, byte 12, is read), or
+ *                     NULL when isMarkerBitmap (4^k bits, bit i of word i/32 = k-mer i is a marker) is given instead
+ *   readFlags       : 1 byte per read (Data/ReadFlags), kept for the LowHash step
+ *   markerToc       : optional, receives uint64[2*readCount+1] (Data/Markers.toc payload); markerData7: optional, receives the
+ *                     7-byte CompressedMarker records (Data/Markers.data payload). Free both with shb_free.
+ * Afterwards the context holds the markers of all reads exactly as after shb_set_markers (k-mer id SoA resident in HBM).
+ */
+typedef struct {
+    uint64_t readCount, baseCount, markerCount;     /* markerCount counts both strands */
+    double   totalMs;                               /* device time incl. the host->device copies of the inputs */
+    uint64_t kernelLaunches, h2dBytes;
+} shb_marker_result;
+shb_status shb_find_markers(shb_context* ctx, uint32_t k, uint64_t readCount, const uint64_t* readWordOffsets,
+                            const uint64_t* readWords, const uint64_t* baseCounts, const uint8_t* kmerTable,
+                            const uint32_t* isMarkerBitmap, const uint8_t* readFlags,
+                            uint64_t** markerToc, uint8_t** markerData7, shb_marker_result* result);
+
+/* ------------------------------------------------------------------------------------------
  * LowHash0.  Replaces Assembler::findAlignmentCandidatesLowHash0 (src/AssemblerLowHash.cpp:10-55,
  * declaration src/Assembler.hpp:688-699; Python binding src/PythonModule.cpp:218-228).
  * Field for field the reference's arguments; threadCount is accepted and ignored.

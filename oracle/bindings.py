@@ -177,6 +177,51 @@ def ref_markers_from_fasta(path, k=10, probability=0.1, seed=231, min_read_lengt
     return out
 
 
+def ref_reads_from_fasta(path, k=10, probability=0.1, seed=231, min_read_length=10000, threads=4):
+    """The inputs of the reference's MarkerFinder as the reference stores them: dict(word_offsets uint64[R+1], words uint64[],
+    base_counts uint64[R], is_marker uint8[4^k]) — RLE reads in LongBaseSequences layout + kmerTable[].isMarker."""
+    lib = ref_lib()
+    lib.ref_reads_from_fasta.restype = C.c_int
+    lib.ref_reads_from_fasta.argtypes = [C.c_char_p, C.c_uint64, C.c_double, C.c_int, C.c_uint64, C.c_uint64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    R = C.c_uint64()
+    off, words, bc, im = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    rc = lib.ref_reads_from_fasta(path.encode(), k, probability, seed, min_read_length, threads,
+                                  C.byref(R), C.byref(off), C.byref(words), C.byref(bc), C.byref(im))
+    if rc != 0:
+        raise RuntimeError("reference read loading failed")
+    R = R.value
+    offn = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_uint64)), (R + 1,)).copy()
+    n = int(offn[-1])
+    out = dict(word_offsets=offn,
+               words=np.ctypeslib.as_array(C.cast(words, C.POINTER(C.c_uint64)), (n,)).copy() if n else np.zeros(0, np.uint64),
+               base_counts=np.ctypeslib.as_array(C.cast(bc, C.POINTER(C.c_uint64)), (R,)).copy() if R else np.zeros(0, np.uint64),
+               is_marker=np.ctypeslib.as_array(C.cast(im, C.POINTER(C.c_uint8)), (1 << (2 * k),)).copy(), k=k)
+    for ptr in (off, words, bc, im):
+        lib.ref_free(ptr)
+    return out
+
+
+def oracle_find_markers(word_offsets, words, base_counts, is_marker, k):
+    """CPU restatement of MarkerFinder (oracle/markers_oracle.c). Returns (toc uint64[2R+1], data uint8[7M])."""
+    lib = oracle_lib()
+    lib.orc_find_markers.restype = C.c_int
+    lib.orc_find_markers.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    wo = np.ascontiguousarray(word_offsets, np.uint64)
+    w = np.ascontiguousarray(words, np.uint64)
+    bc = np.ascontiguousarray(base_counts, np.uint64)
+    im = np.ascontiguousarray(is_marker, np.uint8)
+    R = len(bc)
+    toc, data = C.c_void_p(), C.c_void_p()
+    lib.orc_find_markers(R, k, wo.ctypes.data, w.ctypes.data, bc.ctypes.data, im.ctypes.data, C.byref(toc), C.byref(data))
+    tocn = np.ctypeslib.as_array(C.cast(toc, C.POINTER(C.c_uint64)), (2 * R + 1,)).copy()
+    M = int(tocn[-1])
+    datan = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), (7 * M,)).copy() if M else np.zeros(0, np.uint8)
+    lib.orc_free(toc)
+    lib.orc_free(data)
+    return tocn, datan
+
+
 def candidate_digest(c):
     """FNV-1a style digest over (readId0, readId1, isSameStrand) rows."""
     h = 1469598103934665603

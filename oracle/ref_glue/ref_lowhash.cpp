@@ -156,6 +156,54 @@ int ref_markers_from_fasta(
 }
 
 
+// FASTA -> the INPUTS of the reference's MarkerFinder, as the reference itself stores them: the run-length encoded reads
+// in LongBaseSequences layout (src/LongBaseSequence.hpp:33-41: per read two uint64 words per 64 bases, low bit plane then
+// high bit plane, base 0 in the most significant bit), their base counts, and kmerTable[].isMarker (one byte per k-mer).
+// Used to generate the golden fixture of the device MarkerFinder (tests/golden/make_marker_golden.py).
+int ref_reads_from_fasta(
+    const char* fastaPath, uint64_t k, double markerProbability, int seed,
+    uint64_t minReadLength, uint64_t threadCount,
+    uint64_t* readCountOut, uint64_t** wordOffsetsOut /* R+1 */, uint64_t** wordsOut, uint64_t** baseCountsOut /* R */,
+    uint8_t** isMarkerOut /* 4^k */)
+{
+    try {
+        QuietCout quiet(true);
+        Reads reads;
+        reads.createNew(1, "", "", "", "", "", "", 4096);
+        {
+            ReadLoader loader(fastaPath, 1, minReadLength, false, threadCount, "", 4096, reads);
+        }
+        MemoryMapped::Vector<KmerInfo> kmerTable;
+        buildKmerTable(kmerTable, k, markerProbability, seed);
+        const uint64_t R = reads.readCount();
+        *readCountOut = R;
+        uint64_t* offsets = (uint64_t*)malloc(sizeof(uint64_t) * (R + 1));
+        uint64_t* baseCounts = (uint64_t*)malloc(sizeof(uint64_t) * (R ? R : 1));
+        uint64_t total = 0;
+        for(uint64_t r=0; r<R; r++) {
+            const LongBaseSequenceView v = reads.getRead(ReadId(r));
+            offsets[r] = total; baseCounts[r] = v.baseCount;
+            total += LongBaseSequenceView::wordCount(v.baseCount);
+        }
+        offsets[R] = total;
+        uint64_t* words = (uint64_t*)malloc(sizeof(uint64_t) * (total ? total : 1));
+        for(uint64_t r=0; r<R; r++) {
+            const LongBaseSequenceView v = reads.getRead(ReadId(r));
+            memcpy(words + offsets[r], v.begin, sizeof(uint64_t) * (offsets[r+1] - offsets[r]));
+        }
+        const uint64_t n = 1ULL << (2*k);
+        uint8_t* isMarker = (uint8_t*)malloc(n);
+        for(uint64_t i=0; i<n; i++) isMarker[i] = kmerTable[i].isMarker ? 1 : 0;
+        *wordOffsetsOut = offsets; *wordsOut = words; *baseCountsOut = baseCounts; *isMarkerOut = isMarker;
+        kmerTable.remove();
+        return 0;
+    } catch(const std::exception& e) {
+        fprintf(stderr, "ref_reads_from_fasta: %s\n", e.what());
+        return 1;
+    }
+}
+
+
 // Run the reference LowHash0 on raw marker arrays.
 //   toc: uint64[2R+1]; data: 7-byte CompressedMarker records; flags: 1 byte per read.
 // Outputs: candidates as 12-byte OrientedReadPair records written as 3 x uint32

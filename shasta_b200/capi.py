@@ -58,6 +58,11 @@ class AlignResult(C.Structure):
                 ("compressedDigest", C.c_uint64)]
 
 
+class MarkerResult(C.Structure):
+    _fields_ = [("readCount", C.c_uint64), ("baseCount", C.c_uint64), ("markerCount", C.c_uint64), ("totalMs", C.c_double),
+                ("kernelLaunches", C.c_uint64), ("h2dBytes", C.c_uint64)]
+
+
 class DistTiming(C.Structure):
     _fields_ = [("sweepSeconds", C.c_double), ("partitionSeconds", C.c_double), ("exchangeSeconds", C.c_double),
                 ("processSeconds", C.c_double), ("finalSeconds", C.c_double), ("gatherSeconds", C.c_double),
@@ -108,6 +113,8 @@ def lib():
                                              C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                              C.POINTER(AlignResult)]
         L.shb_compute_alignment_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_find_markers.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(MarkerResult)]
         L.shb_dist_unique_id.argtypes = [C.c_void_p]
         L.shb_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.shb_dist_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -176,6 +183,30 @@ class Context:
         if self._h:
             lib().shb_context_destroy(self._h)
             self._h = C.c_void_p()
+
+    def find_markers(self, k, word_offsets, words, base_counts, flags, kmer_table=None, is_marker_bitmap=None, want_host=True):
+        """Assembler::findMarkers on the device (shb_find_markers). Reads in LongBaseSequences layout. Returns
+        (toc uint64[2R+1], data7 uint8[7M]) when want_host, and the MarkerResult; the context then holds the markers."""
+        word_offsets = np.ascontiguousarray(word_offsets, np.uint64)
+        words = np.ascontiguousarray(words, np.uint64)
+        base_counts = np.ascontiguousarray(base_counts, np.uint64)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        R = len(base_counts)
+        kt = None if kmer_table is None else np.ascontiguousarray(kmer_table, np.uint8)
+        bm = None if is_marker_bitmap is None else np.ascontiguousarray(is_marker_bitmap, np.uint32)
+        toc, data = C.c_void_p(), C.c_void_p()
+        res = MarkerResult()
+        _check(lib().shb_find_markers(self._h, int(k), R, _ptr(word_offsets), _ptr(words), _ptr(base_counts), _ptr(kt), _ptr(bm),
+                                      _ptr(flags), C.byref(toc) if want_host else None, C.byref(data) if want_host else None, C.byref(res)))
+        self.read_count = R
+        if not want_host:
+            return None, None, res
+        tocn = np.ctypeslib.as_array(C.cast(toc, C.POINTER(C.c_uint64)), (2 * R + 1,)).copy()
+        M = int(tocn[-1])
+        datan = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), (7 * M,)).copy() if M else np.zeros(0, np.uint8)
+        lib().shb_free(toc)
+        lib().shb_free(data)
+        return tocn, datan, res
 
     # ---- multi-GPU (one process per GPU; NCCL inside the library) -------------------------------------------------
     def dist_init(self, world, rank, unique_id: bytes):

@@ -32,6 +32,9 @@ void lowhashEmit(shb_context* c, void** candidatesOut, uint64_t* candidateCountO
 void devicePartition(shb_context* c, uint64_t* keys, uint32_t* vals, uint64_t n, uint32_t shift, uint32_t bits,
                      uint64_t* counts, uint64_t** keysOut, uint32_t** valsOut);
 void computeAlignmentTable(shb_context* c, const void* alignmentData, uint64_t n, uint64_t readCount, uint32_t** tocOut, uint32_t** dataOut);
+void findMarkers(shb_context* c, uint32_t k, uint64_t readCount, const uint64_t* wordOffsets, const uint64_t* words,
+                 const uint64_t* baseCounts, const uint8_t* kmerTable24, const uint32_t* isMarkerBitmap,
+                 const uint8_t* readFlags, uint64_t** tocOut, uint8_t** data7Out, shb_marker_result* result);
 void computeCandidateTable(shb_context* c, const void* candidates, uint64_t n, uint64_t readCount, uint64_t** tocOut, uint64_t** dataOut);
 
 template<class F> shb_status guarded(F&& f)
@@ -369,6 +372,17 @@ shb_status shb_compute_alignment_table(shb_context* c, const void* alignmentData
     return guarded([&] {
         SHB_REQUIRE(c && tableToc && tableData && (alignmentData || alignmentCount == 0), SHB_ERR_INVALID, "Null argument.");
         computeAlignmentTable(c, alignmentData, alignmentCount, readCount, tableToc, tableData);
+    });
+}
+
+shb_status shb_find_markers(shb_context* c, uint32_t k, uint64_t readCount, const uint64_t* readWordOffsets,
+                            const uint64_t* readWords, const uint64_t* baseCounts, const uint8_t* kmerTable,
+                            const uint32_t* isMarkerBitmap, const uint8_t* readFlags,
+                            uint64_t** markerToc, uint8_t** markerData7, shb_marker_result* result)
+{
+    return guarded([&] {
+        SHB_REQUIRE(c != nullptr, SHB_ERR_INVALID, "Null context.");
+        findMarkers(c, k, readCount, readWordOffsets, readWords, baseCounts, kmerTable, isMarkerBitmap, readFlags, markerToc, markerData7, result);
     });
 }
 

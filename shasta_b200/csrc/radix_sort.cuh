@@ -154,13 +154,25 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
         for(unsigned w = 0; w < warp; w++) offset += scanTotals[w];
         localOffset[threadIdx.x] = offset + inc - count;
     }
+    // Look-back, a window of kLookback earlier tiles per round trip: when a wave of tiles reaches this point at about the
+    // same time, tile j of the wave has to walk back over about j/2 tiles that have only published their counts; reading
+    // one tile per dependent load would make that hundreds of serial L2 round trips per tile.
+    constexpr int kLookback = 16;
     unsigned long long earlier = 0;
     for(int64_t t = int64_t(tile) - 1; t >= 0; ) {
-        const unsigned long long s = status[uint64_t(t) * kRadix + threadIdx.x];
-        const unsigned long long tag = s & ~kStatusValueMask;
-        if(tag == tagPrefix) { earlier += s & kStatusValueMask; break; }
-        if(tag == tagCount) { earlier += s & kStatusValueMask; t--; }
-        // otherwise: that tile has not published yet (it is running: tiles start in ticket order) -> read again
+        unsigned long long window[kLookback];
+#pragma unroll
+        for(int k = 0; k < kLookback; k++) window[k] = (t - k >= 0) ? status[uint64_t(t - k) * kRadix + threadIdx.x] : tagPrefix;
+        bool done = false;
+#pragma unroll
+        for(int k = 0; k < kLookback; k++) {
+            if(done) continue;
+            const unsigned long long sw = window[k];
+            const unsigned long long tag = sw & ~kStatusValueMask;
+            if(tag == tagPrefix) { earlier += sw & kStatusValueMask; t = -1; done = true; }         // (also the virtual tile -1: value 0)
+            else if(tag == tagCount) { earlier += sw & kStatusValueMask; t--; }
+            else done = true;       // that tile has not published yet (it is running: tiles start in ticket order): read again from it
+        }
     }
     __threadfence();
     *myStatus = tagPrefix | (earlier + count);
@@ -241,6 +253,7 @@ bool radixSort(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* vals
     static bool attributeSet = false;           // per template instantiation (and per process: one device per process)
     if(!attributeSet) {
         SHB_CUDA(cudaFuncSetAttribute(radixOnesweepKernel<HAS_VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamicBytes));
+        SHB_CUDA(cudaFuncSetAttribute(radixOnesweepKernel<HAS_VALUES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attributeSet = true;
     }
     bool inB = false;
