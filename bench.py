@@ -376,6 +376,7 @@ def main():
                     stats_acc["sharded_" + k] = stats_acc.get("sharded_" + k, 0.0) + getattr(tm, k + "Seconds")
             sweep_ms, sweep_launches, launches = res.sweepMs, res.sweepLaunches, res.kernelLaunches
         last["candidate_digest"] = res.candidateDigest
+        last["low_hashes"], last["pair_hits"] = res.lowHashCount, res.pairCount
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         nal = 0
@@ -560,6 +561,8 @@ def main():
                    "align_included": not args.no_align},
         "candidates": total_cand, "alignments": total_al, "skipped_candidates": skipped_total, "too_wide_candidates": too_wide_total,
         "digests": digests, "parity_on_cpu_sample": parity,
+        "lowhash_work_per_step": {"low_hashes": last.get("low_hashes"), "pair_hits": last.get("pair_hits"),
+                                  "note": "low hashes kept / candidate pair hits generated over all iterations (this rank's share when sharded)"},
         "lowhash_pairs_per_s": total_cand * args.steps / lowhash_s,
         "aligned_pairs_per_s": (total_cand * args.steps / align_s) if align_s else None,
         "lowhash_ms_per_step": 1e3 * lowhash_s / args.steps, "align_ms_per_step": 1e3 * align_s / args.steps,

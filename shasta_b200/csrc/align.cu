@@ -56,6 +56,14 @@ uint32_t warpsForClass(const DpClass& k)
     return w ? w : 1;
 }
 size_t smemForClass(const DpClass& k, uint32_t warps) { return k.c > 0 ? 0 : size_t(warps) * 3 * (k.wMax + 1) * 4; }
+// The scan kernels' dynamic shared memory limit is a per-function attribute shared by all host workers: it is always
+// set to the largest class's need, never to the launch's own, so concurrent workers cannot lower it under each other.
+size_t scanKernelSmemLimit()
+{
+    size_t most = 0;
+    for(const DpClass& k : kClasses) most = std::max(most, smemForClass(k, warpsForClass(k)));
+    return most;
+}
 
 template<class... Args> void launchStage1(const DpClass& k, uint32_t blocks, uint32_t threads, size_t smem, cudaStream_t st, Args... args)
 {
@@ -69,7 +77,7 @@ template<class... Args> void launchStage1(const DpClass& k, uint32_t blocks, uin
     case 12: SHB_LAUNCH(method3Stage1Kernel<12>, blocks, threads, smem, st, args...); break;
     case 16: SHB_LAUNCH(method3Stage1Kernel<16>, blocks, threads, smem, st, args...); break;
     default:
-        SHB_CUDA(cudaFuncSetAttribute(method3Stage1Kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        SHB_CUDA(cudaFuncSetAttribute(method3Stage1Kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scanKernelSmemLimit())));
         SHB_LAUNCH(method3Stage1Kernel<0>, blocks, threads, smem, st, args...); break;
     }
 }
@@ -99,7 +107,7 @@ template<class... Args> void launchBanded(const DpClass& k, uint32_t blocks, uin
     case 12: SHB_LAUNCH(bandedAlignKernel<12>, blocks, threads, smem, st, args...); break;
     case 16: SHB_LAUNCH(bandedAlignKernel<16>, blocks, threads, smem, st, args...); break;
     default:
-        SHB_CUDA(cudaFuncSetAttribute(bandedAlignKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        SHB_CUDA(cudaFuncSetAttribute(bandedAlignKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scanKernelSmemLimit())));
         SHB_LAUNCH(bandedAlignKernel<0>, blocks, threads, smem, st, args...); break;
     }
 }
@@ -201,6 +209,9 @@ struct AlignCache {
     DeviceBuffer<uint32_t> outRecords;
     DeviceBuffer<unsigned long long> outToc;
     DeviceBuffer<uint8_t> outData;
+    cudaStream_t finalStream = nullptr;         // rebase / digest / early device->host copy of the finished batches
+    double lastBytesPerCandidate = 0.;          // compressed bytes per candidate of the previous call (sizes the early copy)
+    ~AlignCache() { if(finalStream) cudaStreamDestroy(finalStream); }
 };
 
 AlignCache& cache(shb_context* c)
@@ -493,6 +504,14 @@ struct AlignCall {
     std::mutex arenaMutex;
     std::map<uint64_t, Segment> ledger;     // by batch index (guarded by arenaMutex)
     uint64_t outCount = 0, outBytes = 0;
+    // Finalisation in candidate order, as soon as a prefix of the batches is complete: rebase, digests and (when the host
+    // result blocks are page-locked and large enough) the device->host copy run on their own stream beside the next batches.
+    cudaStream_t finalStream = nullptr;
+    unsigned long long* digests = nullptr;      // device, 2 words
+    uint64_t nextToFinalise = 0, finalRecords = 0, finalBytes = 0;
+    uint8_t* hostRecords = nullptr; uint8_t* hostToc = nullptr; uint8_t* hostData = nullptr;     // null: copy at the end
+    uint64_t hostDataCapacity = 0;
+    bool dataOverflow = false;                  // the estimate for the compressed bytes was too small: copy them at the end
     // failure of any worker stops the others
     std::atomic<bool> failed{false};
     std::exception_ptr error;
@@ -508,7 +527,7 @@ bool nextBatch(AlignCall& call, uint64_t& begin, uint32_t& nb, uint64_t& index)
     nb = 0;
     if(call.method4) {
         const std::vector<uint64_t>& toc = call.c->tocHost;
-        const uint64_t cellBudget = 192ull << 20;      // cells of grid scratch per batch
+        const uint64_t cellBudget = 768ull << 20;      // cells of grid scratch per batch (17 B each, per worker)
         uint64_t cells = 0;
         while(begin + nb < call.n && nb < call.batchMax) {
             const uint64_t i = begin + nb;
@@ -523,6 +542,45 @@ bool nextBatch(AlignCall& call, uint64_t& begin, uint32_t& nb, uint64_t& index)
     index = call.nextIndex++;
     call.nextBegin += nb;
     return true;
+}
+
+// toc[k] += delta for the n entries of one segment.
+__global__ void rebaseTocKernel(unsigned long long* __restrict__ toc, uint64_t n, long long delta)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if(i < n) toc[i] = (unsigned long long)((long long)toc[i] + delta);
+}
+
+// Called with arenaMutex held, after a batch's segment has been recorded (and its write kernel has finished): finalises
+// every segment whose predecessors are all complete. Everything is queued on call.finalStream.
+void finaliseReadySegments(AlignCall& call)
+{
+    AlignCache& ac = *call.ac;
+    cudaStream_t fs = call.finalStream;
+    for(;;) {
+        auto it = call.ledger.find(call.nextToFinalise);
+        if(it == call.ledger.end()) break;
+        const AlignCall::Segment& seg = it->second;
+        if(seg.kept) {
+            unsigned long long* segToc = ac.outToc.get() + seg.recordBase;
+            const long long delta = (long long)call.finalBytes - (long long)seg.byteBase;     // the write kernel stored arena offsets
+            if(delta) SHB_LAUNCH(rebaseTocKernel, ceilDiv(seg.kept, 256), 256, 0, fs, segToc, seg.kept, delta);
+            SHB_LAUNCH(digestRecordsKernel, ceilDiv(seg.kept, 256), 256, 0, fs, (const uint32_t*)ac.outRecords.get() + 16 * seg.recordBase,
+                       seg.kept, 16u, call.digests);
+            SHB_LAUNCH(digestCompressedKernel, ceilDiv(seg.kept, 256), 256, 0, fs, (const uint32_t*)ac.outRecords.get() + 16 * seg.recordBase,
+                       seg.kept, (const unsigned long long*)segToc, call.finalBytes + seg.bytes,
+                       (const uint8_t*)ac.outData.get() + seg.byteBase - call.finalBytes, call.digests + 1);
+            if(call.hostRecords) {
+                SHB_CUDA(cudaMemcpyAsync(call.hostRecords + 64 * call.finalRecords, ac.outRecords.get() + 16 * seg.recordBase, 64 * seg.kept, cudaMemcpyDeviceToHost, fs));
+                SHB_CUDA(cudaMemcpyAsync(call.hostToc + 8 * call.finalRecords, segToc, 8 * seg.kept, cudaMemcpyDeviceToHost, fs));
+                if(!call.dataOverflow && call.finalBytes + seg.bytes <= call.hostDataCapacity) {
+                    SHB_CUDA(cudaMemcpyAsync(call.hostData + call.finalBytes, ac.outData.get() + seg.byteBase, seg.bytes, cudaMemcpyDeviceToHost, fs));
+                } else call.dataOverflow = true;
+            }
+            call.finalRecords += seg.kept; call.finalBytes += seg.bytes;
+        }
+        call.nextToFinalise++;
+    }
 }
 
 // One batch of candidates on one worker, up to the point where its kept alignments sit in the arena.
@@ -681,6 +739,10 @@ void processBatch(AlignCall& call, AlignWorker& w, uint64_t begin, uint32_t nb, 
         AlignCall::Segment seg;
         seg.recordBase = call.outCount; seg.kept = kept; seg.byteBase = call.outBytes; seg.bytes = bytes;
         if(kept) {
+            if(16ull * (call.outCount + kept) > ac.outRecords.capacity() || call.outCount + kept + 1 > ac.outToc.capacity() ||
+               call.outBytes + bytes + 16 > ac.outData.capacity()) {
+                SHB_CUDA(cudaStreamSynchronize(call.finalStream));       // the arena moves: nothing may still be reading it
+            }
             ac.outRecords.reserve(16ull * (call.outCount + kept), true, st);
             ac.outToc.reserve(call.outCount + kept + 1, true, st);
             ac.outData.reserve(call.outBytes + bytes + 16, true, st);
@@ -695,6 +757,7 @@ void processBatch(AlignCall& call, AlignWorker& w, uint64_t begin, uint32_t nb, 
             call.outBytes += bytes;
         }
         call.ledger[batchIndex] = seg;
+        finaliseReadySegments(call);
     }
 }
 
@@ -714,13 +777,6 @@ void workerMain(AlignCall& call, AlignWorker& w)
         call.failed.store(true);
     }
     w.launches = g_launchCount;
-}
-
-// toc[k] += delta for the n entries of one segment.
-__global__ void rebaseTocKernel(unsigned long long* __restrict__ toc, uint64_t n, long long delta)
-{
-    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if(i < n) toc[i] = (unsigned long long)((long long)toc[i] + delta);
 }
 
 } // namespace
@@ -796,6 +852,23 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     const uint32_t workerCount = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(envCount("SHB_ALIGN_WORKERS", 2), batchEstimate)));
     while(ac.workers.size() < workerCount) ac.workers.emplace_back(new AlignWorker());
     for(uint32_t k = 0; k < workerCount; k++) ac.workers[k]->init();
+    if(!ac.finalStream) SHB_CUDA(cudaStreamCreateWithFlags(&ac.finalStream, cudaStreamNonBlocking));
+    call.finalStream = ac.finalStream;
+    call.digests = c->scalars.get() + 58;
+    SHB_CUDA(cudaMemsetAsync(call.digests, 0, 2 * sizeof(unsigned long long), st));
+    // Host result blocks up front when recycled, page-locked blocks are available (every call after the first of a steady
+    // caller): records and toc by their upper bound (every candidate kept), the compressed bytes by the previous call's bytes per
+    // candidate. The finished prefix of the batches is then copied out while the later batches run.
+    HostResult recOut, tocOut, dataOut;
+    if(n && ac.lastBytesPerCandidate > 0.) {
+        const uint64_t dataEstimate = uint64_t(ac.lastBytesPerCandidate * double(n) * 1.03) + (1ull << 20);
+        recOut.reset(allocHostResult(64 * n)); tocOut.reset(allocHostResult(8 * (n + 1))); dataOut.reset(allocHostResult(dataEstimate));
+        if(recOut.p && tocOut.p && dataOut.p && HostPool::instance().isPageLocked(recOut.p) && HostPool::instance().isPageLocked(tocOut.p) &&
+           HostPool::instance().isPageLocked(dataOut.p)) {
+            call.hostRecords = static_cast<uint8_t*>(recOut.p); call.hostToc = static_cast<uint8_t*>(tocOut.p);
+            call.hostData = static_cast<uint8_t*>(dataOut.p); call.hostDataCapacity = dataEstimate;
+        }
+    }
     SHB_CUDA(cudaStreamSynchronize(st));        // derived marker data ready before the workers read it
 
     if(n) {
@@ -806,35 +879,37 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
         if(call.error) std::rethrow_exception(call.error);
     }
 
-    // ---- results: segments back into candidate order, digests, copy to the host --------------------------------------
+    // ---- results: the segments were rebased, digested and (in the steady state) copied to the host in candidate order while
+    // the later batches were still running (finaliseReadySegments); what is left is whatever could not be copied early.
+    SHB_CUDA(cudaStreamSynchronize(call.finalStream));
     const uint64_t count = call.outCount, outBytes = call.outBytes;
     const auto copy0 = std::chrono::steady_clock::now();
-    HostResult recOut(allocHostResult(64 * count)), tocOut(allocHostResult(8 * (count + 1))), dataOut(allocHostResult(outBytes));
+    SHB_REQUIRE(call.nextToFinalise == call.ledger.size() && call.finalRecords == count && call.finalBytes == outBytes, SHB_ERR_CUDA,
+                "Internal error: not every batch was finalised.");
+    const bool earlyCopy = call.hostRecords != nullptr;
+    if(!earlyCopy) {        // first call (no page-locked result blocks yet): exact-size buffers, pipelined copy through pinned staging
+        recOut.reset(allocHostResult(64 * count)); tocOut.reset(allocHostResult(8 * (count + 1)));
+    }
+    if(!earlyCopy || call.dataOverflow) dataOut.reset(allocHostResult(outBytes));
     SHB_REQUIRE(recOut.p && tocOut.p && dataOut.p, SHB_ERR_OOM, "Out of host memory for the alignments.");
-    unsigned long long* digests = c->scalars.get() + 58;
-    SHB_CUDA(cudaMemsetAsync(digests, 0, 2 * sizeof(unsigned long long), st));
-    if(count) {
+    if(count && (!earlyCopy || call.dataOverflow)) {
         const bool lockedRec = HostPool::instance().isPageLocked(recOut.p), lockedToc = HostPool::instance().isPageLocked(tocOut.p),
                    lockedData = HostPool::instance().isPageLocked(dataOut.p);
         uint64_t finalRecords = 0, finalBytes = 0;
         for(const auto& entry : call.ledger) {
             const AlignCall::Segment& seg = entry.second;
             if(!seg.kept) continue;
-            unsigned long long* segToc = ac.outToc.get() + seg.recordBase;
-            const long long delta = (long long)finalBytes - (long long)seg.byteBase;     // the write kernel stored byteBase + offset
-            if(delta) SHB_LAUNCH(rebaseTocKernel, ceilDiv(seg.kept, 256), 256, 0, st, segToc, seg.kept, delta);
-            SHB_LAUNCH(digestRecordsKernel, ceilDiv(seg.kept, 256), 256, 0, st, (const uint32_t*)ac.outRecords.get() + 16 * seg.recordBase,
-                       seg.kept, 16u, digests);
-            SHB_LAUNCH(digestCompressedKernel, ceilDiv(seg.kept, 256), 256, 0, st, (const uint32_t*)ac.outRecords.get() + 16 * seg.recordBase,
-                       seg.kept, (const unsigned long long*)segToc, finalBytes + seg.bytes,
-                       (const uint8_t*)ac.outData.get() + seg.byteBase - finalBytes, digests + 1);
-            copyToHostPipelined(c, static_cast<uint8_t*>(recOut.p) + 64 * finalRecords, ac.outRecords.get() + 16 * seg.recordBase, 64 * seg.kept, lockedRec);
-            copyToHostPipelined(c, static_cast<uint8_t*>(tocOut.p) + 8 * finalRecords, segToc, 8 * seg.kept, lockedToc);
+            if(!earlyCopy) {
+                copyToHostPipelined(c, static_cast<uint8_t*>(recOut.p) + 64 * finalRecords, ac.outRecords.get() + 16 * seg.recordBase, 64 * seg.kept, lockedRec);
+                copyToHostPipelined(c, static_cast<uint8_t*>(tocOut.p) + 8 * finalRecords, ac.outToc.get() + seg.recordBase, 8 * seg.kept, lockedToc);
+            }
             copyToHostPipelined(c, static_cast<uint8_t*>(dataOut.p) + finalBytes, ac.outData.get() + seg.byteBase, seg.bytes, lockedData);
             finalRecords += seg.kept; finalBytes += seg.bytes;
         }
         SHB_CUDA(cudaStreamSynchronize(st));
     }
+    if(n) ac.lastBytesPerCandidate = double(outBytes) / double(n);
+    unsigned long long* digests = call.digests;
     // Counters of the workers.
     unsigned long long skipped = 0, forwardCells = 0, tooWide = 0, bandCells = 0, digestHost[2] = {0, 0};
     uint64_t traceWords = 0, launches = g_launchCount;

@@ -644,9 +644,25 @@ method3Stage1Kernel(Method3Args g, DpJob* __restrict__ jobs1, uint32_t* __restri
 // the same column, one step earlier. Rows beyond ny and columns outside 1..nx are dead: nothing live reads them.
 // Covers ny <= 32*R (R <= 16); longer downsampled reads take method3Stage1Kernel. Same recurrence, tie-break and
 // end-cell rules as bandedOverlapDp.
-constexpr int32_t kNoDiagonalStep = 0x7fffffff;         // offsetMin of a path without diagonal steps
-constexpr int32_t kNoMatchingStep = 0x7ffffffe;         // ... with diagonal steps, none of them on equal k-mers
+// The (smallest, largest) matching ordinal offset of a path travels as ONE packed value: low half = the smallest offset,
+// high half = MINUS the largest, both as signed 16-bit numbers, so that one packed minimum (VIMNMX.S16x2) updates both and
+// one select moves both. Offsets are differences of marker ordinals: the forward kernel therefore only takes pairs whose
+// reads have at most kStage1ForwardMaxMarkers markers (the others take the trace path, method3Stage1Kernel).
+constexpr uint32_t kPairNoDiagonalStep = 0x7fff7fffu;   // path without diagonal steps
+constexpr uint32_t kPairNoMatchingStep = 0x7fff7ffeu;   // ... with diagonal steps, none of them on equal k-mers
 constexpr uint32_t kStage1ForwardMaxRows = 512;
+constexpr uint32_t kStage1ForwardMaxMarkers = 32000;
+
+__device__ __forceinline__ uint32_t packedAdd16(uint32_t x, uint32_t y)
+{
+    uint32_t r;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y));
+    return r;
+}
+__device__ __forceinline__ uint32_t packOffsetPair(int32_t lowHalf, int32_t highHalf)
+{
+    return (uint32_t(lowHalf) & 0xffffu) | (uint32_t(highHalf) << 16);
+}
 
 template<int R> __global__ void __launch_bounds__(kDpMaxWarpsPerBlock * 32)
 method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob* __restrict__ jobs2)
@@ -662,73 +678,79 @@ method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob
     const int32_t nx = int32_t(job.nx), ny = int32_t(job.ny);
     const DpScores sc = g.scores;
 
-    // This lane's rows of b.
-    uint32_t bk[R]; int32_t bo[R];
-    int32_t H[R], Mn[R], Mx[R];                 // column i-1 (then i) of the own rows; column 0 is the boundary
+    // This lane's rows of b. boP = (-ordinal, +ordinal) so that (ordinal_a, -ordinal_a) + boP = (offset, -offset).
+    uint32_t bk[R], boP[R];
+    int32_t H[R];
+    uint32_t P[R];                              // column i-1 (then i) of the own rows; column 0 is the boundary
 #pragma unroll
     for(int r = 0; r < R; r++) {
         const int32_t j = R * lane + r + 1;
-        bk[r] = 0xffffffffu; bo[r] = 0;
-        if(j <= ny) { bk[r] = __ldg(g.dsKmer + job.bOffset + (j - 1)); bo[r] = int32_t(__ldg(g.dsOrdinal + job.bOffset + (j - 1))); }
-        H[r] = 0; Mn[r] = kNoDiagonalStep; Mx[r] = INT32_MIN;
+        bk[r] = 0xffffffffu; boP[r] = 0;
+        if(j <= ny) {
+            bk[r] = __ldg(g.dsKmer + job.bOffset + (j - 1));
+            const int32_t ob = int32_t(__ldg(g.dsOrdinal + job.bOffset + (j - 1)));
+            boP[r] = packOffsetPair(-ob, ob);
+        }
+        H[r] = 0; P[r] = kPairNoDiagonalStep;
     }
     const int32_t lastLane = (ny - 1) / R, rLast = (ny - 1) % R;        // where row ny lives
-    int32_t upH = 0, upMn = kNoDiagonalStep, upMx = INT32_MIN;          // row R*lane of the previous column
-    int32_t bestScore = 0, bestI = kEndCellNone, bestJ = kEndCellNone, bestMn = kNoDiagonalStep, bestMx = INT32_MIN;
+    int32_t upH = 0;                                                    // row R*lane of the previous column
+    uint32_t upP = kPairNoDiagonalStep;
+    int32_t bestScore = 0, bestI = kEndCellNone, bestJ = kEndCellNone;
+    uint32_t bestP = kPairNoDiagonalStep;
 
     const int32_t steps = nx + lastLane;                                // lanes beyond lastLane only hold dead rows
 #pragma unroll 2
     for(int32_t t = 0; t < steps; t++) {
         // Row R*lane of the current column: lane-1's last row, computed one step ago (row 0 for lane 0).
         int32_t inH = __shfl_up_sync(0xffffffffu, H[R - 1], 1);
-        int32_t inMn = __shfl_up_sync(0xffffffffu, Mn[R - 1], 1);
-        int32_t inMx = __shfl_up_sync(0xffffffffu, Mx[R - 1], 1);
-        if(lane == 0) { inH = 0; inMn = kNoDiagonalStep; inMx = INT32_MIN; }
+        uint32_t inP = __shfl_up_sync(0xffffffffu, P[R - 1], 1);
+        if(lane == 0) { inH = 0; inP = kPairNoDiagonalStep; }
         const int32_t i = t - lane + 1;
         if(uint32_t(i - 1) < uint32_t(nx)) {
             const uint32_t ai = __ldg(a + (i - 1));
             const int32_t ao = int32_t(__ldg(oa + (i - 1)));
-            int32_t dH = upH, dMn = upMn, dMx = upMx;                   // (i-1, j-1)
-            int32_t vH = inH, vMn = inMn, vMx = inMx;                   // (i, j-1)
+            const uint32_t aoP = packOffsetPair(ao, -ao);
+            int32_t dH = upH; uint32_t dP = upP;                        // (i-1, j-1)
+            int32_t vH = inH; uint32_t vP = inP;                        // (i, j-1)
 #pragma unroll
             for(int r = 0; r < R; r++) {
-                const int32_t hH = H[r], hMn = Mn[r], hMx = Mx[r];      // (i-1, j)
+                const int32_t hH = H[r]; const uint32_t hP = P[r];      // (i-1, j)
                 const bool eq = (ai == bk[r]);
                 const int32_t diag = dH + (eq ? sc.match : sc.mismatch);
                 const int32_t gapIn = max(vH, hH);
                 const int32_t h = __viaddmax_s32(gapIn, sc.gap, diag);  // tie order: include/shb_dp_policy.h
                 const bool viaGap = SHB_DP_DIAG_WINS_TIES ? (h > diag) : (gapIn + sc.gap >= diag), viaHorz = dpHorzWins(hH, vH);
-                const int32_t off = ao - bo[r];
-                const int32_t stepMn = min(dMn, eq ? off : kNoMatchingStep);
-                const int32_t stepMx = max(dMx, eq ? off : INT32_MIN);
-                const int32_t gapMn = viaHorz ? hMn : vMn, gapMx = viaHorz ? hMx : vMx;
-                const int32_t mn = viaGap ? gapMn : stepMn, mx = viaGap ? gapMx : stepMx;
-                dH = hH; dMn = hMn; dMx = hMx;
-                vH = h; vMn = mn; vMx = mx;
-                H[r] = h; Mn[r] = mn; Mx[r] = mx;
+                // a diagonal step: the pair of the diagonal predecessor, extended by this step's offset if the k-mers are equal
+                const uint32_t stepP = __vmins2(dP, eq ? packedAdd16(aoP, boP[r]) : kPairNoMatchingStep);
+                const uint32_t gapP = viaHorz ? hP : vP;
+                const uint32_t pr = viaGap ? gapP : stepP;
+                dH = hH; dP = hP;
+                vH = h; vP = pr;
+                H[r] = h; P[r] = pr;
             }
-            // End-cell candidates: row ny in every column, then every row of column nx (column-major order, first
-            // strict maximum; the boundary cells score 0 and come first, so only positive scores can win).
+            // End-cell candidates: row ny in every column, then every row of column nx (column-major order; the boundary
+            // cells score 0 and come first, so only positive scores can win under the first-maximum rule).
             if(lane == lastLane) {
-                int32_t h = 0, mn = 0, mx = 0;
+                int32_t h = 0; uint32_t pr = 0;
                 switch(rLast) {                  // warp-uniform; a jump instead of R selects per value
-#define SHB_PICK_ROW(k) case k: if constexpr(k < R) { h = H[k]; mn = Mn[k]; mx = Mx[k]; } break;
+#define SHB_PICK_ROW(k) case k: if constexpr(k < R) { h = H[k]; pr = P[k]; } break;
                 SHB_PICK_ROW(0) SHB_PICK_ROW(1) SHB_PICK_ROW(2) SHB_PICK_ROW(3) SHB_PICK_ROW(4) SHB_PICK_ROW(5) SHB_PICK_ROW(6) SHB_PICK_ROW(7)
                 SHB_PICK_ROW(8) SHB_PICK_ROW(9) SHB_PICK_ROW(10) SHB_PICK_ROW(11) SHB_PICK_ROW(12) SHB_PICK_ROW(13) SHB_PICK_ROW(14) SHB_PICK_ROW(15)
 #undef SHB_PICK_ROW
                 default: break;
                 }
-                if(SHB_DP_END_FIRST_MAX ? (h > bestScore) : (h >= bestScore)) { bestScore = h; bestI = i; bestJ = ny; bestMn = mn; bestMx = mx; }
+                if(SHB_DP_END_FIRST_MAX ? (h > bestScore) : (h >= bestScore)) { bestScore = h; bestI = i; bestJ = ny; bestP = pr; }
             }
             if(i == nx) {
 #pragma unroll
                 for(int r = 0; r < R; r++) {
                     const int32_t j = R * lane + r + 1;
-                    if(j <= ny && (SHB_DP_END_FIRST_MAX ? (H[r] > bestScore) : (H[r] >= bestScore))) { bestScore = H[r]; bestI = i; bestJ = j; bestMn = Mn[r]; bestMx = Mx[r]; }
+                    if(j <= ny && (SHB_DP_END_FIRST_MAX ? (H[r] > bestScore) : (H[r] >= bestScore))) { bestScore = H[r]; bestI = i; bestJ = j; bestP = P[r]; }
                 }
             }
         }
-        upH = inH; upMn = inMn; upMx = inMx;
+        upH = inH; upP = inP;
     }
     // Maximum score, then the visiting order of the end-cell rule.
 #pragma unroll
@@ -736,17 +758,19 @@ method3Stage1ForwardKernel(Method3Args g, const DpJob* __restrict__ jobs1, DpJob
         const int32_t s2 = __shfl_xor_sync(0xffffffffu, bestScore, d);
         const int32_t i2 = __shfl_xor_sync(0xffffffffu, bestI, d);
         const int32_t j2 = __shfl_xor_sync(0xffffffffu, bestJ, d);
-        const int32_t mn2 = __shfl_xor_sync(0xffffffffu, bestMn, d);
-        const int32_t mx2 = __shfl_xor_sync(0xffffffffu, bestMx, d);
+        const uint32_t p2 = __shfl_xor_sync(0xffffffffu, bestP, d);
         if(dpEndCellBetter(s2, i2, j2, bestScore, bestI, bestJ)) {
-            bestScore = s2; bestI = i2; bestJ = j2; bestMn = mn2; bestMx = mx2;
+            bestScore = s2; bestI = i2; bestJ = j2; bestP = p2;
         }
     }
     if(lane == 0) {
         DpJob j2 = jobs2[p];
-        if(bestI == kEndCellNone || bestMn == kNoDiagonalStep) j2.state = kStateEmpty;        // :185-191
+        const uint32_t lowHalf = bestP & 0xffffu;
+        if(bestI == kEndCellNone || lowHalf == (kPairNoDiagonalStep & 0xffffu)) j2.state = kStateEmpty;        // :185-191
         else {
-            const int32_t offsetMin = (bestMn == kNoMatchingStep) ? INT32_MAX : bestMn, offsetMax = bestMx;
+            const bool noMatch = lowHalf == (kPairNoMatchingStep & 0xffffu);
+            const int32_t offsetMin = noMatch ? INT32_MAX : int32_t(int16_t(lowHalf));
+            const int32_t offsetMax = noMatch ? INT32_MIN : -int32_t(int16_t(bestP >> 16));
             // 32-bit wrap-around like the compiled reference (:222-239)
             const int32_t bandMin = int32_t(uint32_t(offsetMin) - uint32_t(g.bandExtend));
             const int32_t bandMax = int32_t(uint32_t(offsetMax) + uint32_t(g.bandExtend));
@@ -816,6 +840,8 @@ __host__ __device__ inline uint32_t dpWavefrontC(uint32_t Wpad)
 // .x = x0 | (length - 1) << 28, .y = y0. Reads have fewer than 2^28 markers (checked by the host).
 constexpr uint32_t kRunLengthShift = 28, kRunOrdinalMask = (1u << kRunLengthShift) - 1u;
 
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+
 static __global__ void __launch_bounds__(128)
 tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __restrict__ jobs, const int2* __restrict__ endCells,
                 const uint32_t* __restrict__ trace, uint2* __restrict__ runs, uint32_t* __restrict__ runCounts)
@@ -838,10 +864,19 @@ tracebackKernel(uint32_t n, const uint32_t* __restrict__ order, const DpJob* __r
         uint2* __restrict__ out = runs + job.outOffset;
         const int32_t hi = job.hi;
         // One dependent load per iteration; the threads of a warp stay in step (one run or one gap step per iteration).
+        uint32_t lastBlock = 0xffffffffu;
         while(i > 0 && j > 0) {
             const uint32_t e = uint32_t(j - i + hi) + shift;
             const uint32_t t = uint32_t(i - iFirst) + ((e * reciprocal) >> 16);
-            const uint32_t word = tr[uint64_t(t >> 4) * Wpad + e];
+            const uint32_t block = t >> 4;
+            const uint32_t word = tr[uint64_t(block) * Wpad + e];
+            // The walk is a chain of dependent loads, and each 16-step block of the trace is a new DRAM line: ask for the
+            // lines of the two blocks above (same offset; the path drifts by a few offsets per block) when a block is entered.
+            if(block != lastBlock) {
+                lastBlock = block;
+                if(block >= 1) prefetchL1(tr + uint64_t(block - 1) * Wpad + e);
+                if(block >= 2) prefetchL1(tr + uint64_t(block - 2) * Wpad + e);
+            }
             // Diagonal steps stay on the same offset: a run of them is a run of equal codes going down this word.
             const uint32_t q = t & 15u;
             int32_t run;
@@ -1153,18 +1188,20 @@ static __global__ void method3SetupKernel(const uint32_t* __restrict__ candidate
     j1.aOffset = dsToc[o0]; j1.nx = uint32_t(dsToc[o0 + 1] - dsToc[o0]);
     j1.bOffset = dsToc[o1]; j1.ny = uint32_t(dsToc[o1 + 1] - dsToc[o1]);
     j1.lo = -int32_t(j1.ny); j1.hi = int32_t(j1.nx);
-    j1.traceOffset = 0; j1.outOffset = 0; j1.pad = 0;
+    j1.traceOffset = 0; j1.outOffset = 0;
     j1.state = (j1.nx == 0 || j1.ny == 0) ? kStateEmpty : kStateRun;       // src/AssemblerAlign3.cpp:100-106
-    if(j1.state == kStateRun && j1.ny > kStage1ForwardMaxRows && dpPaddedWidth(j1.lo, j1.hi) > maxWidth) {
-        j1.state = kStateSkipped; atomicAdd(tooWide, 1ull);
-    }
     j2.aOffset = toc[o0]; j2.nx = uint32_t(toc[o0 + 1] - toc[o0]);
     j2.bOffset = toc[o1]; j2.ny = uint32_t(toc[o1 + 1] - toc[o1]);
     j2.lo = 0; j2.hi = 0; j2.traceOffset = 0; j2.outOffset = 0; j2.pad = 0;
+    // Only the jobs that the forward kernel cannot take need a trace: too many downsampled rows, or reads so long that an
+    // ordinal offset does not fit the kernel's 16-bit offset pair. pad = 1 marks the forward-kernel jobs for the class sort.
+    const bool forward = j1.ny <= kStage1ForwardMaxRows && max(j2.nx, j2.ny) <= kStage1ForwardMaxMarkers;
+    j1.pad = forward ? 1u : 0u;
+    if(j1.state == kStateRun && !forward && dpPaddedWidth(j1.lo, j1.hi) > maxWidth) {
+        j1.state = kStateSkipped; atomicAdd(tooWide, 1ull);
+    }
     j2.state = (j1.state == kStateEmpty) ? kStateEmpty : kStateSkipped;     // stage 1 overwrites it when it runs
     jobs1[p] = j1; jobs2[p] = j2;
-    // Only the jobs that are too long for the forward kernel need a trace.
-    const bool forward = j1.ny <= kStage1ForwardMaxRows;
     traceWords1[p] = (j1.state == kStateRun && !forward) ? dpTraceWords(j1.nx, j1.ny, j1.lo, j1.hi) : 0ull;
     if(j1.state == kStateRun && forward) atomicAdd(forwardCells, (unsigned long long)j1.nx * j1.ny);
     outCount[p] = min(j2.nx, j2.ny);
@@ -1194,7 +1231,7 @@ static __global__ void dpClassKeysKernel(const DpJob* __restrict__ jobs, uint32_
     const DpJob j = jobs[p];
     uint32_t cls = 255;
     if(j.state == kStateRun) {
-        if(forwardClasses && j.ny <= classLimits[forwardClasses - 1]) {
+        if(forwardClasses && j.pad) {           // marked by method3SetupKernel: few enough rows and short enough reads
             for(uint32_t k = 0; k < forwardClasses; k++) if(j.ny <= classLimits[k]) { cls = k; break; }
         } else {
             const uint32_t Wpad = dpPaddedWidth(j.lo, j.hi);

@@ -105,6 +105,7 @@ struct HostResult {
     HostResult& operator=(const HostResult&) = delete;
     ~HostResult() { if(p) HostPool::instance().release(p); }
     void* take() { void* q = p; p = nullptr; return q; }
+    void reset(void* q) { if(p) HostPool::instance().release(p); p = q; }
 };
 
 } // namespace shb

@@ -121,7 +121,7 @@ void accReserve(shb_context* c, Accumulator& a, uint64_t n)
 // wrap-around is applied when the frequency is read, frequencyFlagsKernel).
 void mergeAccumulator(shb_context* c, Accumulator& acc, uint32_t readBits)
 {
-    if(acc.count == 0) return;
+    if(acc.count == 0 || acc.sorted) return;
     SHB_REQUIRE(acc.count < (1ull << 32), SHB_ERR_INVALID, "LowHash0: candidate accumulator exceeds 2^32-1 items.");
     const uint32_t n = uint32_t(acc.count);
     cudaStream_t st = c->stream;
@@ -147,6 +147,31 @@ void mergeAccumulator(shb_context* c, Accumulator& acc, uint32_t readBits)
                (const uint32_t*)c->segStartBuf.get(), numSeg, outK.get(), outV.get());
     acc.inB = !acc.inB;
     acc.count = numSeg;
+    acc.sorted = true;
+}
+
+// Raw pair hits are kept unsorted across iterations (one 8-byte key per hit) and reduced in one go: sort, run lengths,
+// (pairKey, count) appended to the accumulator. When the accumulator was empty the result already is the merged table.
+void reduceRawPairs(shb_context* c, Accumulator& acc, uint32_t readBits)
+{
+    if(acc.rawCount == 0) return;
+    SHB_REQUIRE(acc.rawCount < (1ull << 32), SHB_ERR_INVALID, "LowHash0: more than 2^32-1 buffered candidate pair hits.");
+    const uint32_t np = uint32_t(acc.rawCount);
+    cudaStream_t st = c->stream;
+    c->pairsB.reserve(np);
+    const int pairRanges[2][2] = {{0, int(readBits) + 1}, {32, 32 + int(readBits)}};
+    const bool inB = radixSort<false>(c->pairsA.get(), c->pairsB.get(), nullptr, nullptr, np, pairRanges, 2, c->sortWs, st);
+    const uint64_t* sortedPairs = inB ? c->pairsB.get() : c->pairsA.get();
+    const uint32_t numUnique = buildSegments(c, sortedPairs, np, 0);
+    const bool first = (acc.count == 0);
+    accReserve(c, acc, acc.count + numUnique);
+    SHB_LAUNCH(uniqueCountsKernel, ceilDiv(numUnique, 256), 256, 0, st, sortedPairs,
+               (const uint32_t*)c->segStartBuf.get(), numUnique,
+               accKeys(c, acc) + acc.count, accVals(c, acc) + acc.count);
+    acc.count += numUnique;
+    acc.sorted = first;
+    acc.rawCount = 0;
+    if(acc.count > (1ull << 30)) mergeAccumulator(c, acc, readBits);     // keep the accumulator below 2^32 items
 }
 
 uint64_t countHighFrequency(shb_context* c, const Accumulator& acc, uint64_t minFrequency, bool keepOffsets)
@@ -194,6 +219,10 @@ void lowhashBegin(shb_context* c, const shb_lowhash_params& p)
     LowHashState& S = lowhashState(c);
     S = LowHashState();
     S.p = p;
+    if(const char* e = std::getenv("SHB_LOWHASH_RAW_LIMIT")) {          // test hook: force the intermediate reductions
+        const long long v = std::atoll(e);
+        if(v > 0) S.acc.rawLimit = uint64_t(v);
+    }
     g_launchCount = 0;
     const uint64_t R = c->readCountTotal;
 
@@ -315,22 +344,18 @@ void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uin
     const uint32_t np = uint32_t(np64);
     S.pairCount += np;
     if(np == 0) return;
-    c->pairsA.reserve(np);
-    c->pairsB.reserve(np);
+    // The hits are appended to the raw pair buffer; sorting and counting happen once for many iterations.
+    if(S.acc.rawCount && S.acc.rawCount + np > S.acc.rawLimit) reduceRawPairs(c, S.acc, S.readBits);
+    const uint64_t want = S.acc.rawCount + np;
+    if(c->pairsA.capacity() < want) {
+        const uint64_t iterations = std::max<uint64_t>(1, p.minHashIterationCount);
+        c->pairsA.reserve(std::max<uint64_t>(want, std::min<uint64_t>(S.acc.rawLimit, uint64_t(np + np / 8) * iterations)), true, st);
+    }
     SHB_LAUNCH(bucketPairsKernel<true>, ceilDiv(n, 256), 256, 0, st, keys, vals, n,
                (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(),
                (const uint32_t*)c->segStartBuf.get(), p.minBucketSize, p.maxBucketSize,
-               (unsigned long long*)nullptr, (unsigned long long*)nullptr, c->countsBuf.get(), c->pairsA.get());
-    const int pairRanges[2][2] = {{0, int(S.readBits) + 1}, {32, 32 + int(S.readBits)}};
-    const bool inB = radixSort<false>(c->pairsA.get(), c->pairsB.get(), nullptr, nullptr, np, pairRanges, 2, c->sortWs, st);
-    const uint64_t* sortedPairs = inB ? c->pairsB.get() : c->pairsA.get();
-    const uint32_t numUnique = buildSegments(c, sortedPairs, np, 0);
-    accReserve(c, S.acc, S.acc.count + numUnique);
-    SHB_LAUNCH(uniqueCountsKernel, ceilDiv(numUnique, 256), 256, 0, st, sortedPairs,
-               (const uint32_t*)c->segStartBuf.get(), numUnique,
-               accKeys(c, S.acc) + S.acc.count, accVals(c, S.acc) + S.acc.count);
-    S.acc.count += numUnique;
-    if(S.acc.count > (1ull << 30)) mergeAccumulator(c, S.acc, S.readBits);     // keep the accumulator below 2^32 items
+               (unsigned long long*)nullptr, (unsigned long long*)nullptr, c->countsBuf.get(), c->pairsA.get() + S.acc.rawCount);
+    S.acc.rawCount = want;
 }
 
 // Merge the local accumulator; returns its device arrays (valid until the next LowHash call on this context).
@@ -339,6 +364,7 @@ void lowhashLocalPairs(shb_context* c, uint64_t** keys, uint32_t** counts, uint6
     LowHashState& S = lowhashState(c);
     SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
     SHB_CUDA(cudaSetDevice(c->device));
+    reduceRawPairs(c, S.acc, S.readBits);
     mergeAccumulator(c, S.acc, S.readBits);
     *keys = accKeys(c, S.acc); *counts = accVals(c, S.acc); *n = S.acc.count;
 }
@@ -350,7 +376,9 @@ void lowhashSetPairs(shb_context* c, const uint64_t* keys, const uint32_t* count
     SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
     SHB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
+    const uint64_t rawLimit = S.acc.rawLimit;
     S.acc = Accumulator();
+    S.acc.rawLimit = rawLimit;
     accReserve(c, S.acc, n);
     if(n) {
         SHB_CUDA(cudaMemcpyAsync(accKeys(c, S.acc), keys, 8 * n, cudaMemcpyDeviceToDevice, st));
@@ -368,6 +396,7 @@ uint64_t lowhashEmitDevice(shb_context* c)
     SHB_REQUIRE(S.active, SHB_ERR_STATE, "shb_lowhash_begin was not called.");
     SHB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
+    reduceRawPairs(c, S.acc, S.readBits);
     mergeAccumulator(c, S.acc, S.readBits);
     const uint64_t nOut = countHighFrequency(c, S.acc, S.p.minFrequency, true);
     unsigned long long* digestDev = c->scalars.get() + 41;
@@ -477,6 +506,7 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
         for(uint32_t s = 0; s < group; s++, iteration++) {
             lowhashProcessEntries(c, c->sweepKeys.get() + uint64_t(s) * S.capacity, c->sweepVals.get() + uint64_t(s) * S.capacity, counts[s]);
             if(perIteration) {
+                reduceRawPairs(c, S.acc, S.readBits);
                 mergeAccumulator(c, S.acc, S.readBits);
                 highFrequency = countHighFrequency(c, S.acc, p.minFrequency, false);
                 if(iterSummary && iteration < maxIterSummary) {

@@ -124,6 +124,24 @@ template<int MM> __device__ __forceinline__ U64Halves murmurAlmost(U64Halves h, 
     return h;
 }
 
+// The complete MurmurHash64A of the feature of m k-mer ids at w (src/MurmurHash2.cpp:96-140 on 4*m bytes), seed < 2^32.
+template<int MM> __device__ __forceinline__ uint64_t featureHash(const uint32_t* w, uint32_t m, uint32_t seed, uint64_t lenTimesM)
+{
+    const uint32_t blocks = (MM > 0) ? uint32_t(MM / 2) : (m >> 1);
+    U64Halves h = halves(lenTimesM);
+    h.lo ^= seed;
+    for(uint32_t b = 0; b < blocks; b++) {
+        const U64Halves k = halves(murmurMix(uint64_t(w[2*b]) | (uint64_t(w[2*b + 1]) << 32)));
+        h.lo ^= k.lo; h.hi ^= k.hi;
+        h = mulM(h);
+    }
+    if(m & 1u) { h.lo ^= w[m - 1]; h = mulM(h); }
+    h.lo ^= h.hi >> 15;
+    h = mulM(h);
+    h.lo ^= h.hi >> 15;
+    return whole(h);
+}
+
 // Which oriented read does marker position p belong to, and is the feature starting at p valid
 // (inside one read, read not palindromic: src/LowHash0.cpp:325,337,344)? Returns the LOCAL
 // oriented read index or 0xffffffff.
@@ -140,9 +158,10 @@ __device__ __forceinline__ uint32_t resolveFeature(const SweepArgs& a, uint64_t 
 }
 
 // The hot loop hashes every position for every seed of the launch and tests only the HIGH word of the hash against the
-// threshold (one compare). The few hashes that pass (about hashFraction of them) finish the hash, make the exact test and
-// are queued in shared memory; the divergent work on them (toc binary search, validity, output slot) is done afterwards by
-// all threads of the block over the queue, so a warp never serialises behind one lane's rare path.
+// threshold (one compare), collecting the (position, seed) pairs that pass (about hashFraction of them) in bit masks. They
+// are queued in shared memory once per tile; all the work on them (complete hash, exact test, toc binary search, validity,
+// output slot) is done afterwards by all threads of the block over the queue, one entry per lane, so a warp never
+// serialises behind one lane's rare path.
 // KK > 0: the number of fused iterations is a compile-time constant (fully unrolled seed loop); KK == 0: a.iterationCount.
 template<int MM, int KK> __global__ void __launch_bounds__(kSweepThreads)
 lowhashSweepKernel(const SweepArgs a)
@@ -174,6 +193,8 @@ lowhashSweepKernel(const SweepArgs a)
     const uint32_t thresholdHigh = uint32_t(threshold >> 32);
     const uint32_t seed0 = a.iterationBegin * 37u;                    // iteration * 37 fits 32 bits
 
+    static_assert(kSweepPositionsPerThread <= 8 && kMaxFusedIterations <= 16, "hit masks: 16 bits x 8 positions");
+    uint64_t hitsA = 0, hitsB = 0;
 #pragma unroll 1
     for(int slot = 0; slot < kSweepPositionsPerThread; slot++) {
         const int local = slot * kSweepThreads + threadIdx.x;
@@ -202,34 +223,38 @@ lowhashSweepKernel(const SweepArgs a)
 
         // Hot loop: hash for every seed and remember WHICH seeds passed the high-word test in a bit mask (no divergent work
         // here: a warp step in which one of the 32 lanes has a hit would otherwise drag the whole warp through the rare path,
-        // and with hashFraction 0.01 that is one step in four).
+        // and with hashFraction 0.01 and 10 seeds that is nearly every step).
         uint32_t hitMask = 0;
 #pragma unroll
         for(uint32_t s = 0; s < ((KK > 0) ? uint32_t(KK) : K); s++) {
             const U64Halves h = murmurAlmost<MM>(U64Halves{uint32_t(x0) ^ (seed0 + 37u * s), uint32_t(x0 >> 32)}, mixed, blocks, hasTail, tail);
             hitMask |= (h.hi <= thresholdHigh) ? (1u << s) : 0u;
         }
-        // Rare path (about hashFraction of the hashes): recompute the few candidates, make the exact test and queue them.
-        while(hitMask) {
-            const uint32_t s = uint32_t(__ffs(int(hitMask))) - 1u;
-            hitMask &= hitMask - 1u;
-            const U64Halves h = murmurAlmost<MM>(U64Halves{uint32_t(x0) ^ (seed0 + 37u * s), uint32_t(x0 >> 32)}, mixed, blocks, hasTail, tail);
-            const uint64_t hash = whole(U64Halves{h.lo ^ (h.hi >> 15), h.hi});
+        // 16 mask bits per position, four positions per word.
+        if(slot < 4) hitsA |= uint64_t(hitMask) << (16 * slot);
+        else hitsB |= uint64_t(hitMask) << (16 * (slot - 4));
+    }
+    // The hits of all the thread's positions are queued in one go (the warp loops as often as its busiest lane has hits in
+    // the whole tile, not once per position); only (position, seed) is queued: the hash is recomputed, lane-dense, below.
+    for(;;) {
+        uint32_t bit;
+        if(hitsA) { bit = uint32_t(__ffsll((long long)hitsA)) - 1u; hitsA &= hitsA - 1ull; }
+        else if(hitsB) { bit = 64u + uint32_t(__ffsll((long long)hitsB)) - 1u; hitsB &= hitsB - 1ull; }
+        else break;
+        const uint32_t local = (bit >> 4) * kSweepThreads + threadIdx.x, s = bit & 15u;
+        const uint32_t q = atomicAdd(&queueCount, 1u);
+        if(q < a.queueCapacity) queueMeta[q] = local | (s << 16);
+        else {
+            // Queue full (cannot happen for the sizes the host derives from hashFraction unless the data are pathological):
+            // do the rare path inline.
+            const uint64_t hash = featureHash<MM>(sk + local, m, seed0 + 37u * s, lenTimesM);
             if(hash >= threshold) continue;
-            const uint32_t q = atomicAdd(&queueCount, 1u);
-            if(q < a.queueCapacity) {
-                queueHash[q] = hash;
-                queueMeta[q] = uint32_t(local) | (s << 16);
-            } else {
-                // Queue full (cannot happen for the sizes the host derives from hashFraction unless the data are pathological):
-                // do the rare path inline.
-                const uint32_t o = resolveFeature(a, p, m);
-                if(o != 0xffffffffu) {
-                    const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
-                    if(gi < a.capacity) {
-                        a.keys[uint64_t(s) * a.capacity + gi] = ((hash & a.bucketMask) << 32) | (hash >> 32);
-                        a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
-                    }
+            const uint32_t o = resolveFeature(a, tileBase + local, m);
+            if(o != 0xffffffffu) {
+                const unsigned long long gi = atomicAdd(&a.counts[s], 1ull);
+                if(gi < a.capacity) {
+                    a.keys[uint64_t(s) * a.capacity + gi] = ((hash & a.bucketMask) << 32) | (hash >> 32);
+                    a.vals[uint64_t(s) * a.capacity + gi] = a.orientedReadBase + o;
                 }
             }
         }
@@ -241,7 +266,10 @@ lowhashSweepKernel(const SweepArgs a)
     for(uint32_t q = threadIdx.x; q < nq; q += kSweepThreads) {
         const uint32_t meta = queueMeta[q];
         const uint32_t local = meta & 0xffffu, s = meta >> 16;
-        const uint32_t o = resolveFeature(a, tileBase + local, m);
+        // The complete hash and the exact test (the hot loop looked at the high word only).
+        const uint64_t hash = featureHash<MM>(sk + local, m, seed0 + 37u * s, lenTimesM);
+        const uint32_t o = (hash < threshold) ? resolveFeature(a, tileBase + local, m) : 0xffffffffu;
+        queueHash[q] = hash;
         if(o != 0xffffffffu) {
             queueMeta[q] = atomicAdd(&seedCount[s], 1u) | (s << 24);
             queueRead[q] = a.orientedReadBase + o;

@@ -7,8 +7,8 @@
 //     started in order), ranks its items stably inside the tile (per-warp digit counters in shared memory, match_any
 //     inside a warp round), publishes the tile's digit counts, and obtains the number of equal-digit items in all EARLIER
 //     tiles by decoupled look-back over the tiles' published counts / inclusive prefixes (thread d follows digit d);
-//   * the items are first permuted into digit order in shared memory and then written out run by run, so that
-//     consecutive threads write consecutive addresses.
+//   * the items are permuted into digit order in shared memory (before the look-back, which needs no item registers)
+//     and then written out run by run, so that consecutive threads write consecutive addresses.
 // Per pass and item: 12 (8) bytes read + 12 (8) bytes written with (without) payload, against three kernels and two reads
 // per digit of the previous histogram / scan / scatter organisation.
 #pragma once
@@ -79,7 +79,12 @@ radixDigitStartsKernel(unsigned long long* __restrict__ hist, int passCount)
 constexpr int kStatusTagShift = 56;
 constexpr unsigned long long kStatusValueMask = (1ull << kStatusTagShift) - 1ull;
 
-template<bool HAS_VALUES> __global__ void __launch_bounds__(kSortThreads)
+// The pass kernel runs 512 threads x 8 items on the same 4096-item tile: half the registers per thread of a 256 x 16
+// organisation, so two blocks (32 warps) stay resident per SM and hide the shared-memory / match latencies of the ranking.
+constexpr int kOnesweepThreads = 512;
+constexpr int kOnesweepItems = kSortTile / kOnesweepThreads;
+
+template<bool HAS_VALUES> __global__ void __launch_bounds__(kOnesweepThreads, 2)
 radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ keysOut,
                     const uint32_t* __restrict__ valsIn, uint32_t* __restrict__ valsOut,
                     uint32_t n, int shift, uint32_t digitMask,
@@ -87,35 +92,42 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
                     volatile unsigned long long* __restrict__ status,        // [numTiles * 256]
                     uint32_t* __restrict__ ticket, uint32_t tagBase)
 {
-    constexpr int kWarps = kSortThreads / 32;
+    constexpr int kWarps = kOnesweepThreads / 32;
+    constexpr int kDigitWarps = kRadix / 32;                // warps whose threads each own one digit
     __shared__ uint32_t warpHist[kWarps][kRadix];           // per warp: digit count, then start inside the tile's digit run
     __shared__ uint32_t localOffset[kRadix];                // start of each digit's run inside the sorted tile
     __shared__ unsigned long long digitBase[kRadix];        // where the tile's digit run starts in the output
     extern __shared__ uint64_t sortedKeys[];                // kSortTile keys, then (HAS_VALUES) kSortTile payloads
     uint32_t* sortedVals = reinterpret_cast<uint32_t*>(sortedKeys + kSortTile);
     __shared__ uint32_t tileShared;
-    __shared__ uint32_t scanTotals[kWarps];
+    __shared__ uint32_t scanTotals[kDigitWarps];
 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool ownsDigit = threadIdx.x < unsigned(kRadix);
     if(threadIdx.x == 0) tileShared = atomicAdd(ticket, 1u);
 #pragma unroll
-    for(int w = 0; w < kWarps; w++) warpHist[w][threadIdx.x] = 0;
+    for(int i = 0; i < kWarps * kRadix / kOnesweepThreads; i++) (&warpHist[0][0])[i * kOnesweepThreads + threadIdx.x] = 0;
     __syncthreads();
     const uint32_t tile = tileShared;
     const uint32_t tileBegin = tile * uint32_t(kSortTile);
     const uint32_t tileCount = min(uint32_t(kSortTile), n - tileBegin);
 
-    // Load: warp w owns the contiguous items [w*512, (w+1)*512) of the tile, 16 rounds of 32 lanes (coalesced).
+    // Load: warp w owns the contiguous items [w*256, (w+1)*256) of the tile, 8 rounds of 32 lanes (coalesced).
     // Rank: items with the same digit keep their input order (warp, round, lane).
-    uint64_t key[kSortItemsPerThread];
-    uint32_t val[kSortItemsPerThread];
-    uint32_t slot[kSortItemsPerThread];                     // digit | rank among the warp's items with that digit << 9
+    uint64_t key[kOnesweepItems];
+    uint32_t val[kOnesweepItems];
+    uint32_t slot[kOnesweepItems];                          // digit | rank among the warp's items with that digit << 9
 #pragma unroll
-    for(int r = 0; r < kSortItemsPerThread; r++) {
-        const uint32_t local = warp * (32u * kSortItemsPerThread) + uint32_t(r) * 32u + lane;
+    for(int r = 0; r < kOnesweepItems; r++) {
+        const uint32_t local = warp * (32u * kOnesweepItems) + uint32_t(r) * 32u + lane;
         const bool valid = local < tileCount;
         key[r] = valid ? keysIn[tileBegin + local] : ~0ull;
         if(HAS_VALUES) val[r] = valid ? valsIn[tileBegin + local] : 0u;
+    }
+#pragma unroll
+    for(int r = 0; r < kOnesweepItems; r++) {
+        const uint32_t local = warp * (32u * kOnesweepItems) + uint32_t(r) * 32u + lane;
+        const bool valid = local < tileCount;
         const uint32_t d = valid ? (uint32_t(key[r] >> shift) & digitMask) : uint32_t(kRadix);      // invalid slots: digit 256
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const uint32_t rankInRound = __popc(peers & ((1u << lane) - 1u));
@@ -128,60 +140,40 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
     }
     __syncthreads();
 
-    // Per digit (thread d): the tile's count, the start of every warp's items inside the digit's run, and the look-back.
-    uint32_t count = 0;
-#pragma unroll
-    for(int w = 0; w < kWarps; w++) {
-        const uint32_t c = warpHist[w][threadIdx.x];
-        warpHist[w][threadIdx.x] = count;
-        count += c;
-    }
+    // Per digit (thread d): the tile's count, the start of every warp's items inside the digit's run.
     const unsigned long long tagCount = (unsigned long long)(tagBase) << kStatusTagShift;
     const unsigned long long tagPrefix = (unsigned long long)(tagBase + 1u) << kStatusTagShift;
     volatile unsigned long long* myStatus = status + uint64_t(tile) * kRadix + threadIdx.x;
-    *myStatus = tagCount | count;
-    // exclusive scan of the counts over the digits -> localOffset
-    {
-        uint32_t inc = count;
+    uint32_t count = 0, inc = 0;
+    if(ownsDigit) {
+#pragma unroll
+        for(int w = 0; w < kWarps; w++) {
+            const uint32_t c = warpHist[w][threadIdx.x];
+            warpHist[w][threadIdx.x] = count;
+            count += c;
+        }
+        *myStatus = tagCount | count;
+        // exclusive scan of the counts over the digits -> localOffset
+        inc = count;
 #pragma unroll
         for(int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
             if(lane >= unsigned(d)) inc += t;
         }
         if(lane == 31) scanTotals[warp] = inc;
-        __syncthreads();
+    }
+    __syncthreads();
+    if(ownsDigit) {
         uint32_t offset = 0;
         for(unsigned w = 0; w < warp; w++) offset += scanTotals[w];
         localOffset[threadIdx.x] = offset + inc - count;
     }
-    // Look-back, a window of kLookback earlier tiles per round trip: when a wave of tiles reaches this point at about the
-    // same time, tile j of the wave has to walk back over about j/2 tiles that have only published their counts; reading
-    // one tile per dependent load would make that hundreds of serial L2 round trips per tile.
-    constexpr int kLookback = 16;
-    unsigned long long earlier = 0;
-    for(int64_t t = int64_t(tile) - 1; t >= 0; ) {
-        unsigned long long window[kLookback];
-#pragma unroll
-        for(int k = 0; k < kLookback; k++) window[k] = (t - k >= 0) ? status[uint64_t(t - k) * kRadix + threadIdx.x] : tagPrefix;
-        bool done = false;
-#pragma unroll
-        for(int k = 0; k < kLookback; k++) {
-            if(done) continue;
-            const unsigned long long sw = window[k];
-            const unsigned long long tag = sw & ~kStatusValueMask;
-            if(tag == tagPrefix) { earlier += sw & kStatusValueMask; t = -1; done = true; }         // (also the virtual tile -1: value 0)
-            else if(tag == tagCount) { earlier += sw & kStatusValueMask; t--; }
-            else done = true;       // that tile has not published yet (it is running: tiles start in ticket order): read again from it
-        }
-    }
-    __threadfence();
-    *myStatus = tagPrefix | (earlier + count);
-    digitBase[threadIdx.x] = digitStart[threadIdx.x] + earlier;
     __syncthreads();
 
-    // Permute into digit order in shared memory ...
+    // Permute into digit order in shared memory (this needs only tile-local offsets, so it is done BEFORE the look-back:
+    // the keys leave the registers, and the other warps' shared-memory traffic overlaps the look-back's global loads).
 #pragma unroll
-    for(int r = 0; r < kSortItemsPerThread; r++) {
+    for(int r = 0; r < kOnesweepItems; r++) {
         const uint32_t d = slot[r] & 0x1ffu;
         if(d < uint32_t(kRadix)) {
             const uint32_t pos = localOffset[d] + warpHist[warp][d] + (slot[r] >> 9);
@@ -189,11 +181,38 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
             if(HAS_VALUES) sortedVals[pos] = val[r];
         }
     }
-    __syncthreads();
-    // ... and write the runs out: item i of the sorted tile goes to digitBase[d] + (i - localOffset[d]).
+
+    // Look-back, a window of kLookback earlier tiles per round trip: when a wave of tiles reaches this point at about the
+    // same time, tile j of the wave has to walk back over about j/2 tiles that have only published their counts; reading
+    // one tile per dependent load would make that hundreds of serial L2 round trips per tile.
+    if(ownsDigit) {
+        constexpr int kLookback = 16;
+        unsigned long long earlier = 0;
+        for(int64_t t = int64_t(tile) - 1; t >= 0; ) {
+            unsigned long long window[kLookback];
 #pragma unroll
-    for(int r = 0; r < kSortItemsPerThread; r++) {
-        const uint32_t i = uint32_t(r) * kSortThreads + threadIdx.x;
+            for(int k = 0; k < kLookback; k++) window[k] = (t - k >= 0) ? status[uint64_t(t - k) * kRadix + threadIdx.x] : tagPrefix;
+            bool done = false;
+#pragma unroll
+            for(int k = 0; k < kLookback; k++) {
+                if(done) continue;
+                const unsigned long long sw = window[k];
+                const unsigned long long tag = sw & ~kStatusValueMask;
+                if(tag == tagPrefix) { earlier += sw & kStatusValueMask; t = -1; done = true; }         // (also the virtual tile -1: value 0)
+                else if(tag == tagCount) { earlier += sw & kStatusValueMask; t--; }
+                else done = true;       // that tile has not published yet (it is running: tiles start in ticket order): read again from it
+            }
+        }
+        __threadfence();
+        *myStatus = tagPrefix | (earlier + count);
+        digitBase[threadIdx.x] = digitStart[threadIdx.x] + earlier;
+    }
+    __syncthreads();
+
+    // Write the runs out: item i of the sorted tile goes to digitBase[d] + (i - localOffset[d]).
+#pragma unroll
+    for(int r = 0; r < kOnesweepItems; r++) {
+        const uint32_t i = uint32_t(r) * kOnesweepThreads + threadIdx.x;
         if(i < tileCount) {
             const uint64_t k = sortedKeys[i];
             const uint32_t d = uint32_t(k >> shift) & digitMask;
@@ -262,7 +281,7 @@ bool radixSort(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* vals
         uint64_t* kout = inB ? keysA : keysB;
         uint32_t* vin = inB ? valsB : valsA;
         uint32_t* vout = inB ? valsA : valsB;
-        SHB_LAUNCH((radixOnesweepKernel<HAS_VALUES>), numTiles, kSortThreads, kDynamicBytes, stream,
+        SHB_LAUNCH((radixOnesweepKernel<HAS_VALUES>), numTiles, kOnesweepThreads, kDynamicBytes, stream,
                    (const uint64_t*)kin, kout, (const uint32_t*)vin, vout, uint32_t(n), passes.shift[p], passes.mask[p],
                    (const unsigned long long*)(ws.hist.get() + uint64_t(p) * kRadix),
                    (volatile unsigned long long*)ws.status.get(), tickets + 2 * p, ws.nextTag);

@@ -47,6 +47,23 @@ def test_golden_deferred_merge(ctx, name, golden_dir):
     assert res.kernelLaunches > 0
 
 
+@pytest.mark.parametrize("limit", [1, 5000])
+def test_golden_with_forced_intermediate_reductions(ctx, golden_dir, monkeypatch, limit):
+    """The pair hits of the iterations are buffered raw and reduced (sorted, counted) in one go; a tiny buffer limit
+    forces a reduction + merge after every iteration or every few, which must give the same candidates."""
+    from shasta_b200 import capi
+    g = np.load(os.path.join(golden_dir, "lowhash_golden.npz"))
+    monkeypatch.setenv("SHB_LOWHASH_RAW_LIMIT", str(limit))
+    for name, (spec, params) in MG.LOWHASH_CASES.items():
+        if params.get("minHashIterationCount", 10) == 0:
+            continue
+        d = MG.load_input(spec)
+        ctx.set_markers(d["toc"], d["data"], d["flags"])
+        cand, stats, _, res = ctx.lowhash0(_params(capi, params))
+        assert np.array_equal(cand, g[name + "/candidates"]), name
+        assert np.array_equal(stats, g[name + "/stats"]), name
+
+
 @pytest.mark.parametrize("name", list(MG.LOWHASH_CASES))
 def test_golden_per_iteration_merge(ctx, name, golden_dir):
     from shasta_b200 import capi

@@ -52,7 +52,7 @@ def test_tinytest_markers_bit_for_bit(ctx):
 @pytest.mark.skipif(not B.have_ref(), reason="reference build absent")
 @pytest.mark.parametrize("k", [6, 10, 14])
 def test_synthetic_fasta_against_live_reference(ctx, tmp_path, k):
-    from tests.test_oracle_markers import write_synthetic_fasta
+    from test_oracle_markers import write_synthetic_fasta
     fasta = str(tmp_path / "synthetic.fasta")
     write_synthetic_fasta(fasta, reads=60, seed=k)
     r = B.ref_reads_from_fasta(fasta, k=k, min_read_length=1000)
