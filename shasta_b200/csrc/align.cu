@@ -496,6 +496,7 @@ struct AlignCall {
     bool method4;
     DpScores scores; FilterOptions fo;
     uint32_t batchMax;
+    uint32_t align4SmemCells = kAlign4SmemCells;   // candidates with more existing cells take the global-memory path (SHB_ALIGN4_SMEM_CELLS: test hook)
     // batch dispenser (method 4 sizes a batch by its grid cells, so the cut is made under the lock, in order)
     std::mutex dispenserMutex;
     uint64_t nextBegin = 0, nextIndex = 0;
@@ -688,7 +689,8 @@ void processBatch(AlignCall& call, AlignWorker& w, uint64_t begin, uint32_t nb, 
         g.maxBand = int64_t(uint64_t(o.maxBand));
         g.cellOffsets = b.cellOff.get(); g.counts = b.gridCounts.get(); g.aux = b.gridAux.get(); g.list = b.gridList.get();
         g.flags = b.gridFlags.get(); g.bands = b.gridBands.get(); g.componentCount = b.componentCount.get();
-        SHB_LAUNCH(align4FrontEndKernel, ceilDiv(nb, 4), 128, 0, st, g);
+        SHB_LAUNCH(align4MatrixKernel, ceilDiv(nb, 4), 128, 0, st, g);
+        SHB_LAUNCH(align4ComponentsKernel, ceilDiv(nb, kAlign4WarpsPerBlock), kAlign4WarpsPerBlock * 32, 0, st, g, call.align4SmemCells);
         exclusiveScan<uint32_t>(b.componentCount.get(), b.jobOffsets.get(), nb, total32, w.scanWs.get(), st);
         nJobs = readBack<uint32_t>(total32, st);
         if(nJobs) {
@@ -848,6 +850,7 @@ void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, c
     // SHB_ALIGN_BATCH / SHB_ALIGN_CHUNK / SHB_ALIGN_WORKERS: test hooks that shrink the batch and chunk sizes so that small
     // inputs exercise the multi-batch, multi-chunk, multi-worker paths (tests/test_gpu_scale.py).
     call.batchMax = envCount("SHB_ALIGN_BATCH", call.method4 ? 32768 : (o.alignMethod == 1 ? 16384 : 262144));
+    call.align4SmemCells = std::min<uint32_t>(kAlign4SmemCells, envCount("SHB_ALIGN4_SMEM_CELLS", kAlign4SmemCells));
     const uint64_t batchEstimate = (n + call.batchMax - 1) / call.batchMax;
     const uint32_t workerCount = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(envCount("SHB_ALIGN_WORKERS", 2), batchEstimate)));
     while(ac.workers.size() < workerCount) ac.workers.emplace_back(new AlignWorker());

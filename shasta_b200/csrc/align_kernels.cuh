@@ -1348,33 +1348,66 @@ __device__ __forceinline__ void align4Getxy(int32_t X, int32_t Y, int32_t nx, in
     y = (X + Y - nx + 1) / 2;
 }
 
-static __global__ void __launch_bounds__(128) align4FrontEndKernel(Align4Args g)
+// The cell that holds alignment-matrix entry (x, y) of a grid with nIX cells per row.
+struct Align4Grid {
+    uint32_t nx, ny, nIX, nIY, nCells;
+    uint64_t aBegin, bBegin, base;
+};
+__device__ __forceinline__ Align4Grid align4Grid(const Align4Args& g, uint32_t p)
+{
+    uint64_t o0, o1;
+    candidateOrientedReads(g.candidates, p, o0, o1);
+    Align4Grid r;
+    r.aBegin = g.toc[o0]; r.bBegin = g.toc[o1];
+    r.nx = uint32_t(g.toc[o0 + 1] - r.aBegin); r.ny = uint32_t(g.toc[o1 + 1] - r.bBegin);
+    align4GridSize(r.nx, r.ny, g.deltaX, g.deltaY, r.nIX, r.nIY);
+    r.nCells = r.nIX * r.nIY;
+    r.base = g.cellOffsets[p];
+    return r;
+}
+
+// Cell flags of createCells (:380-436): 1 exists, 2|8 near the left / top boundary (forward seeds), 4 near right / bottom.
+__device__ __forceinline__ uint8_t align4CellFlags(const Align4Args& g, const Align4Grid& G, uint32_t iX, uint32_t iY)
+{
+    const int32_t nx = int32_t(G.nx), ny = int32_t(G.ny);
+    int32_t x, y;
+    align4Getxy(int32_t(iX * g.deltaX), int32_t((iY + 1) * g.deltaY), nx, x, y);
+    const uint32_t dLeft = x < 0 ? 0u : uint32_t(x);
+    align4Getxy(int32_t((iX + 1) * g.deltaX), int32_t(iY * g.deltaY), nx, x, y);
+    const uint32_t dRight = (x >= nx - 1) ? 0u : uint32_t(nx - 1 - x);
+    align4Getxy(int32_t(iX * g.deltaX), int32_t(iY * g.deltaY), nx, x, y);
+    const uint32_t dTop = y < 0 ? 0u : uint32_t(y);
+    align4Getxy(int32_t((iX + 1) * g.deltaX), int32_t((iY + 1) * g.deltaY), nx, x, y);
+    const uint32_t dBottom = (y >= ny - 1) ? 0u : uint32_t(ny - 1 - y);
+    uint8_t f = 1;
+    if(uint64_t(dLeft) < g.maxDistanceFromBoundary || uint64_t(dTop) < g.maxDistanceFromBoundary) f |= 2 | 8;   // seeds are forward accessible
+    if(uint64_t(dRight) < g.maxDistanceFromBoundary || uint64_t(dBottom) < g.maxDistanceFromBoundary) f |= 4;
+    return f;
+}
+
+// Front end, kernel 1 of 2, one warp per candidate: createAlignmentMatrix (:195-267) as a dense grid of entry counts in
+// global scratch. Every pair of equal k-mers (x in read 0, y in read 1) adds one entry to cell (X/deltaX, Y/deltaY),
+// X = x + y, Y = y + nx - 1 - x. The cell whose count reaches the existence threshold of createCells is appended (in
+// any order) to the candidate's cell list; listCount (= componentCount[p] until kernel 2 overwrites it) counts them.
+static __global__ void __launch_bounds__(128) align4MatrixKernel(Align4Args g)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if(p >= g.n) return;
-    uint64_t o0, o1;
-    candidateOrientedReads(g.candidates, p, o0, o1);
-    const uint64_t aBegin = g.toc[o0], bBegin = g.toc[o1];
-    const uint32_t nx = uint32_t(g.toc[o0 + 1] - aBegin), ny = uint32_t(g.toc[o1 + 1] - bBegin);
-    uint32_t nIX, nIY;
-    align4GridSize(nx, ny, g.deltaX, g.deltaY, nIX, nIY);
-    const uint32_t nCells = nIX * nIY;
-    const uint64_t base = g.cellOffsets[p];
-    uint32_t* counts = g.counts + base;
-    uint32_t* aux = g.aux + base;
-    uint32_t* list = g.list + base;
-    uint8_t* flags = g.flags + base;
-    int32_t* bands = g.bands + base;
-    if(nCells == 0) { if(lane == 0) g.componentCount[p] = 0; return; }
-
+    const Align4Grid G = align4Grid(g, p);
+    const uint32_t nx = G.nx, ny = G.ny, nIX = G.nIX, nCells = G.nCells;
+    uint32_t* counts = g.counts + G.base;
+    uint32_t* list = g.list + G.base;
+    uint8_t* flags = g.flags + G.base;
+    if(lane == 0) g.componentCount[p] = 0;
+    if(nCells == 0) return;
     for(uint32_t i = lane; i < nCells; i += 32) { counts[i] = 0; flags[i] = 0; }
     __syncwarp();
-
-    // createAlignmentMatrix (:195-267): every pair of equal k-mers (x in read 0, y in read 1) adds one entry
-    // to cell (X/deltaX, Y/deltaY), X = x + y, Y = y + nx - 1 - x.
-    const uint32_t* sa = g.sortedKmer + aBegin; const uint32_t* oa = g.sortedOrdinal + aBegin;
-    const uint32_t* sb = g.sortedKmer + bBegin; const uint32_t* ob = g.sortedOrdinal + bBegin;
+    // A cell exists when its count is positive and not below minEntryCountPerCell (:398-402).
+    const int64_t minEntries = int64_t(g.minEntryCountPerCell);
+    const uint32_t threshold = minEntries <= 1 ? 1u : (minEntries > int64_t(0xffffffffu) ? 0xffffffffu : uint32_t(minEntries));
+    const uint32_t* sa = g.sortedKmer + G.aBegin; const uint32_t* oa = g.sortedOrdinal + G.aBegin;
+    const uint32_t* sb = g.sortedKmer + G.bBegin; const uint32_t* ob = g.sortedOrdinal + G.bBegin;
     for(uint32_t t = lane; t < nx; t += 32) {
         const uint32_t kmer = sa[t];
         uint32_t lo = 0, hi = ny;               // lower bound of kmer in sb
@@ -1383,10 +1416,22 @@ static __global__ void __launch_bounds__(128) align4FrontEndKernel(Align4Args g)
         for(uint32_t q = lo; q < ny && sb[q] == kmer; q++) {
             const uint32_t y = ob[q];
             const uint32_t X = x + y, Y = nx + y - x - 1;
-            atomicAdd(&counts[(Y / g.deltaY) * nIX + X / g.deltaX], 1u);
+            const uint32_t cell = (Y / g.deltaY) * nIX + X / g.deltaX;
+            if(atomicAdd(&counts[cell], 1u) + 1u == threshold) list[atomicAdd(&g.componentCount[p], 1u)] = cell;
         }
     }
-    __syncwarp();
+}
+
+// The rest of the front end on the dense global grid (any number of existing cells): the slow path of kernel 2.
+__device__ __noinline__ void align4GlobalTail(const Align4Args& g, uint32_t p, const Align4Grid& G)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t nx = G.nx, nIX = G.nIX, nIY = G.nIY, nCells = G.nCells;
+    uint32_t* counts = g.counts + G.base;
+    uint32_t* aux = g.aux + G.base;
+    uint32_t* list = g.list + G.base;
+    uint8_t* flags = g.flags + G.base;
+    int32_t* bands = g.bands + G.base;
 
     // createCells (:380-436) + compact list of existing cells in raster order.
     uint32_t listSize = 0;
@@ -1397,19 +1442,7 @@ static __global__ void __launch_bounds__(128) align4FrontEndKernel(Align4Args g)
             const uint32_t cnt = counts[i];
             exists = cnt > 0 && !(int64_t(cnt) < int64_t(g.minEntryCountPerCell));
             if(exists) {
-                const uint32_t iX = i % nIX, iY = i / nIX;
-                int32_t x, y;
-                align4Getxy(int32_t(iX * g.deltaX), int32_t((iY + 1) * g.deltaY), int32_t(nx), x, y);
-                const uint32_t dLeft = x < 0 ? 0u : uint32_t(x);
-                align4Getxy(int32_t((iX + 1) * g.deltaX), int32_t(iY * g.deltaY), int32_t(nx), x, y);
-                const uint32_t dRight = (x >= int32_t(nx) - 1) ? 0u : (nx - 1 - uint32_t(x));
-                align4Getxy(int32_t(iX * g.deltaX), int32_t(iY * g.deltaY), int32_t(nx), x, y);
-                const uint32_t dTop = y < 0 ? 0u : uint32_t(y);
-                align4Getxy(int32_t((iX + 1) * g.deltaX), int32_t((iY + 1) * g.deltaY), int32_t(nx), x, y);
-                const uint32_t dBottom = (y >= int32_t(ny) - 1) ? 0u : (ny - 1 - uint32_t(y));
-                uint8_t f = 1;
-                if(uint64_t(dLeft) < g.maxDistanceFromBoundary || uint64_t(dTop) < g.maxDistanceFromBoundary) f |= 2 | 8;   // seeds are forward accessible
-                if(uint64_t(dRight) < g.maxDistanceFromBoundary || uint64_t(dBottom) < g.maxDistanceFromBoundary) f |= 4;
+                const uint8_t f = align4CellFlags(g, G, i % nIX, i / nIX);
                 flags[i] = f;
             }
         }
@@ -1539,6 +1572,171 @@ static __global__ void __launch_bounds__(128) align4FrontEndKernel(Align4Args g)
         }
         nBands += __popc(m);
     }
+    if(lane == 0) g.componentCount[p] = nBands;
+}
+
+
+// Front end, kernel 2 of 2, one warp per candidate: cell flags, forward / backward reachability, components, bands.
+// A true overlap leaves a few cells per grid column (100 - 300 for a pair of ultra-long reads, out of 10^4 - 10^5 grid
+// cells), and the three fixpoints over them are chains of dependent neighbour reads: with the existing cells in shared
+// memory (sorted raster indices, an 8-neighbour slot table built once by binary search, flags, labels) a sweep costs
+// shared-memory latencies instead of global ones. Candidates with more existing cells than fit take the global path.
+constexpr uint32_t kAlign4SmemCells = 512;
+constexpr uint32_t kAlign4WarpsPerBlock = 2;
+constexpr uint16_t kAlign4NoSlot = 0xffffu;
+
+static __global__ void __launch_bounds__(kAlign4WarpsPerBlock * 32) align4ComponentsKernel(Align4Args g, uint32_t smemCells)
+{
+    __shared__ uint32_t sIdxAll[kAlign4WarpsPerBlock][kAlign4SmemCells];          // raster index, later the cell's row iY
+    __shared__ uint32_t sYMaxAll[kAlign4WarpsPerBlock][kAlign4SmemCells];
+    __shared__ uint16_t sNbrAll[kAlign4WarpsPerBlock][kAlign4SmemCells][9];       // slot of neighbour (oY+1)*3 + (oX+1)
+    __shared__ uint16_t sLabelAll[kAlign4WarpsPerBlock][kAlign4SmemCells];
+    __shared__ uint8_t sFlagAll[kAlign4WarpsPerBlock][kAlign4SmemCells];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * kAlign4WarpsPerBlock + warp;
+    if(p >= g.n) return;
+    const Align4Grid G = align4Grid(g, p);
+    if(G.nCells == 0) { if(lane == 0) g.componentCount[p] = 0; return; }
+    const uint32_t n = g.componentCount[p];                 // existing cells (kernel 1)
+    if(n > smemCells) { align4GlobalTail(g, p, G); return; }
+    if(n == 0) return;                                      // no cells, no components: componentCount[p] is already 0
+    uint32_t* sIdx = sIdxAll[warp]; uint32_t* sYMax = sYMaxAll[warp];
+    uint16_t (*sNbr)[9] = sNbrAll[warp]; uint16_t* sLabel = sLabelAll[warp]; uint8_t* sFlag = sFlagAll[warp];
+    const uint32_t nIX = G.nIX, nIY = G.nIY;
+
+    // The cell list in raster order: bitonic sort of the (padded) list.
+    uint32_t P = 32;
+    while(P < n) P <<= 1;
+    const uint32_t* list = g.list + G.base;
+    for(uint32_t t = lane; t < P; t += 32) sIdx[t] = t < n ? list[t] : 0xffffffffu;
+    __syncwarp();
+    for(uint32_t k = 2; k <= P; k <<= 1) {
+        for(uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for(uint32_t t = lane; t < P; t += 32) {
+                const uint32_t u = t ^ j;
+                if(u > t) {
+                    const uint32_t a = sIdx[t], b = sIdx[u];
+                    if((a > b) == ((t & k) == 0)) { sIdx[t] = b; sIdx[u] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // Flags and the neighbour slots.
+    for(uint32_t t = lane; t < n; t += 32) {
+        const uint32_t i = sIdx[t];
+        const uint32_t iX = i % nIX, iY = i / nIX;
+        sFlag[t] = align4CellFlags(g, G, iX, iY);
+#pragma unroll
+        for(int oY = -1; oY <= 1; oY++) {
+#pragma unroll
+            for(int oX = -1; oX <= 1; oX++) {
+                uint16_t slot = kAlign4NoSlot;
+                const int32_t qX = int32_t(iX) + oX, qY = int32_t(iY) + oY;
+                if((oX || oY) && qX >= 0 && qY >= 0 && qX < int32_t(nIX) && qY < int32_t(nIY)) {
+                    const uint32_t j = uint32_t(qY) * nIX + uint32_t(qX);
+                    uint32_t lo = 0, hi = n;        // lower bound of j in sIdx[0, n)
+                    while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(sIdx[mid] < j) lo = mid + 1; else hi = mid; }
+                    if(lo < n && sIdx[lo] == j) slot = uint16_t(lo);
+                }
+                sNbr[t][(oY + 1) * 3 + (oX + 1)] = slot;
+            }
+        }
+    }
+    __syncwarp();
+    for(uint32_t t = lane; t < n; t += 32) sIdx[t] /= nIX;          // from here on only the row is needed
+    __syncwarp();
+
+    // forwardSearch (:682-729): a cell is forward accessible if one of its parents (iX - {0,1}, iY - {-1,0,1}) is.
+    for(;;) {
+        bool changed = false;
+        for(uint32_t t = lane; t < n; t += 32) {
+            const uint8_t f = sFlag[t];
+            if(f & 8) continue;
+            bool reach = false;
+#pragma unroll
+            for(int e = 0; e < 5; e++) {
+                constexpr int kParents[5] = {7, 6, 3, 1, 0};
+                const uint16_t q = sNbr[t][kParents[e]];
+                if(q != kAlign4NoSlot && (sFlag[q] & 8)) reach = true;
+            }
+            if(reach) { sFlag[t] = f | 8; changed = true; }
+        }
+        __syncwarp();
+        if(!__any_sync(0xffffffffu, changed)) break;
+    }
+    // backwardSearch (:736-787): seeds = near right / bottom and forward accessible; then through the children.
+    for(uint32_t t = lane; t < n; t += 32) {
+        const uint8_t f = sFlag[t];
+        if((f & 4) && (f & 8)) sFlag[t] = f | 16;
+    }
+    __syncwarp();
+    for(;;) {
+        bool changed = false;
+        for(uint32_t t = lane; t < n; t += 32) {
+            const uint8_t f = sFlag[t];
+            if(f & 16) continue;
+            bool reach = false;
+#pragma unroll
+            for(int e = 0; e < 5; e++) {
+                constexpr int kChildren[5] = {8, 7, 5, 2, 1};
+                const uint16_t q = sNbr[t][kChildren[e]];
+                if(q != kAlign4NoSlot && (sFlag[q] & 16)) reach = true;
+            }
+            if(reach) { sFlag[t] = f | 16; changed = true; }
+        }
+        __syncwarp();
+        if(!__any_sync(0xffffffffu, changed)) break;
+    }
+    // Connected components of the active cells (8-neighbourhood): min-label propagation over the slots. Slots are in
+    // raster order, so a component's label ends up as the slot of its first cell in raster order.
+    for(uint32_t t = lane; t < n; t += 32) { sLabel[t] = ((sFlag[t] & 24) == 24) ? uint16_t(t) : kAlign4NoSlot; sYMax[t] = 0; }
+    __syncwarp();
+    for(;;) {
+        bool changed = false;
+        for(uint32_t t = lane; t < n; t += 32) {
+            const uint16_t label = sLabel[t];
+            if(label == kAlign4NoSlot) continue;
+            uint16_t best = label;
+#pragma unroll
+            for(int k = 0; k < 9; k++) {
+                if(k == 4) continue;
+                const uint16_t q = sNbr[t][k];
+                if(q != kAlign4NoSlot) best = min(best, sLabel[q]);     // inactive neighbours carry kAlign4NoSlot = the largest value
+            }
+            if(best < label) { sLabel[t] = best; changed = true; }
+        }
+        __syncwarp();
+        if(!__any_sync(0xffffffffu, changed)) break;
+    }
+    for(uint32_t t = lane; t < n; t += 32) {
+        const uint16_t label = sLabel[t];
+        if(label != kAlign4NoSlot) atomicMax(&sYMax[label], sIdx[t]);
+    }
+    __syncwarp();
+    // One band per component (:890-934), components in raster order of their first cell; too-wide bands dropped.
+    int32_t* bands = g.bands + G.base;
+    const uint32_t nx = G.nx;
+    uint32_t nBands = 0;
+    for(uint32_t t0 = 0; t0 < n; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        bool emit = false;
+        int32_t bandMin = 0, bandMax = 0;
+        if(t < n && sLabel[t] == uint16_t(t)) {
+            const uint32_t YMin = sIdx[t] * g.deltaY, YMax = (sYMax[t] + 1) * g.deltaY - 1;
+            bandMin = int32_t(nx) - 1 - int32_t(YMax);
+            bandMax = int32_t(nx) - 1 - int32_t(YMin);
+            emit = !(int64_t(bandMax - bandMin + 1) > g.maxBand);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if(emit) {
+            const uint32_t slot = nBands + __popc(m & ((1u << lane) - 1u));
+            bands[2 * slot] = bandMin;
+            bands[2 * slot + 1] = bandMax;
+        }
+        nBands += __popc(m);
+    }
+    __syncwarp();
     if(lane == 0) g.componentCount[p] = nBands;
 }
 

@@ -13,7 +13,7 @@ struct LowHashAccumulator {
     bool inB = false;       // which of the acc ping-pong buffers holds the data
     bool sorted = false;    // the reduced items are one sorted run with unique keys (nothing left to merge)
     uint64_t rawCount = 0;  // raw pair hits (one key per hit, any order) of the iterations since the last reduction, in pairsA
-    uint64_t rawLimit = 1ull << 30;     // reduce the raw hits when one more iteration would exceed this many (SHB_LOWHASH_RAW_LIMIT)
+    uint64_t rawLimit = 1ull << 31;     // reduce the raw hits when one more iteration would exceed this many (SHB_LOWHASH_RAW_LIMIT)
 };
 // State of a staged LowHash0 run (shb_lowhash_begin ... shb_lowhash_emit).
 struct LowHashState {

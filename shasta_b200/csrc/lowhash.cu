@@ -325,37 +325,33 @@ void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uin
     const uint64_t* keys = inTmp ? c->entryKeysTmp.get() : keysA;
     const uint32_t* vals = inTmp ? c->entryValsTmp.get() : valsA;
 
-    buildSegments(c, keys, n, 32, false);
-
-    // Count pass (also per-read statistics), scan, emit pass.
-    c->countsBuf.reserve(n);
-    unsigned long long* pairTotal = c->scalars.get() + 40;
-    SHB_CUDA(cudaMemsetAsync(pairTotal, 0, sizeof(unsigned long long), st));
-    SHB_LAUNCH(bucketPairsKernel<false>, ceilDiv(n, 256), 256, 0, st, keys, vals, n,
-               (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(),
-               (const uint32_t*)c->segStartBuf.get(), p.minBucketSize, p.maxBucketSize,
-               c->stats.get(), pairTotal, c->countsBuf.get(), (uint64_t*)nullptr);
-    c->scanWs.reserve(scanWorkspaceElements(n));
-    exclusiveScan<uint32_t>(c->countsBuf.get(), c->countsBuf.get(), n, (uint32_t*)nullptr, c->scanWs.get(), st);
-    // The exact 64-bit total guards the 32-bit offsets.
-    const unsigned long long np64 = readScalar<unsigned long long>(pairTotal, st);
-    SHB_REQUIRE(np64 < (1ull << 32), SHB_ERR_INVALID,
-                "LowHash0: more than 2^32-1 candidate pair hits in one iteration (maxBucketSize too large).");
-    const uint32_t np = uint32_t(np64);
-    S.pairCount += np;
-    if(np == 0) return;
-    // The hits are appended to the raw pair buffer; sorting and counting happen once for many iterations.
-    if(S.acc.rawCount && S.acc.rawCount + np > S.acc.rawLimit) reduceRawPairs(c, S.acc, S.readBits);
-    const uint64_t want = S.acc.rawCount + np;
-    if(c->pairsA.capacity() < want) {
+    // One pass: per-read statistics and the pair hits, appended (in any order) to the raw pair buffer; sorting and counting
+    // happen once for many iterations. The pass reports the exact number of hits; if they did not fit, the buffer grows
+    // (after a reduction of what it holds, when that would exceed the limit) and the pass runs again without the statistics.
+    unsigned long long* cursor = c->scalars.get() + 40;
+    if(c->pairsA.capacity() == 0) c->pairsA.reserve(1ull << 20);
+    bool withStats = true;
+    for(;;) {
+        const uint64_t room = c->pairsA.capacity() - S.acc.rawCount;
+        SHB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+        SHB_LAUNCH(bucketPairsKernel, ceilDiv(n, 256), 256, 0, st, keys, vals, n, p.minBucketSize, p.maxBucketSize,
+                   withStats ? c->stats.get() : (unsigned long long*)nullptr, cursor, c->pairsA.get() + S.acc.rawCount,
+                   (unsigned long long)room);
+        const unsigned long long np64 = readScalar<unsigned long long>(cursor, st);
+        SHB_REQUIRE(np64 < (1ull << 32), SHB_ERR_INVALID,
+                    "LowHash0: more than 2^32-1 candidate pair hits in one iteration (maxBucketSize too large).");
+        if(np64 <= room) {
+            S.pairCount += np64;
+            S.acc.rawCount += np64;
+            break;
+        }
+        withStats = false;
+        if(S.acc.rawCount && S.acc.rawCount + np64 > S.acc.rawLimit) reduceRawPairs(c, S.acc, S.readBits);
         const uint64_t iterations = std::max<uint64_t>(1, p.minHashIterationCount);
-        c->pairsA.reserve(std::max<uint64_t>(want, std::min<uint64_t>(S.acc.rawLimit, uint64_t(np + np / 8) * iterations)), true, st);
+        const uint64_t want = S.acc.rawCount + np64;
+        c->pairsA.reserve(std::max<uint64_t>(want, std::min<uint64_t>(S.acc.rawLimit, (np64 + np64 / 8) * iterations)), true, st);
     }
-    SHB_LAUNCH(bucketPairsKernel<true>, ceilDiv(n, 256), 256, 0, st, keys, vals, n,
-               (const uint32_t*)c->flagsBuf.get(), (const uint32_t*)c->indexBuf.get(),
-               (const uint32_t*)c->segStartBuf.get(), p.minBucketSize, p.maxBucketSize,
-               (unsigned long long*)nullptr, (unsigned long long*)nullptr, c->countsBuf.get(), c->pairsA.get() + S.acc.rawCount);
-    S.acc.rawCount = want;
+    if(S.acc.rawCount > S.acc.rawLimit) reduceRawPairs(c, S.acc, S.readBits);
 }
 
 // Merge the local accumulator; returns its device arrays (valid until the next LowHash call on this context).

@@ -298,67 +298,69 @@ lowhashSweepKernel(const SweepArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// a7/a8. Bucket inspection. Entries (key = bucketId<<32 | hashHigh, val = orientedReadId) are sorted
-// by bucketId; segStart delimits the buckets. One thread per entry e0:
-//   * classifies its bucket size (sparse / good / crowded) into readLowHashStatistics (pass2,
-//     src/LowHash0.cpp:386-393);
-//   * for buckets whose size is in [max(2,minBucketSize), maxBucketSize], visits the bucket and
-//     counts / emits (readId0, readId1, strand) for equal hashHigh and readId1 > readId0 (pass3,
-//     src/LowHash0.cpp:430-458).
-__device__ __forceinline__ uint32_t segmentOf(const uint32_t* flags, const uint32_t* segIndexExclusive, uint32_t i)
-{
-    return segIndexExclusive[i] + flags[i] - 1u;
-}
-
-template<bool EMIT> __global__ void __launch_bounds__(256)
+// a7/a8. Bucket inspection in ONE pass. Entries (key = bucketId<<32 | hashHigh, val = orientedReadId) are sorted by
+// bucketId. One thread per entry e0:
+//   * finds its bucket by walking left and right over equal bucket ids, giving up once the bucket is known to be larger
+//     than maxBucketSize (buckets are a handful of entries; no head flags / scan / segment table);
+//   * classifies the bucket size (sparse / good / crowded) into readLowHashStatistics (pass2, src/LowHash0.cpp:386-393);
+//   * for buckets whose size is in [max(2,minBucketSize), maxBucketSize], counts the entries with equal hashHigh and
+//     readId1 > readId0 (pass3, src/LowHash0.cpp:430-458), reserves room for them in the raw pair buffer (one atomic per
+//     warp on `cursor`) and writes (readId0, readId1, strand). The order of the raw pair hits is arbitrary: they are sorted
+//     and counted later. Hits that do not fit below `capacity` are not written; *cursor still ends up as the exact total,
+//     so the host can grow the buffer and run the pass again (with stats == nullptr).
+static __global__ void __launch_bounds__(256)
 bucketPairsKernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n,
-                  const uint32_t* __restrict__ flags, const uint32_t* __restrict__ segIndexExclusive,
-                  const uint32_t* __restrict__ segStart,
                   uint64_t minBucketSize, uint64_t maxBucketSize,
-                  unsigned long long* __restrict__ stats,          // COUNT pass only (may be null)
-                  unsigned long long* __restrict__ pairTotal,      // COUNT pass only: 64-bit total of all counts
-                  uint32_t* __restrict__ pairCounts,               // COUNT pass: out; EMIT pass: exclusive offsets in
-                  uint64_t* __restrict__ pairsOut)                 // EMIT pass
+                  unsigned long long* __restrict__ stats,          // may be null
+                  unsigned long long* __restrict__ cursor,         // pair hits reserved so far
+                  uint64_t* __restrict__ pairsOut, unsigned long long capacity)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < n;
-    uint32_t count = 0;
-    if(active) {
-        const uint32_t seg = segmentOf(flags, segIndexExclusive, i);
-        const uint32_t begin = segStart[seg];
-        const uint32_t end = segStart[seg + 1];
-        const uint64_t size = end - begin;
-        const uint32_t oread0 = vals[i];
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t count = 0, begin = 0, end = 0, oread0 = 0, hashHigh0 = 0;
+    if(i < n) {
+        const uint64_t key0 = keys[i];
+        const uint32_t bucket = uint32_t(key0 >> 32);
+        hashHigh0 = uint32_t(key0);
+        oread0 = vals[i];
+        begin = i; end = i + 1;
+        uint64_t size = 1;          // exact when <= maxBucketSize, else maxBucketSize + 1 = "crowded"
+        while(size <= maxBucketSize && begin > 0 && uint32_t(keys[begin - 1] >> 32) == bucket) { begin--; size++; }
+        while(size <= maxBucketSize && end < n && uint32_t(keys[end] >> 32) == bucket) { end++; size++; }
         const uint32_t readId0 = oread0 >> 1;
-        if(!EMIT && stats) {
+        if(stats) {
             const int cls = (size < minBucketSize) ? 0 : ((size > maxBucketSize) ? 2 : 1);
             atomicAdd(&stats[3ull * readId0 + cls], 1ull);
         }
         const uint64_t lowest = minBucketSize > 2 ? minBucketSize : 2;
-        uint64_t out = EMIT ? pairCounts[i] : 0;
         if(size >= lowest && size <= maxBucketSize) {
-            const uint32_t hashHigh0 = uint32_t(keys[i]);
             for(uint32_t j = begin; j < end; j++) {
-                if(uint32_t(keys[j]) != hashHigh0) continue;
-                const uint32_t oread1 = vals[j];
-                const uint32_t readId1 = oread1 >> 1;
-                if(readId1 <= readId0) continue;
-                if(EMIT) {
-                    const uint32_t strand = (oread0 ^ oread1) & 1u;        // 0 = same strand
-                    pairsOut[out++] = (uint64_t(readId0) << 32) | (uint64_t(readId1) << 1) | strand;
-                } else {
-                    count++;
-                }
+                if(uint32_t(keys[j]) == hashHigh0 && (vals[j] >> 1) > readId0) count++;
             }
-        }
-        if(!EMIT) pairCounts[i] = count;
+        } else end = begin;         // nothing to emit
     }
-    if(!EMIT) {
-        // Exact 64-bit total (the per-entry offsets are 32 bit; the host checks the total fits).
-        uint32_t warpSum = count;
+    // Room for the warp's hits: exclusive prefix over the lanes + one atomic.
+    uint32_t inclusive = count;
 #pragma unroll
-        for(int d = 16; d > 0; d >>= 1) warpSum += __shfl_down_sync(0xffffffffu, warpSum, d);
-        if((threadIdx.x & 31u) == 0 && warpSum) atomicAdd(pairTotal, (unsigned long long)warpSum);
+    for(int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inclusive, d);
+        if(lane >= unsigned(d)) inclusive += t;
+    }
+    const uint32_t warpTotal = __shfl_sync(0xffffffffu, inclusive, 31);
+    if(warpTotal == 0) return;
+    unsigned long long base = 0;
+    if(lane == 31) base = atomicAdd(cursor, (unsigned long long)warpTotal);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned long long out = base + (inclusive - count);
+    if(count == 0 || out + count > capacity) return;
+    const uint32_t readId0 = oread0 >> 1;
+    for(uint32_t j = begin; j < end; j++) {
+        if(uint32_t(keys[j]) != hashHigh0) continue;
+        const uint32_t oread1 = vals[j];
+        const uint32_t readId1 = oread1 >> 1;
+        if(readId1 <= readId0) continue;
+        const uint32_t strand = (oread0 ^ oread1) & 1u;        // 0 = same strand
+        pairsOut[out++] = (uint64_t(readId0) << 32) | (uint64_t(readId1) << 1) | strand;
     }
 }
 

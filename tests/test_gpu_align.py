@@ -128,6 +128,19 @@ def test_method4_small_cells_strict_and_containments(ctx):
              align4MaxDistanceFromBoundary=1000, maxBand=100, suppressContainments=1)
 
 
+@pytest.mark.parametrize("smem_cells", ["1", "6"])
+def test_method4_front_end_global_path(ctx, monkeypatch, smem_cells):
+    """The Align4 front end keeps a candidate's existing cells in shared memory when they fit; candidates with more
+    cells take the global-memory path. A tiny limit sends (nearly) every candidate through that path."""
+    monkeypatch.setenv("SHB_ALIGN4_SMEM_CELLS", smem_cells)
+    d, cand = _dataset(250, 14, 9)
+    _compare(ctx, d, cand[:600], alignMethod=4, k=14, maxSkip=100, maxDrift=100, maxTrim=100, minAlignedMarkerCount=10,
+             minAlignedFraction=0.1, align4DeltaX=50, align4DeltaY=20, align4MinEntryCountPerCell=1,
+             align4MaxDistanceFromBoundary=1000, maxBand=100)
+    _compare(ctx, d, cand[:600], alignMethod=4, k=14, maxSkip=100, maxDrift=100, maxTrim=100,
+             minAlignedMarkerCount=10, minAlignedFraction=0.1, maxBand=1000)
+
+
 def test_method4_random_pairs(ctx):
     d, _ = _dataset(120, 10, 21)
     rng = np.random.default_rng(5)
