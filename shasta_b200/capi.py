@@ -225,7 +225,6 @@ class Context:
         stats = np.zeros((self.read_count, 3), np.uint64) if want_stats else None
         _check(lib().shb_lowhash0_sharded(self._h, C.byref(params), C.byref(cand), C.byref(n), _ptr(stats), C.byref(res)))
         out = _records_to_array(cand, n.value)
-        lib().shb_free(cand)
         return out, stats, res
 
     def dist_timing(self):
@@ -280,7 +279,6 @@ class Context:
         _check(lib().shb_lowhash0(self._h, C.byref(params), C.byref(cand), C.byref(n), _ptr(stats), _ptr(summ),
                                   max_iter_summary, C.byref(res)))
         out = _records_to_array(cand, n.value)
-        lib().shb_free(cand)
         if summ is not None:
             summ = summ[:min(res.iterations, max_iter_summary)]
         return out, stats, summ, res
@@ -299,7 +297,6 @@ class Context:
                                                            C.byref(cand), C.byref(n), _ptr(stats), C.byref(res)))
         self.read_count = R
         out = _records_to_array(cand, n.value)
-        lib().shb_free(cand)
         return out, stats, res
 
 
@@ -376,9 +373,8 @@ def _owned_array(ptr, count, dtype):
 
 def candidates_to_records(cand):
     """uint32[n,3] (readId0, readId1, isSameStrand) -> n 12-byte OrientedReadPair records (as uint32[n,3])."""
-    c = np.ascontiguousarray(cand, dtype=np.uint32).reshape(-1, 3).copy()
-    c[:, 2] &= 1
-    return c
+    # The library reads byte 0 of the third word (0 / 1); no copy when the array already has the record layout.
+    return np.ascontiguousarray(cand, dtype=np.uint32).reshape(-1, 3)
 
 
 def compute_alignments(ctx: Context, candidates, options: AlignOptions):
@@ -489,7 +485,8 @@ def digest_compressed(records, ctoc, cdata):
 def _records_to_array(ptr, n):
     """12-byte OrientedReadPair records -> uint32[n,3] with column 2 = isSameStrand (byte 0 of the third word)."""
     if n == 0:
+        if ptr:
+            lib().shb_free(ptr)
         return np.zeros((0, 3), np.uint32)
-    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), (n, 3)).copy()
-    a[:, 2] &= 0xFF
-    return a
+    # No copy: the library writes the third word as 0 / 1 (byte 0 = isSameStrand, padding bytes zero).
+    return _owned_array(ptr, 3 * n, np.uint32).reshape(n, 3)

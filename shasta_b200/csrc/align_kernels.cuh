@@ -310,10 +310,14 @@ template<bool OrEqual> __device__ __forceinline__ void fmaPipeAddIfGreater(uint3
 //   bit 0 = the cell took a gap move (its score is gapIn + gap, not the diagonal's), bit 1 = the horizontal input was the
 //   larger gap input (meaningful when bit 0 is set). After the 16 steps of a block, step s of the block sits at bits
 //   2 * (15 - s). (The scan kernel keeps the older code format: 0 none, 1 diagonal, 2 vertical, 3 horizontal.)
-template<int C, bool Boundary> __device__ __forceinline__ void systolicSubChunk(
+// Step >= 0: the step's position in its 16-step block is a compile-time constant (fully unrolled block) and the trace word
+// was cleared at the start of the block, so the code is added in place (one multiply-add less per cell than shifting the
+// register); Step < 0: shift register.
+template<int C, bool Boundary, int Step = -1> __device__ __forceinline__ void systolicSubChunk(
     int32_t (&H)[C], uint32_t (&Tr)[C], const SubChunkLimits<C>& lim, int32_t i, uint32_t ai,
     int32_t below /* H(i, p0-1) */, int32_t top /* H(i-1, p0+C) */, const uint32_t* bw, DpScores sc, FmaUnits u)
 {
+    constexpr int32_t kCodeUnit = (Step >= 0) ? int32_t(1u << (2 * (15 - (Step >= 0 ? Step : 0)))) : 1;      // bit 0 of this step's code
     int32_t vertIn = below;
     const int32_t matchBonus = sc.match - sc.mismatch;
 #pragma unroll
@@ -324,10 +328,16 @@ template<int C, bool Boundary> __device__ __forceinline__ void systolicSubChunk(
         // max(diag, vert, horz) as one max and one add-max; the tie order (include/shb_dp_policy.h) only enters the trace.
         const int32_t gapIn = max(vertIn, horzIn);
         int32_t h = __viaddmax_s32(gapIn, lim.gap[c], diag);
-        uint32_t tr = fmaPipeMul(Tr[c], uint32_t(u.four));                      // shift the older codes up by two bits
-        if(SHB_DP_DIAG_WINS_TIES) fmaPipeAddIfGreater<false>(tr, h, diag, u.one, u.one);
-        else fmaPipeAddIfGreater<true>(tr, fmaPipeAdd(gapIn, lim.gap[c], u.one), diag, u.one, u.one);
-        fmaPipeAddIfGreater<!SHB_DP_VERT_BEFORE_HORZ>(tr, horzIn, vertIn, u.one, u.two);
+        uint32_t tr = (Step >= 0) ? Tr[c] : fmaPipeMul(Tr[c], uint32_t(u.four));      // shift the older codes up by two bits
+        if(Step >= 0) {
+            if(SHB_DP_DIAG_WINS_TIES) fmaPipeAddIfGreater<false>(tr, h, diag, u.one, kCodeUnit);
+            else fmaPipeAddIfGreater<true>(tr, fmaPipeAdd(gapIn, lim.gap[c], u.one), diag, u.one, kCodeUnit);
+            fmaPipeAddIfGreater<!SHB_DP_VERT_BEFORE_HORZ>(tr, horzIn, vertIn, u.one, 2 * kCodeUnit);
+        } else {
+            if(SHB_DP_DIAG_WINS_TIES) fmaPipeAddIfGreater<false>(tr, h, diag, u.one, u.one);
+            else fmaPipeAddIfGreater<true>(tr, fmaPipeAdd(gapIn, lim.gap[c], u.one), diag, u.one, u.one);
+            fmaPipeAddIfGreater<!SHB_DP_VERT_BEFORE_HORZ>(tr, horzIn, vertIn, u.one, u.two);
+        }
         Tr[c] = tr;
         if(Boundary) h = (i == lim.first[c]) ? 0 : h;
         H[c] = h;
@@ -370,42 +380,60 @@ template<int C> struct SystolicState {
 
 // 16 steps. Checked = false: no boundary cell and no end cell can occur in these steps for any lane, and every k-mer
 // the lanes load lies inside its row (see the block ranges in bandedOverlapDpSystolic), so the loads are unconditional.
+template<int C, bool Checked, int Step> __device__ __forceinline__ void systolicStep(
+    SystolicState<C>& s, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc, FmaUnits fu)
+{
+    uint32_t ai = 0xfffffffeu;
+    uint32_t bIn = 0xffffffffu;                     // enters the window after this step
+    if(Checked) {
+        if(uint32_t(s.i - 1) < uint32_t(nx)) ai = __ldg(s.ap);
+        if(uint32_t(s.jNext) < uint32_t(ny)) bIn = __ldg(s.bNext);
+    } else {
+        ai = __ldg(s.ap);
+        bIn = __ldg(s.bNext);
+    }
+    // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i
+    // (lane 0: its own value comes back, which only the barrier offset p = 0 reads).
+    const int32_t below = __shfl_up_sync(0xffffffffu, s.HB[C - 1], 1);
+    systolicSubChunk<C, Checked, Step>(s.HA, s.TA, s.limA, s.i, ai, below, s.HB[0], s.bw, sc, fu);
+    // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1
+    // (lane 31: its own value comes back, read only by barrier / padding offsets).
+    const int32_t top = __shfl_down_sync(0xffffffffu, s.HA[0], 1);
+    systolicSubChunk<C, Checked, Step>(s.HB, s.TB, s.limB, s.i, ai, s.HA[C - 1], top, s.bw + C, sc, fu);
+    if(Checked) {
+        // End-cell bookkeeping for both sub-chunks: offsets eA + cStar (row ny) and, in column nx, all rows.
+        const int32_t cStar = rowEndA - s.i;
+        if((uint32_t(cStar) < uint32_t(2 * C) || s.i == nx) && uint32_t(s.i) <= uint32_t(nx)) {
+            systolicEndCells<C>(s.HA, s.limA, eA, s.i, cStar, nx, s.bestScore, s.bestI, s.bestJ);
+            systolicEndCells<C>(s.HB, s.limB, eB, s.i, cStar - C, nx, s.bestScore, s.bestI, s.bestJ);
+        }
+    }
+    // Next column: every offset moves one row down.
+#pragma unroll
+    for(int k = 0; k + 1 < 2 * C; k++) s.bw[k] = s.bw[k + 1];
+    s.bw[2 * C - 1] = bIn;
+    s.i++; s.ap++; s.bNext++; s.jNext++;
+}
+
+template<int C, bool Checked, int... Steps> __device__ __forceinline__ void systolicStepsInPlace(
+    SystolicState<C>& s, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc, FmaUnits fu,
+    std::integer_sequence<int, Steps...>)
+{
+    (systolicStep<C, Checked, Steps>(s, eA, eB, rowEndA, nx, ny, sc, fu), ...);
+}
+
 template<int C, bool Checked> __device__ __forceinline__ void systolicBlock(
     SystolicState<C>& s, int32_t eA, int32_t eB, int32_t rowEndA, int32_t nx, int32_t ny, DpScores sc, FmaUnits fu)
 {
-    constexpr int kUnroll = (C == 1) ? 16 : (C == 2) ? 8 : (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
-#pragma unroll kUnroll
-    for(int step = 0; step < 16; step++) {
-        uint32_t ai = 0xfffffffeu;
-        uint32_t bIn = 0xffffffffu;                     // enters the window after this step
-        if(Checked) {
-            if(uint32_t(s.i - 1) < uint32_t(nx)) ai = __ldg(s.ap);
-            if(uint32_t(s.jNext) < uint32_t(ny)) bIn = __ldg(s.bNext);
-        } else {
-            ai = __ldg(s.ap);
-            bIn = __ldg(s.bNext);
-        }
-        // Even step: sub-chunk A of column i. Its vertical input is the last offset of lane-1's B at column i
-        // (lane 0: its own value comes back, which only the barrier offset p = 0 reads).
-        const int32_t below = __shfl_up_sync(0xffffffffu, s.HB[C - 1], 1);
-        systolicSubChunk<C, Checked>(s.HA, s.TA, s.limA, s.i, ai, below, s.HB[0], s.bw, sc, fu);
-        // Odd step: sub-chunk B of column i. Its horizontal input is the first offset of lane+1's A at column i-1
-        // (lane 31: its own value comes back, read only by barrier / padding offsets).
-        const int32_t top = __shfl_down_sync(0xffffffffu, s.HA[0], 1);
-        systolicSubChunk<C, Checked>(s.HB, s.TB, s.limB, s.i, ai, s.HA[C - 1], top, s.bw + C, sc, fu);
-        if(Checked) {
-            // End-cell bookkeeping for both sub-chunks: offsets eA + cStar (row ny) and, in column nx, all rows.
-            const int32_t cStar = rowEndA - s.i;
-            if((uint32_t(cStar) < uint32_t(2 * C) || s.i == nx) && uint32_t(s.i) <= uint32_t(nx)) {
-                systolicEndCells<C>(s.HA, s.limA, eA, s.i, cStar, nx, s.bestScore, s.bestI, s.bestJ);
-                systolicEndCells<C>(s.HB, s.limB, eB, s.i, cStar - C, nx, s.bestScore, s.bestI, s.bestJ);
-            }
-        }
-        // Next column: every offset moves one row down.
+    if constexpr(C <= 2) {
+        // Fully unrolled: every step adds its trace code at its own bit position of a cleared word.
 #pragma unroll
-        for(int k = 0; k + 1 < 2 * C; k++) s.bw[k] = s.bw[k + 1];
-        s.bw[2 * C - 1] = bIn;
-        s.i++; s.ap++; s.bNext++; s.jNext++;
+        for(int c = 0; c < C; c++) { s.TA[c] = 0; s.TB[c] = 0; }
+        systolicStepsInPlace<C, Checked>(s, eA, eB, rowEndA, nx, ny, sc, fu, std::make_integer_sequence<int, 16>{});
+    } else {
+        constexpr int kUnroll = (C <= 4) ? 4 : (C <= 8) ? 2 : 1;
+#pragma unroll kUnroll
+        for(int step = 0; step < 16; step++) systolicStep<C, Checked, -1>(s, eA, eB, rowEndA, nx, ny, sc, fu);
     }
 }
 

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <utility>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>

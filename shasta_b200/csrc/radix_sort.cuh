@@ -81,6 +81,17 @@ constexpr unsigned long long kStatusValueMask = (1ull << kStatusTagShift) - 1ull
 
 // The pass kernel runs 512 threads x 8 items on the same 4096-item tile: half the registers per thread of a 256 x 16
 // organisation, so two blocks (32 warps) stay resident per SM and hide the shared-memory / match latencies of the ranking.
+__device__ __forceinline__ unsigned long long loadStatus(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void storeStatus(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 constexpr int kOnesweepThreads = 512;
 constexpr int kOnesweepItems = kSortTile / kOnesweepThreads;
 
@@ -89,7 +100,7 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
                     const uint32_t* __restrict__ valsIn, uint32_t* __restrict__ valsOut,
                     uint32_t n, int shift, uint32_t digitMask,
                     const unsigned long long* __restrict__ digitStart,      // [256] of this pass
-                    volatile unsigned long long* __restrict__ status,        // [numTiles * 256]
+                    unsigned long long* __restrict__ status,                 // [numTiles * 256]
                     uint32_t* __restrict__ ticket, uint32_t tagBase)
 {
     constexpr int kWarps = kOnesweepThreads / 32;
@@ -124,26 +135,33 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
         key[r] = valid ? keysIn[tileBegin + local] : ~0ull;
         if(HAS_VALUES) val[r] = valid ? valsIn[tileBegin + local] : 0u;
     }
+    // All the match operations first (independent, so they pipeline), then per round one shared-memory atomic by each
+    // digit group's first lane (returns the group's base rank and reserves its items) and one shuffle to hand the base to
+    // the group: the rounds form no dependent chain through shared memory, and a warp's atomics on one counter are
+    // performed in program order, which keeps the ranking stable.
+    uint32_t digit[kOnesweepItems];
+    unsigned peers[kOnesweepItems];
 #pragma unroll
     for(int r = 0; r < kOnesweepItems; r++) {
         const uint32_t local = warp * (32u * kOnesweepItems) + uint32_t(r) * 32u + lane;
-        const bool valid = local < tileCount;
-        const uint32_t d = valid ? (uint32_t(key[r] >> shift) & digitMask) : uint32_t(kRadix);      // invalid slots: digit 256
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t rankInRound = __popc(peers & ((1u << lane) - 1u));
+        digit[r] = (local < tileCount) ? (uint32_t(key[r] >> shift) & digitMask) : uint32_t(kRadix);      // invalid slots: digit 256
+        peers[r] = __match_any_sync(0xffffffffu, digit[r]);
+    }
+#pragma unroll
+    for(int r = 0; r < kOnesweepItems; r++) {
+        const uint32_t rankInRound = __popc(peers[r] & ((1u << lane) - 1u));
+        const int leader = __ffs(int(peers[r])) - 1;
         uint32_t base = 0;
-        if(valid) base = warpHist[warp][d];
-        __syncwarp();
-        if(valid && rankInRound == 0) warpHist[warp][d] = base + __popc(peers);
-        __syncwarp();
-        slot[r] = d | ((base + rankInRound) << 9);
+        if(rankInRound == 0 && digit[r] < uint32_t(kRadix)) base = atomicAdd(&warpHist[warp][digit[r]], uint32_t(__popc(peers[r])));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        slot[r] = digit[r] | ((base + rankInRound) << 9);
     }
     __syncthreads();
 
     // Per digit (thread d): the tile's count, the start of every warp's items inside the digit's run.
     const unsigned long long tagCount = (unsigned long long)(tagBase) << kStatusTagShift;
     const unsigned long long tagPrefix = (unsigned long long)(tagBase + 1u) << kStatusTagShift;
-    volatile unsigned long long* myStatus = status + uint64_t(tile) * kRadix + threadIdx.x;
+    unsigned long long* myStatus = status + uint64_t(tile) * kRadix + threadIdx.x;
     uint32_t count = 0, inc = 0;
     if(ownsDigit) {
 #pragma unroll
@@ -152,7 +170,7 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
             warpHist[w][threadIdx.x] = count;
             count += c;
         }
-        *myStatus = tagCount | count;
+        storeStatus(myStatus, tagCount | count);
         // exclusive scan of the counts over the digits -> localOffset
         inc = count;
 #pragma unroll
@@ -182,29 +200,35 @@ radixOnesweepKernel(const uint64_t* __restrict__ keysIn, uint64_t* __restrict__ 
         }
     }
 
-    // Look-back, a window of kLookback earlier tiles per round trip: when a wave of tiles reaches this point at about the
-    // same time, tile j of the wave has to walk back over about j/2 tiles that have only published their counts; reading
-    // one tile per dependent load would make that hundreds of serial L2 round trips per tile.
+    // Look-back. In the steady state the previous tile has already published its inclusive prefix and ONE load ends the
+    // walk; only when it has not (the first wave of tiles, which all reach this point together) does the walk continue,
+    // and then over a window of earlier tiles per round trip: tile j of such a wave has to pass about j/2 tiles that have
+    // published only their counts. A status word carries its own tag and value, so relaxed gpu-scope accesses are enough.
     if(ownsDigit) {
-        constexpr int kLookback = 16;
         unsigned long long earlier = 0;
-        for(int64_t t = int64_t(tile) - 1; t >= 0; ) {
+        int64_t t = int64_t(tile) - 1;
+        if(t >= 0) {
+            const unsigned long long sw = loadStatus(status + uint64_t(t) * kRadix + threadIdx.x);
+            const unsigned long long tag = sw & ~kStatusValueMask;
+            if(tag == tagPrefix) { earlier = sw & kStatusValueMask; t = -1; }
+            else if(tag == tagCount) { earlier = sw & kStatusValueMask; t--; }
+        }
+        constexpr int kLookback = 8;
+        while(t >= 0) {
             unsigned long long window[kLookback];
 #pragma unroll
-            for(int k = 0; k < kLookback; k++) window[k] = (t - k >= 0) ? status[uint64_t(t - k) * kRadix + threadIdx.x] : tagPrefix;
+            for(int k = 0; k < kLookback; k++) window[k] = (t - k >= 0) ? loadStatus(status + uint64_t(t - k) * kRadix + threadIdx.x) : tagPrefix;
             bool done = false;
 #pragma unroll
             for(int k = 0; k < kLookback; k++) {
-                if(done) continue;
                 const unsigned long long sw = window[k];
                 const unsigned long long tag = sw & ~kStatusValueMask;
-                if(tag == tagPrefix) { earlier += sw & kStatusValueMask; t = -1; done = true; }         // (also the virtual tile -1: value 0)
-                else if(tag == tagCount) { earlier += sw & kStatusValueMask; t--; }
-                else done = true;       // that tile has not published yet (it is running: tiles start in ticket order): read again from it
+                const bool isPrefix = tag == tagPrefix, isCount = tag == tagCount;
+                if(!done && (isPrefix || isCount)) { earlier += sw & kStatusValueMask; t = isPrefix ? -1 : t - 1; }
+                done = done || !isCount;        // a prefix ends the walk; an unpublished tile is read again (it is running: tiles start in ticket order)
             }
         }
-        __threadfence();
-        *myStatus = tagPrefix | (earlier + count);
+        storeStatus(myStatus, tagPrefix | (earlier + count));
         digitBase[threadIdx.x] = digitStart[threadIdx.x] + earlier;
     }
     __syncthreads();
@@ -284,7 +308,7 @@ bool radixSort(uint64_t* keysA, uint64_t* keysB, uint32_t* valsA, uint32_t* vals
         SHB_LAUNCH((radixOnesweepKernel<HAS_VALUES>), numTiles, kOnesweepThreads, kDynamicBytes, stream,
                    (const uint64_t*)kin, kout, (const uint32_t*)vin, vout, uint32_t(n), passes.shift[p], passes.mask[p],
                    (const unsigned long long*)(ws.hist.get() + uint64_t(p) * kRadix),
-                   (volatile unsigned long long*)ws.status.get(), tickets + 2 * p, ws.nextTag);
+                   ws.status.get(), tickets + 2 * p, ws.nextTag);
         ws.nextTag += 2;
         inB = !inB;
     }
