@@ -64,6 +64,7 @@ public:
         // Grow geometrically to amortise repeated appends.
         uint64_t newCap = n;
         if(keep && capacity_) newCap = (n > capacity_ + capacity_/2) ? n : capacity_ + capacity_/2;
+        if(!keep) release();            // nothing to preserve: return the old block first (the buffers can be tens of GB)
         T* p = nullptr;
         SHB_CUDA(cudaMalloc(&p, (newCap ? newCap : 1) * sizeof(T)));
         if(keep && ptr_ && capacity_) {

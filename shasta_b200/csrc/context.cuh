@@ -21,6 +21,7 @@ struct LowHashState {
     shb_lowhash_params p{};
     uint64_t log2BucketCount = 0, bucketMask = 0, hashThreshold = 0, capacity = 0;
     uint32_t readBits = 1, slabGroup = 0;
+    bool aggregateByRead = false;       // pair hits are counted per read in shared memory before they reach the accumulator
     LowHashAccumulator acc;
     uint64_t lowHashCount = 0, pairCount = 0, sweepLaunches = 0;
     uint64_t emittedCount = 0, candidateDigest = 0;     // of the last shb_lowhash_emit
@@ -54,6 +55,8 @@ struct shb_context {
 
     // ---- LowHash buffers (see lowhash.cu) -----------------------------------------------------
     shb::DeviceBuffer<uint64_t> sweepKeys;  shb::DeviceBuffer<uint32_t> sweepVals;
+    shb::DeviceBuffer<uint32_t> sweepTileFirstRead;     // per sweep tile: the oriented read that holds its first position
+    uint64_t sweepTileGeneration = ~0ull;               // markerGeneration the table was built for
     shb::DeviceBuffer<uint64_t> entryKeysTmp; shb::DeviceBuffer<uint32_t> entryValsTmp;
     shb::DeviceBuffer<uint32_t> flagsBuf, indexBuf, segStartBuf, countsBuf;
     shb::DeviceBuffer<uint64_t> pairsA, pairsB;

@@ -36,9 +36,10 @@ void lowhashBegin(shb_context* c, const shb_lowhash_params& p);
 void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsigned long long* counts);
 void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uint64_t n64);
 void lowhashLocalPairs(shb_context* c, uint64_t** keys, uint32_t** counts, uint64_t* n);
+void lowhashReleaseLargeScratch(shb_context* c);
 void lowhashSetPairs(shb_context* c, const uint64_t* keys, const uint32_t* counts, uint64_t n);
 uint64_t lowhashEmitDevice(shb_context* c);
-uint32_t nextSweepGroup(uint64_t remaining);
+uint32_t nextSweepGroup(uint64_t remaining, uint64_t slabCapacity);
 void devicePartition(shb_context* c, uint64_t* keys, uint32_t* vals, uint64_t n, uint32_t shift, uint32_t bits,
                      uint64_t* counts, uint64_t** keysOut, uint32_t** valsOut);
 void computeAlignments(shb_context* c, const void* candidatesHost, uint64_t n, const shb_align_options& o,
@@ -228,7 +229,7 @@ void lowhash0Sharded(shb_context* c, const shb_lowhash_params& p, void** candida
 
     uint64_t iteration = 0;
     while(iteration < p.minHashIterationCount) {
-        const uint32_t group = nextSweepGroup(p.minHashIterationCount - iteration);
+        const uint32_t group = nextSweepGroup(p.minHashIterationCount - iteration, S.capacity);
         auto ta = std::chrono::steady_clock::now();
         unsigned long long counts[kMaxFusedIterations];
         lowhashSweep(c, iteration, group, counts);
@@ -397,6 +398,7 @@ void lowhash0Sharded(shb_context* c, const shb_lowhash_params& p, void** candida
     SHB_CUDA(cudaEventRecord(total.b, st));
     SHB_CUDA(cudaStreamSynchronize(st));
     S.candidateDigest = digest;
+    lowhashReleaseLargeScratch(c);
     d.timing.finalSeconds = seconds(tFinal, std::chrono::steady_clock::now());
     d.timing.totalSeconds = seconds(t0, std::chrono::steady_clock::now());
     float totalMs = 0.f;

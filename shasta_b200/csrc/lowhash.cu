@@ -43,9 +43,13 @@ template<class T> T readScalar(const T* dev, cudaStream_t stream)
 // unrolled kernel for; the iteration loop of lowhash0 cuts the iterations into groups of these sizes.
 const uint32_t kUnrolledGroups[] = {16, 10, 8, 4, 2, 1};
 
-uint32_t nextSweepGroupImpl(uint64_t remaining)
+// Largest supported group that fits the remaining iterations and keeps the group's slabs (12 bytes per entry) within a
+// fixed memory budget (HiFi at 2 M reads: 277 M entries per slab).
+uint32_t nextSweepGroupImpl(uint64_t remaining, uint64_t slabCapacity)
 {
-    for(uint32_t g : kUnrolledGroups) if(g <= remaining) return g;
+    constexpr uint64_t kSlabBudgetBytes = 16ull << 30;
+    const uint64_t fit = std::max<uint64_t>(1, kSlabBudgetBytes / (12ull * std::max<uint64_t>(slabCapacity, 1)));
+    for(uint32_t g : kUnrolledGroups) if(g <= remaining && g <= fit) return g;
     return 1;
 }
 
@@ -168,6 +172,7 @@ void reduceRawPairs(shb_context* c, Accumulator& acc, uint32_t readBits)
     SHB_LAUNCH(uniqueCountsKernel, ceilDiv(numUnique, 256), 256, 0, st, sortedPairs,
                (const uint32_t*)c->segStartBuf.get(), numUnique,
                accKeys(c, acc) + acc.count, accVals(c, acc) + acc.count);
+    if(std::getenv("SHB_LOWHASH_VERBOSE")) fprintf(stderr, "[shasta_b200] raw pair hits %u -> %u distinct pairs\n", np, numUnique);
     acc.count += numUnique;
     acc.sorted = first;
     acc.rawCount = 0;
@@ -192,7 +197,7 @@ uint64_t countHighFrequency(shb_context* c, const Accumulator& acc, uint64_t min
 
 } // namespace
 
-uint32_t nextSweepGroup(uint64_t remaining) { return nextSweepGroupImpl(remaining); }
+uint32_t nextSweepGroup(uint64_t remaining, uint64_t slabCapacity) { return nextSweepGroupImpl(remaining, slabCapacity); }
 
 
 // ---------------------------------------------------------------------------------------------
@@ -219,6 +224,11 @@ void lowhashBegin(shb_context* c, const shb_lowhash_params& p)
     LowHashState& S = lowhashState(c);
     S = LowHashState();
     S.p = p;
+    // Count the pair hits per read before they reach the accumulator when one read pair collides many times per iteration
+    // (hashFraction x overlap length: HiFi 0.05 -> ~25 hits per pair and iteration; at Nanopore's 0.01 both organisations
+    // cost the same and the raw buffer is kept).
+    S.aggregateByRead = p.hashFraction >= 0.03;
+    if(const char* e = std::getenv("SHB_LOWHASH_AGGREGATE")) S.aggregateByRead = std::atoi(e) != 0;
     if(const char* e = std::getenv("SHB_LOWHASH_RAW_LIMIT")) {          // test hook: force the intermediate reductions
         const long long v = std::atoll(e);
         if(v > 0) S.acc.rawLimit = uint64_t(v);
@@ -275,6 +285,7 @@ void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsig
         a.bucketMask = S.bucketMask;
         a.iterationBegin = uint32_t(iterationBegin);
         a.iterationCount = group;
+        for(uint32_t k = 0; k < uint32_t(kMaxFusedIterations); k++) a.seeds[k] = (uint32_t(iterationBegin) + k) * 37u;
         a.keys = c->sweepKeys.get();
         a.vals = c->sweepVals.get();
         a.capacity = S.capacity;
@@ -283,6 +294,14 @@ void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsig
             const double expected = double(kSweepTile) * double(group) * S.p.hashFraction;
             a.queueCapacity = uint32_t(std::min<double>(kSweepQueueMax, std::max<double>(kSweepQueueMin, 1.5 * expected + 64.)));
         }
+        const uint32_t tileCount = uint32_t(ceilDiv(M, kSweepTile));
+        if(tileCount && (c->sweepTileGeneration != c->markerGeneration || c->sweepTileFirstRead.capacity() < tileCount)) {
+            c->sweepTileFirstRead.reserve(tileCount);
+            SHB_LAUNCH(sweepTileReadsKernel, ceilDiv(tileCount, 256), 256, 0, st, (const uint64_t*)c->toc.get(), a.orientedReadCount,
+                       tileCount, c->sweepTileFirstRead.get());
+            c->sweepTileGeneration = c->markerGeneration;
+        }
+        a.tileFirstRead = c->sweepTileFirstRead.get();
         const bool run = M >= S.p.m && M > 0;
         if(run) {
             SHB_CUDA(cudaEventRecord(sweepTimer.a, st));
@@ -325,6 +344,49 @@ void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uin
     const uint64_t* keys = inTmp ? c->entryKeysTmp.get() : keysA;
     const uint32_t* vals = inTmp ? c->entryValsTmp.get() : valsA;
 
+    if(S.aggregateByRead) {
+        // Entries grouped by read (stable sort of (readId, entry index)), each read's partners counted in shared memory.
+        uint64_t* otherKeys = inTmp ? keysA : c->entryKeysTmp.get();
+        uint32_t* otherVals = inTmp ? valsA : c->entryValsTmp.get();
+        c->pairsA.reserve(n);           // bucket spans (uint2 per entry)
+        c->pairsB.reserve(n);           // sort ping-pong
+        c->countsBuf.reserve(n);
+        uint2* span = reinterpret_cast<uint2*>(c->pairsA.get());
+        SHB_LAUNCH(bucketSpanKernel, ceilDiv(n, 256), 256, 0, st, keys, vals, n, p.minBucketSize, p.maxBucketSize, c->stats.get(), span);
+        SHB_LAUNCH(readKeysKernel, ceilDiv(n, 256), 256, 0, st, vals, n, otherKeys, otherVals);
+        const int readRange[1][2] = {{0, int(S.readBits)}};
+        const bool flipped = radixSort<true>(otherKeys, c->pairsB.get(), otherVals, c->countsBuf.get(), n, readRange, 1, c->sortWs, st);
+        const uint64_t* sortedReadKeys = flipped ? c->pairsB.get() : otherKeys;
+        const uint32_t* order = flipped ? c->countsBuf.get() : otherVals;
+        const uint32_t numReads = buildSegments(c, sortedReadKeys, n, 0);
+        unsigned long long* cursor = c->scalars.get() + 40;
+        unsigned long long* hits = c->scalars.get() + 43;
+        uint32_t maxProbes = kPairTableMaxProbes;
+        if(const char* e = std::getenv("SHB_LOWHASH_TABLE_PROBES")) maxProbes = uint32_t(std::max(1, std::atoi(e)));     // test hook: force the overflow path
+        for(;;) {
+            if(accKeys(c, S.acc) == nullptr) accReserve(c, S.acc, std::max<uint64_t>(S.acc.count + n, 1ull << 20));
+            const uint64_t liveCapacity = S.acc.inB ? c->accKeysB.capacity() : c->accKeysA.capacity();
+            const uint64_t room = liveCapacity - S.acc.count;
+            SHB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+            SHB_CUDA(cudaMemsetAsync(hits, 0, sizeof(unsigned long long), st));
+            SHB_LAUNCH(readPairsKernel, ceilDiv(numReads, kPairTableWarps), kPairTableWarps * 32, 0, st, keys, vals, (const uint2*)span,
+                       sortedReadKeys, order, (const uint32_t*)c->segStartBuf.get(), numReads, cursor, hits,
+                       accKeys(c, S.acc) + S.acc.count, accVals(c, S.acc) + S.acc.count, (unsigned long long)room, maxProbes);
+            unsigned long long totals[4];      // scalars 40..43: cursor, (candidate digest), (marker total), hits
+            SHB_CUDA(cudaMemcpyAsync(totals, cursor, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            SHB_CUDA(cudaStreamSynchronize(st));
+            if(totals[0] <= room) {
+                S.acc.count += totals[0];
+                if(totals[0]) S.acc.sorted = false;
+                S.pairCount += totals[3];
+                break;
+            }
+            accReserve(c, S.acc, S.acc.count + totals[0] + totals[0] / 16);
+        }
+        if(S.acc.count > (1ull << 30)) mergeAccumulator(c, S.acc, S.readBits);
+        return;
+    }
+
     // One pass: per-read statistics and the pair hits, appended (in any order) to the raw pair buffer; sorting and counting
     // happen once for many iterations. The pass reports the exact number of hits; if they did not fit, the buffer grows
     // (after a reduction of what it holds, when that would exceed the limit) and the pass runs again without the statistics.
@@ -349,7 +411,8 @@ void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uin
         if(S.acc.rawCount && S.acc.rawCount + np64 > S.acc.rawLimit) reduceRawPairs(c, S.acc, S.readBits);
         const uint64_t iterations = std::max<uint64_t>(1, p.minHashIterationCount);
         const uint64_t want = S.acc.rawCount + np64;
-        c->pairsA.reserve(std::max<uint64_t>(want, std::min<uint64_t>(S.acc.rawLimit, (np64 + np64 / 8) * iterations)), true, st);
+        c->pairsA.reserve(std::max<uint64_t>(want + want / 32, std::min<uint64_t>(S.acc.rawLimit, (np64 + np64 / 8) * iterations)),
+                          S.acc.rawCount != 0, st);
     }
     if(S.acc.rawCount > S.acc.rawLimit) reduceRawPairs(c, S.acc, S.readBits);
 }
@@ -406,6 +469,28 @@ uint64_t lowhashEmitDevice(shb_context* c)
     }
     S.emittedCount = nOut;
     return nOut;
+}
+
+// The scratch of a LowHash0 run stays allocated for the next run unless it is huge (HiFi at 2 M reads: ~100 GB of pair
+// buffers), in which case it is returned so that the alignment phase that follows finds room.
+void lowhashReleaseLargeScratch(shb_context* c)
+{
+    auto bytes = [](auto& b) { return uint64_t(b.capacity()) * sizeof(*b.get()); };
+    const uint64_t total = bytes(c->pairsA) + bytes(c->pairsB) + bytes(c->flagsBuf) + bytes(c->indexBuf) + bytes(c->segStartBuf) +
+                           bytes(c->countsBuf) + bytes(c->scanWs) + bytes(c->accKeysA) + bytes(c->accKeysB) + bytes(c->accValsA) +
+                           bytes(c->accValsB) + bytes(c->entryKeysTmp) + bytes(c->entryValsTmp) + bytes(c->sweepKeys) +
+                           bytes(c->sweepVals) + bytes(c->partKeys) + bytes(c->partVals);
+    if(total < (64ull << 30)) return;
+    SHB_CUDA(cudaStreamSynchronize(c->stream));
+    c->pairsA.release(); c->pairsB.release(); c->flagsBuf.release(); c->indexBuf.release(); c->segStartBuf.release();
+    c->countsBuf.release(); c->scanWs.release(); c->accKeysA.release(); c->accKeysB.release(); c->accValsA.release();
+    c->accValsB.release(); c->entryKeysTmp.release(); c->entryValsTmp.release(); c->sweepKeys.release(); c->sweepVals.release();
+    c->partKeys.release(); c->partVals.release();
+    c->sortWs.status.release();
+    LowHashState& S = lowhashState(c);
+    const uint64_t rawLimit = S.acc.rawLimit;
+    S.acc = LowHashAccumulator();
+    S.acc.rawLimit = rawLimit;
 }
 
 // ... and copied to a host buffer (shb_free) of 12-byte records.
@@ -495,7 +580,7 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
                         "MinHash.alignmentCandidatesPerRead was not reached after 4096 LowHash iterations.");
         } else {
             if(iteration == p.minHashIterationCount) break;
-            if(!perIteration) group = nextSweepGroup(p.minHashIterationCount - iteration);
+            if(!perIteration) group = nextSweepGroup(p.minHashIterationCount - iteration, S.capacity);
         }
         unsigned long long counts[kMaxFusedIterations];
         lowhashSweep(c, iteration, group, counts);
@@ -521,6 +606,7 @@ void lowhash0(shb_context* c, const shb_lowhash_params& p,
     SHB_CUDA(cudaStreamSynchronize(st));
     float totalMs = 0.f;
     SHB_CUDA(cudaEventElapsedTime(&totalMs, totalTimer.a, totalTimer.b));
+    lowhashReleaseLargeScratch(c);
     if(result) {
         result->iterations = iteration;
         result->log2BucketCount = S.log2BucketCount;

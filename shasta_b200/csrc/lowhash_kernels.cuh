@@ -59,6 +59,7 @@ constexpr int kSweepTile = kSweepThreads * kSweepPositionsPerThread;      // 204
 // (205 for K = 10 and hashFraction 0.01; 1640 for K = 16 and the HiFi configuration's 0.05) with 50 % slack.
 constexpr uint32_t kSweepQueueMin = 256, kSweepQueueMax = 6144;
 constexpr int kMaxTemplatedM = 8;
+constexpr int kSweepTileReads = 32;                   // toc entries staged per tile (more reads than that: global binary search)
 
 struct SweepArgs {
     const uint32_t* kmerIds;        // local k-mer ids
@@ -77,7 +78,14 @@ struct SweepArgs {
     uint64_t capacity;
     unsigned long long* counts;     // [iterationCount]
     uint32_t queueCapacity;         // entries of the shared-memory low-hash queue (16 bytes each, dynamic shared memory)
+    const uint32_t* tileFirstRead;  // per tile: largest local oriented read r with toc[r] <= first position of the tile
+    uint32_t seeds[kMaxFusedIterations];    // MurmurHash seed of every fused iteration, (iterationBegin + s) * 37: read straight
+                                            // from the constant bank by the hot loop's xor
 };
+
+// tileFirstRead[t] for every sweep tile (built once per marker set).
+static __global__ void sweepTileReadsKernel(const uint64_t* __restrict__ toc, uint32_t orientedReadCount, uint32_t tileCount,
+                                            uint32_t* __restrict__ tileFirstRead);
 
 // 64-bit values as two 32-bit halves: the hash is pure 32-bit integer work on this machine, and keeping the halves apart
 // stops the compiler from routing them through 64-bit adds with carry chains.
@@ -142,6 +150,20 @@ template<int MM> __device__ __forceinline__ uint64_t featureHash(const uint32_t*
     return whole(h);
 }
 
+static __global__ void sweepTileReadsKernel(const uint64_t* __restrict__ toc, uint32_t orientedReadCount, uint32_t tileCount,
+                                            uint32_t* __restrict__ tileFirstRead)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= tileCount) return;
+    const uint64_t p = uint64_t(t) * kSweepTile;
+    uint32_t lo = 0, hi = orientedReadCount;            // largest lo with toc[lo] <= p (toc[0] = 0)
+    while(hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if(toc[mid] <= p) lo = mid; else hi = mid;
+    }
+    tileFirstRead[t] = lo;
+}
+
 // Which oriented read does marker position p belong to, and is the feature starting at p valid
 // (inside one read, read not palindromic: src/LowHash0.cpp:325,337,344)? Returns the LOCAL
 // oriented read index or 0xffffffff.
@@ -167,11 +189,13 @@ template<int MM, int KK> __global__ void __launch_bounds__(kSweepThreads)
 lowhashSweepKernel(const SweepArgs a)
 {
     constexpr int kHalo = 2 * kMaxFusedIterations;       // >= any supported m (generic path caps m at 32)
-    __shared__ uint32_t sk[kSweepTile + kHalo];
+    __shared__ __align__(16) uint32_t sk[kSweepTile + kHalo];
     extern __shared__ uint64_t queueHash[];              // a.queueCapacity low hashes queued per block, then per entry:
     uint32_t* queueMeta = reinterpret_cast<uint32_t*>(queueHash + a.queueCapacity);   // in: local | s<<16   out: rank within (block, seed) | s<<24, or ~0
     uint32_t* queueRead = queueMeta + a.queueCapacity;                               // oriented read (global)
     __shared__ uint32_t queueCount;
+    __shared__ unsigned long long tileToc[kSweepTileReads + 1];      // toc[tileFirstRead + k]
+    __shared__ uint32_t tileFirstRead;
     __shared__ uint32_t seedCount[kMaxFusedIterations];
     __shared__ unsigned long long seedBase[kMaxFusedIterations];
 
@@ -181,9 +205,30 @@ lowhashSweepKernel(const SweepArgs a)
 
     if(threadIdx.x < kMaxFusedIterations) seedCount[threadIdx.x] = 0;
     if(threadIdx.x == 0) queueCount = 0;
-    for(int i = threadIdx.x; i < kSweepTile + kHalo; i += kSweepThreads) {
-        const uint64_t g = tileBase + i;
-        sk[i] = (g < a.markerCount) ? a.kmerIds[g] : 0u;
+    // Tile load: all of a thread's loads are issued before the first store (the load phase is one memory latency, not
+    // eight). Full tiles whose first id is 16-byte aligned are read as two uint4 per thread.
+    if(tileBase + kSweepTile <= a.markerCount && (reinterpret_cast<uintptr_t>(a.kmerIds + tileBase) & 15u) == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.kmerIds + tileBase);
+        const uint4 v0 = src[threadIdx.x], v1 = src[threadIdx.x + kSweepThreads];
+        uint32_t h = 0;
+        if(threadIdx.x < kHalo) { const uint64_t g = tileBase + kSweepTile + threadIdx.x; h = (g < a.markerCount) ? a.kmerIds[g] : 0u; }
+        reinterpret_cast<uint4*>(sk)[threadIdx.x] = v0;
+        reinterpret_cast<uint4*>(sk)[threadIdx.x + kSweepThreads] = v1;
+        if(threadIdx.x < kHalo) sk[kSweepTile + threadIdx.x] = h;
+    } else {
+        for(int i = threadIdx.x; i < kSweepTile + kHalo; i += kSweepThreads) {
+            const uint64_t g = tileBase + i;
+            sk[i] = (g < a.markerCount) ? a.kmerIds[g] : 0u;
+        }
+    }
+    // The reads that cover this tile: a tile of 2048 positions spans a few reads, so the oriented read of a queued position
+    // is found in a shared-memory copy of the toc entries from the tile's first read on (the first read of every tile comes
+    // from a table built once per marker set) instead of a 21-step binary search in global memory per low hash.
+    if(threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        const uint32_t lo = a.tileFirstRead[blockIdx.x];
+        tileToc[lane] = a.toc[min(lo + lane, a.orientedReadCount)];
+        if(lane == 0) { tileToc[kSweepTileReads] = a.toc[min(lo + uint32_t(kSweepTileReads), a.orientedReadCount)]; tileFirstRead = lo; }
     }
     __syncthreads();
 
@@ -227,8 +272,9 @@ lowhashSweepKernel(const SweepArgs a)
         uint32_t hitMask = 0;
 #pragma unroll
         for(uint32_t s = 0; s < ((KK > 0) ? uint32_t(KK) : K); s++) {
-            const U64Halves h = murmurAlmost<MM>(U64Halves{uint32_t(x0) ^ (seed0 + 37u * s), uint32_t(x0 >> 32)}, mixed, blocks, hasTail, tail);
-            hitMask |= (h.hi <= thresholdHigh) ? (1u << s) : 0u;
+            const U64Halves h = murmurAlmost<MM>(U64Halves{uint32_t(x0) ^ a.seeds[s], uint32_t(x0 >> 32)}, mixed, blocks, hasTail, tail);
+            // hitMask |= (h.hi <= thresholdHigh) << s, as one compare and one predicated or
+            asm("{\n\t.reg .pred q;\n\tsetp.le.u32 q, %1, %2;\n\t@q or.b32 %0, %0, %3;\n\t}" : "+r"(hitMask) : "r"(h.hi), "r"(thresholdHigh), "r"(1u << s));
         }
         // 16 mask bits per position, four positions per word.
         if(slot < 4) hitsA |= uint64_t(hitMask) << (16 * slot);
@@ -268,7 +314,20 @@ lowhashSweepKernel(const SweepArgs a)
         const uint32_t local = meta & 0xffffu, s = meta >> 16;
         // The complete hash and the exact test (the hot loop looked at the high word only).
         const uint64_t hash = featureHash<MM>(sk + local, m, seed0 + 37u * s, lenTimesM);
-        const uint32_t o = (hash < threshold) ? resolveFeature(a, tileBase + local, m) : 0xffffffffu;
+        uint32_t o = 0xffffffffu;
+        if(hash < threshold) {
+            const uint64_t p = tileBase + local;
+            int k = 0;
+#pragma unroll 1
+            while(k < kSweepTileReads && tileToc[k + 1] <= p) k++;          // largest k with toc[first + k] <= p
+            const uint32_t r = tileFirstRead + uint32_t(k);
+            if(k == kSweepTileReads || r >= a.orientedReadCount) o = resolveFeature(a, p, m);      // beyond the staged entries
+            else {
+                const bool inside = (p + m <= tileToc[k + 1]);
+                const bool palindromic = (a.readFlags[(a.orientedReadBase + r) >> 1] & 1u) != 0;
+                o = (inside && !palindromic) ? r : 0xffffffffu;
+            }
+        }
         queueHash[q] = hash;
         if(o != 0xffffffffu) {
             queueMeta[q] = atomicAdd(&seedCount[s], 1u) | (s << 24);
@@ -361,6 +420,136 @@ bucketPairsKernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
         if(readId1 <= readId0) continue;
         const uint32_t strand = (oread0 ^ oread1) & 1u;        // 0 = same strand
         pairsOut[out++] = (uint64_t(readId0) << 32) | (uint64_t(readId1) << 1) | strand;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7/a8 for configurations in which one overlapping read pair collides in MANY buckets of the same iteration (HiFi:
+// hashFraction 0.05 on low-error reads gives ~25 hits per pair and iteration, 3.3 G hits per iteration at 2 M reads): the
+// hits are counted per read in a shared-memory hash table, and only (pair, count) leaves the kernel.
+//   bucketSpanKernel    per entry: statistics as in bucketPairsKernel, and the entry's bucket [begin, begin + size) when the
+//                       bucket is eligible for pair generation (size 0 otherwise);
+//   readKeysKernel      (readId, entry index) for the stable sort that groups the entries by read;
+//   readPairsKernel     one warp per read: visits the buckets of the read's entries, counts the partners (readId1 > readId0,
+//                       equal hashHigh) in the table, then writes the table's (pair, count) items at a slot range reserved
+//                       with one atomic; *hits accumulates the number of hits counted (the reference's pair hits).
+static __global__ void __launch_bounds__(256)
+bucketSpanKernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n,
+                 uint64_t minBucketSize, uint64_t maxBucketSize, unsigned long long* __restrict__ stats, uint2* __restrict__ span)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const uint32_t bucket = uint32_t(keys[i] >> 32);
+    uint32_t begin = i, end = i + 1;
+    uint64_t size = 1;          // exact when <= maxBucketSize, else maxBucketSize + 1 = "crowded"
+    while(size <= maxBucketSize && begin > 0 && uint32_t(keys[begin - 1] >> 32) == bucket) { begin--; size++; }
+    while(size <= maxBucketSize && end < n && uint32_t(keys[end] >> 32) == bucket) { end++; size++; }
+    if(stats) {
+        const int cls = (size < minBucketSize) ? 0 : ((size > maxBucketSize) ? 2 : 1);
+        atomicAdd(&stats[3ull * (vals[i] >> 1) + cls], 1ull);
+    }
+    const uint64_t lowest = minBucketSize > 2 ? minBucketSize : 2;
+    const bool eligible = size >= lowest && size <= maxBucketSize;
+    span[i] = make_uint2(begin, eligible ? uint32_t(size) : 0u);
+}
+
+static __global__ void readKeysKernel(const uint32_t* __restrict__ vals, uint32_t n, uint64_t* __restrict__ readKeys, uint32_t* __restrict__ index)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    readKeys[i] = uint64_t(vals[i] >> 1);
+    index[i] = i;
+}
+
+constexpr uint32_t kPairTableSlots = 512;           // per warp; a power of two (a read has ~40 - 300 partners per iteration)
+constexpr uint32_t kPairTableLog2Slots = 9;
+constexpr uint32_t kPairTableWarps = 8;
+constexpr uint32_t kPairTableEmpty = 0xffffffffu;   // never a key: readId1 < 2^31
+constexpr uint32_t kPairTableMaxProbes = 24;
+
+static __global__ void __launch_bounds__(kPairTableWarps * 32)
+readPairsKernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint2* __restrict__ span,
+                const uint64_t* __restrict__ sortedReadKeys, const uint32_t* __restrict__ order,
+                const uint32_t* __restrict__ segStart, uint32_t numReads,
+                unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ hits,
+                uint64_t* __restrict__ outKeys, uint32_t* __restrict__ outCounts, unsigned long long capacity, uint32_t maxProbes)
+{
+    __shared__ uint32_t tableKeyAll[kPairTableWarps][kPairTableSlots];
+    __shared__ uint32_t tableCountAll[kPairTableWarps][kPairTableSlots];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t seg = blockIdx.x * kPairTableWarps + warp;
+    if(seg >= numReads) return;
+    uint32_t* tableKey = tableKeyAll[warp];
+    uint32_t* tableCount = tableCountAll[warp];
+#pragma unroll
+    for(uint32_t s = lane; s < kPairTableSlots; s += 32) { tableKey[s] = kPairTableEmpty; tableCount[s] = 0; }
+    __syncwarp();
+    const uint32_t a = segStart[seg], b = segStart[seg + 1];
+    const uint32_t readId0 = uint32_t(sortedReadKeys[a]);
+    uint32_t myHits = 0;
+    // 32 entries of the read at a time (one per lane), then entry by entry with the bucket's members spread over the lanes:
+    // the member loads are coalesced, and every lane works on every bucket.
+    for(uint32_t e0 = a; e0 < b; e0 += 32) {
+        uint32_t begin = 0, size = 0, hashHigh0 = 0, oread0 = 0;
+        if(e0 + lane < b) {
+            const uint32_t i = order[e0 + lane];
+            const uint2 sp = span[i];
+            begin = sp.x; size = sp.y;
+            if(size) { hashHigh0 = uint32_t(keys[i]); oread0 = vals[i]; }
+        }
+        unsigned live = __ballot_sync(0xffffffffu, size != 0);
+        while(live) {
+            const int t = __ffs(int(live)) - 1;
+            live &= live - 1u;
+            const uint32_t tBegin = __shfl_sync(0xffffffffu, begin, t), tSize = __shfl_sync(0xffffffffu, size, t);
+            const uint32_t tHash = __shfl_sync(0xffffffffu, hashHigh0, t), tRead = __shfl_sync(0xffffffffu, oread0, t);
+            for(uint32_t j = tBegin + lane; j < tBegin + tSize; j += 32) {
+                if(uint32_t(keys[j]) != tHash) continue;
+                const uint32_t oread1 = vals[j];
+                const uint32_t readId1 = oread1 >> 1;
+                if(readId1 <= readId0) continue;
+                const uint32_t k = (readId1 << 1) | ((tRead ^ oread1) & 1u);       // strand bit 0 = same strand
+                myHits++;
+                uint32_t slot = (k * 2654435761u) >> (32 - kPairTableLog2Slots);
+                uint32_t probes = 0;
+                for(;;) {
+                    const uint32_t prev = atomicCAS(&tableKey[slot], kPairTableEmpty, k);
+                    if(prev == kPairTableEmpty || prev == k) { atomicAdd(&tableCount[slot], 1u); break; }
+                    slot = (slot + 1u) & (kPairTableSlots - 1u);
+                    if(++probes >= maxProbes) {
+                        // Table (nearly) full: this hit goes out on its own; the merge adds the counts up.
+                        const unsigned long long at = atomicAdd(cursor, 1ull);
+                        if(at < capacity) { outKeys[at] = (uint64_t(readId0) << 32) | k; outCounts[at] = 1u; }
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // Occupied slots -> output: count them, reserve, write.
+    uint32_t occupied = 0;
+#pragma unroll
+    for(uint32_t s = lane; s < kPairTableSlots; s += 32) occupied += (tableKey[s] != kPairTableEmpty) ? 1u : 0u;
+    uint32_t inclusive = occupied, hitSum = myHits;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inclusive, d);
+        if(lane >= unsigned(d)) inclusive += t;
+    }
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1) hitSum += __shfl_down_sync(0xffffffffu, hitSum, d);
+    const uint32_t total = __shfl_sync(0xffffffffu, inclusive, 31);
+    if(lane == 0 && hitSum) atomicAdd(hits, (unsigned long long)hitSum);
+    if(total == 0) return;
+    unsigned long long base = 0;
+    if(lane == 31) base = atomicAdd(cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if(base + total > capacity) return;
+    unsigned long long out = base + (inclusive - occupied);
+    for(uint32_t s = lane; s < kPairTableSlots; s += 32) {
+        const uint32_t k = tableKey[s];
+        if(k != kPairTableEmpty) { outKeys[out] = (uint64_t(readId0) << 32) | k; outCounts[out] = tableCount[s]; out++; }
     }
 }
 

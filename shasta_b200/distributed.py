@@ -271,8 +271,7 @@ class CudaStages:
         C = self.C
         cand, n = C.c_void_p(), C.c_uint64()
         self._check(self.capi.lib().shb_lowhash_emit(self.ctx._h, C.byref(cand), C.byref(n)))
-        out = self.capi._records_to_array(cand, n.value)
-        self.capi.lib().shb_free(cand)
+        out = self.capi._records_to_array(cand, n.value)        # owns the buffer (shb_free when collected)
         return out
 
     def stats_tensor(self):

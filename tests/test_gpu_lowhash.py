@@ -64,6 +64,24 @@ def test_golden_with_forced_intermediate_reductions(ctx, golden_dir, monkeypatch
         assert np.array_equal(stats, g[name + "/stats"]), name
 
 
+@pytest.mark.parametrize("aggregate", ["0", "1", "overflow"])
+def test_golden_with_and_without_per_read_aggregation(ctx, golden_dir, monkeypatch, aggregate):
+    """Pair hits are either buffered raw (Nanopore-like hashFraction) or counted per read in shared memory first (HiFi-like);
+    both organisations must give the reference's candidates and statistics on every golden case, including the
+    candidate-driven iteration count."""
+    from shasta_b200 import capi
+    g = np.load(os.path.join(golden_dir, "lowhash_golden.npz"))
+    monkeypatch.setenv("SHB_LOWHASH_AGGREGATE", "0" if aggregate == "0" else "1")
+    if aggregate == "overflow":         # one probe only: every collision in the per-read table takes the single-hit path
+        monkeypatch.setenv("SHB_LOWHASH_TABLE_PROBES", "1")
+    for name, (spec, params) in MG.LOWHASH_CASES.items():
+        d = MG.load_input(spec)
+        ctx.set_markers(d["toc"], d["data"], d["flags"])
+        cand, stats, _, res = ctx.lowhash0(_params(capi, params))
+        assert np.array_equal(cand, g[name + "/candidates"]), name
+        assert np.array_equal(stats, g[name + "/stats"]), name
+
+
 @pytest.mark.parametrize("name", list(MG.LOWHASH_CASES))
 def test_golden_per_iteration_merge(ctx, name, golden_dir):
     from shasta_b200 import capi
