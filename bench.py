@@ -232,12 +232,14 @@ def run_reference(args, wl, rank):
 
 
 # The kernels that dominate the step (the banded / unbanded marker DPs) are bound by the integer ALU pipe, not by HBM or
-# the tensor cores (profiles/README.md: 89 % ALU-pipe busy, DRAM a few percent), so next to the contract's `roofline`
-# (the LowHash sweep, HBM by contract) the line carries the DP's own ceiling: the B200's integer ALU rate divided by the
-# ALU operations a DP cell needs.
+# the tensor cores (profiles/README.md: ALU pipe 72 % busy at 72 % issue, DRAM a few percent), so next to the contract's
+# `roofline` (the LowHash sweep, HBM by contract) the line carries the DP's own ceiling: the B200's integer ALU rate divided
+# by the ALU-pipe instructions a DP cell needs (counted in the SASS of the wavefront kernel's unchecked block,
+# profiles/r2_sass_banded1_unchecked_block.txt: ISETP x3, VIMNMX, VIADDMNMX per cell; the adds and the trace codes issue
+# on the FMA pipe as IMADs). Informational: the cells counted include the padding of the band classes.
 ALU_LANES_PER_SM = 64            # INT32 compare/select/min/max lanes per SM and clock (ncu: 2 warp instructions/clk/SM at 100 %)
 SM_COUNT = 148
-ALU_OPS_PER_CELL = 9             # equality test, score select, max, add-max, 2 compares, 2 code selects, trace insert
+ALU_OPS_PER_CELL = 5             # k-mer equality test, max, add-max, 2 trace compares
 
 
 def alignment_roofline(dp_cells, dp_ms, sm_mhz):
