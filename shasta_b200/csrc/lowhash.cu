@@ -305,7 +305,7 @@ void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsig
         const bool run = M >= S.p.m && M > 0;
         if(run) {
             SHB_CUDA(cudaEventRecord(sweepTimer.a, st));
-            launchSweep(a, ceilDiv(M, kSweepTile), st);
+            launchSweep(a, ceilDiv(ceilDiv(M, kSweepTile), uint64_t(kSweepTilesPerBlock)), st);
             SHB_CUDA(cudaEventRecord(sweepTimer.b, st));
             S.sweepLaunches++;
         }

@@ -185,58 +185,88 @@ __device__ __forceinline__ uint32_t resolveFeature(const SweepArgs& a, uint64_t 
 // output slot) is done afterwards by all threads of the block over the queue, one entry per lane, so a warp never
 // serialises behind one lane's rare path.
 // KK > 0: the number of fused iterations is a compile-time constant (fully unrolled seed loop); KK == 0: a.iterationCount.
+constexpr int kSweepTilesPerBlock = 4;      // consecutive tiles per block: the next tile streams into shared memory (cp.async)
+                                            // while the current one is hashed
+
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* globalSrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(uint32_t(__cvta_generic_to_shared(smemDst))), "l"(globalSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommitAndWaitNone() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template<int MM, int KK> __global__ void __launch_bounds__(kSweepThreads)
 lowhashSweepKernel(const SweepArgs a)
 {
     constexpr int kHalo = 2 * kMaxFusedIterations;       // >= any supported m (generic path caps m at 32)
-    __shared__ __align__(16) uint32_t sk[kSweepTile + kHalo];
+    __shared__ __align__(16) uint32_t skBuf[2][kSweepTile + kHalo];
     extern __shared__ uint64_t queueHash[];              // a.queueCapacity low hashes queued per block, then per entry:
     uint32_t* queueMeta = reinterpret_cast<uint32_t*>(queueHash + a.queueCapacity);   // in: local | s<<16   out: rank within (block, seed) | s<<24, or ~0
     uint32_t* queueRead = queueMeta + a.queueCapacity;                               // oriented read (global)
-    __shared__ uint32_t queueCount;
-    __shared__ unsigned long long tileToc[kSweepTileReads + 1];      // toc[tileFirstRead + k]
-    __shared__ uint32_t tileFirstRead;
-    __shared__ uint32_t seedCount[kMaxFusedIterations];
+    __shared__ uint32_t queueCountBuf[2];
+    __shared__ unsigned long long tileTocBuf[2][kSweepTileReads + 1];      // toc[tileFirstRead + k]
+    __shared__ uint32_t tileFirstReadBuf[2];
+    __shared__ uint32_t seedCountBuf[2][kMaxFusedIterations];
     __shared__ unsigned long long seedBase[kMaxFusedIterations];
 
     const uint64_t M = 0xc6a4a7935bd1e995ull;
     const uint32_t m = (MM > 0) ? uint32_t(MM) : a.m;
-    const uint64_t tileBase = uint64_t(blockIdx.x) * kSweepTile;
-
-    if(threadIdx.x < kMaxFusedIterations) seedCount[threadIdx.x] = 0;
-    if(threadIdx.x == 0) queueCount = 0;
-    // Tile load: all of a thread's loads are issued before the first store (the load phase is one memory latency, not
-    // eight). Full tiles whose first id is 16-byte aligned are read as two uint4 per thread.
-    if(tileBase + kSweepTile <= a.markerCount && (reinterpret_cast<uintptr_t>(a.kmerIds + tileBase) & 15u) == 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.kmerIds + tileBase);
-        const uint4 v0 = src[threadIdx.x], v1 = src[threadIdx.x + kSweepThreads];
-        uint32_t h = 0;
-        if(threadIdx.x < kHalo) { const uint64_t g = tileBase + kSweepTile + threadIdx.x; h = (g < a.markerCount) ? a.kmerIds[g] : 0u; }
-        reinterpret_cast<uint4*>(sk)[threadIdx.x] = v0;
-        reinterpret_cast<uint4*>(sk)[threadIdx.x + kSweepThreads] = v1;
-        if(threadIdx.x < kHalo) sk[kSweepTile + threadIdx.x] = h;
-    } else {
-        for(int i = threadIdx.x; i < kSweepTile + kHalo; i += kSweepThreads) {
-            const uint64_t g = tileBase + i;
-            sk[i] = (g < a.markerCount) ? a.kmerIds[g] : 0u;
-        }
-    }
-    // The reads that cover this tile: a tile of 2048 positions spans a few reads, so the oriented read of a queued position
-    // is found in a shared-memory copy of the toc entries from the tile's first read on (the first read of every tile comes
-    // from a table built once per marker set) instead of a 21-step binary search in global memory per low hash.
-    if(threadIdx.x < 32) {
-        const unsigned lane = threadIdx.x;
-        const uint32_t lo = a.tileFirstRead[blockIdx.x];
-        tileToc[lane] = a.toc[min(lo + lane, a.orientedReadCount)];
-        if(lane == 0) { tileToc[kSweepTileReads] = a.toc[min(lo + uint32_t(kSweepTileReads), a.orientedReadCount)]; tileFirstRead = lo; }
-    }
-    __syncthreads();
-
+    const uint32_t tileCount = uint32_t((a.markerCount + kSweepTile - 1) / kSweepTile);
+    const uint32_t firstTile = blockIdx.x * kSweepTilesPerBlock;
+    const uint32_t lastTile = min(firstTile + uint32_t(kSweepTilesPerBlock), tileCount);
     const uint32_t K = (KK > 0) ? uint32_t(KK) : a.iterationCount;
     const uint64_t lenTimesM = uint64_t(4u * m) * M;
     const uint64_t threshold = a.hashThreshold;
     const uint32_t thresholdHigh = uint32_t(threshold >> 32);
     const uint32_t seed0 = a.iterationBegin * 37u;                    // iteration * 37 fits 32 bits
+
+    // Streams tile t into buffer `buf`: full, 16-byte aligned tiles with cp.async (no registers, no wait here); the last or
+    // a misaligned tile with plain loads. Also stages the toc entries of the reads that cover the tile: a tile of 2048
+    // positions spans a few reads, so the oriented read of a queued position is found in a shared-memory copy of the toc
+    // entries from the tile's first read on (the first read of every tile comes from a table built once per marker set)
+    // instead of a 21-step binary search in global memory per low hash.
+    auto prefetchTile = [&](uint32_t t, int buf) {
+        const uint64_t base = uint64_t(t) * kSweepTile;
+        uint32_t* dst = skBuf[buf];
+        if(base + kSweepTile <= a.markerCount && (reinterpret_cast<uintptr_t>(a.kmerIds + base) & 15u) == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.kmerIds + base);
+            cpAsync16(reinterpret_cast<uint4*>(dst) + threadIdx.x, src + threadIdx.x);
+            cpAsync16(reinterpret_cast<uint4*>(dst) + threadIdx.x + kSweepThreads, src + threadIdx.x + kSweepThreads);
+            if(threadIdx.x < kHalo) { const uint64_t g = base + kSweepTile + threadIdx.x; dst[kSweepTile + threadIdx.x] = (g < a.markerCount) ? a.kmerIds[g] : 0u; }
+        } else {
+            for(int i = threadIdx.x; i < kSweepTile + kHalo; i += kSweepThreads) {
+                const uint64_t g = base + i;
+                dst[i] = (g < a.markerCount) ? a.kmerIds[g] : 0u;
+            }
+        }
+        cpAsyncCommitAndWaitNone();
+        if(threadIdx.x >= kSweepThreads - 32) {          // the last warp (the first ones own the halo loads)
+            const unsigned lane = threadIdx.x & 31u;
+            const uint32_t lo = a.tileFirstRead[t];
+            tileTocBuf[buf][lane] = a.toc[min(lo + lane, a.orientedReadCount)];
+            if(lane == 0) { tileTocBuf[buf][kSweepTileReads] = a.toc[min(lo + uint32_t(kSweepTileReads), a.orientedReadCount)]; tileFirstReadBuf[buf] = lo; }
+        }
+    };
+
+    if(threadIdx.x < 2 * kMaxFusedIterations) (&seedCountBuf[0][0])[threadIdx.x] = 0;
+    if(threadIdx.x < 2) queueCountBuf[threadIdx.x] = 0;
+    if(firstTile < lastTile) prefetchTile(firstTile, 0);
+
+    for(uint32_t tile = firstTile; tile < lastTile; tile++) {
+    const int cur = int(tile - firstTile) & 1;
+    cpAsyncWaitAll();
+    __syncthreads();            // tile `tile` is in skBuf[cur]; everybody is done with the previous tile (buffer cur ^ 1, the queue)
+    if(tile + 1 < lastTile) prefetchTile(tile + 1, cur ^ 1);
+    if(tile != firstTile) {     // counters of the other parity: last used by the previous tile, next used by the next one
+        if(threadIdx.x < kMaxFusedIterations) seedCountBuf[cur ^ 1][threadIdx.x] = 0;
+        if(threadIdx.x == 0) queueCountBuf[cur ^ 1] = 0;
+    }
+    const uint32_t* sk = skBuf[cur];
+    uint32_t& queueCount = queueCountBuf[cur];
+    uint32_t* seedCount = seedCountBuf[cur];
+    const unsigned long long* tileToc = tileTocBuf[cur];
+    const uint32_t tileFirstRead = tileFirstReadBuf[cur];
+    const uint64_t tileBase = uint64_t(tile) * kSweepTile;
 
     static_assert(kSweepPositionsPerThread <= 8 && kMaxFusedIterations <= 16, "hit masks: 16 bits x 8 positions");
     uint64_t hitsA = 0, hitsB = 0;
@@ -354,6 +384,7 @@ lowhashSweepKernel(const SweepArgs a)
             a.vals[uint64_t(s) * a.capacity + gi] = queueRead[q];
         }
     }
+    }   // tiles of this block
 }
 
 // ---------------------------------------------------------------------------------------------
