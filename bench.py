@@ -317,6 +317,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def allgather_floats(xs):
+        """Every rank's values (one row per rank)."""
+        t = torch.tensor([float(v) for v in xs], dtype=torch.float64, device="cuda")
+        if world == 1:
+            return [t.tolist()]
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return [q.tolist() for q in parts]
+
     def allsum_u64(x):
         """Sum of 64-bit digests over the ranks, mod 2^64 (gathered as two 32-bit halves: exact)."""
         x = int(x) & M64
@@ -432,6 +441,11 @@ def main():
     wall = allmax(wall)
     total_cand = allsum(len(cand))
     total_al = allsum(nal)
+    # Per-rank view of the timed steps (the aggregate keys below are maxima over the ranks, which do not add up): host-clock
+    # time inside the LowHash0 call (includes waiting for slower ranks in its collectives), inside the alignment call, the DP
+    # kernels' CUDA-event time, and the candidates each rank aligned.
+    per_rank = allgather_floats([1e3 * stats_acc["lowhash_s"] / args.steps, 1e3 * (stats_acc["align_s"] + stats_acc["gather_s"]) / args.steps,
+                                 stats_acc["dp_ms"] / args.steps, len(cand)])
     lowhash_s = allmax(stats_acc["lowhash_s"])
     align_s = allmax(stats_acc["align_s"] + stats_acc["gather_s"])
     value = total_cand * args.steps / wall
@@ -580,6 +594,8 @@ def main():
                      "useful_g_per_s": (dp_useful_all / (1e-3 * dp_ms_max) / 1e9) if dp_ms_max else None,
                      "note": "useful = in-band, in-matrix cells (what the reference's DP fills) + the unbanded stage-1 cells; computed also "
                              "counts the padding of the band classes to multiples of 64 offsets and the two barrier offsets"},
+        "per_rank_ms_per_step": {"lowhash_call": [round(r[0], 2) for r in per_rank], "alignment_call": [round(r[1], 2) for r in per_rank],
+                                 "dp_kernels": [round(r[2], 2) for r in per_rank], "candidates": [int(r[3]) for r in per_rank]},
         "gpu_launches": int(stats_acc["launches"]), "clocks": clocks.summary(),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }

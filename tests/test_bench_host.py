@@ -11,7 +11,7 @@ def test_alignment_roofline_arithmetic():
     r = bench.alignment_roofline(dp_cells=3e12, dp_ms=3000.0, sm_mhz=1965.0)
     assert r["bound"] == "alu" and r["unit"] == "G cell updates/s"
     assert abs(r["achieved"] - 1000.0) < 1e-6
-    assert abs(r["peak"] - 148 * 64 * 1.965e9 / 9 / 1e9) < 1e-6
+    assert abs(r["peak"] - 148 * 64 * 1.965e9 / bench.ALU_OPS_PER_CELL / 1e9) < 1e-6 and bench.ALU_OPS_PER_CELL == 5
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert bench.alignment_roofline(0, 0.0, 1965.0) is None
     assert bench.alignment_roofline(1e9, 1.0, None)["peak"] == r["peak"]      # falls back to the B200's 1965 MHz
