@@ -444,8 +444,10 @@ def main():
     # Per-rank view of the timed steps (the aggregate keys below are maxima over the ranks, which do not add up): host-clock
     # time inside the LowHash0 call (includes waiting for slower ranks in its collectives), inside the alignment call, the DP
     # kernels' CUDA-event time, and the candidates each rank aligned.
+    own_clocks = clocks.summary()
     per_rank = allgather_floats([1e3 * stats_acc["lowhash_s"] / args.steps, 1e3 * (stats_acc["align_s"] + stats_acc["gather_s"]) / args.steps,
-                                 stats_acc["dp_ms"] / args.steps, len(cand)])
+                                 stats_acc["dp_ms"] / args.steps, len(cand), own_clocks.get("sm_mhz") or 0.0,
+                                 1.0 if "sw_power_cap" in (own_clocks.get("reasons") or []) else 0.0])
     lowhash_s = allmax(stats_acc["lowhash_s"])
     align_s = allmax(stats_acc["align_s"] + stats_acc["gather_s"])
     value = total_cand * args.steps / wall
@@ -595,7 +597,8 @@ def main():
                      "note": "useful = in-band, in-matrix cells (what the reference's DP fills) + the unbanded stage-1 cells; computed also "
                              "counts the padding of the band classes to multiples of 64 offsets and the two barrier offsets"},
         "per_rank_ms_per_step": {"lowhash_call": [round(r[0], 2) for r in per_rank], "alignment_call": [round(r[1], 2) for r in per_rank],
-                                 "dp_kernels": [round(r[2], 2) for r in per_rank], "candidates": [int(r[3]) for r in per_rank]},
+                                 "dp_kernels": [round(r[2], 2) for r in per_rank], "candidates": [int(r[3]) for r in per_rank],
+                                 "sm_mhz": [r[4] for r in per_rank], "sw_power_cap_seen": [int(r[5]) for r in per_rank]},
         "gpu_launches": int(stats_acc["launches"]), "clocks": clocks.summary(),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }
