@@ -204,7 +204,11 @@ def run_reference(args, wl, rank):
     if rank != 0:
         return
     from shasta_b200 import synth
-    p = synth_params(wl, reads=min(CPU_SAMPLE_READS, wl["reads"]), seed=2)
+    # Bounded sample: the whole --steps K --warmup W run should end within a few minutes. One pass over the 20 000-read sample
+    # takes ~25 s on the box's 128 threads (time is linear in the reads at fixed coverage), so the sample shrinks with K + W.
+    budget_s, full_sample_s = 240.0, 25.0
+    reads = int(CPU_SAMPLE_READS * min(1.0, budget_s / (max(1, args.steps + args.warmup) * full_sample_s)))
+    p = synth_params(wl, reads=min(max(reads, 2000), wl["reads"]), seed=2)
     d = synth.generate(p)
     cores = os.cpu_count()
     for _ in range(args.warmup):

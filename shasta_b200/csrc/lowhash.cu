@@ -324,8 +324,9 @@ void lowhashSweep(shb_context* c, uint64_t iterationBegin, uint32_t group, unsig
 }
 
 // passes 2 and 3 on one iteration's entries (keys = bucketId<<32 | hashHigh, vals = orientedReadId), which must all
-// belong to buckets owned by this GPU: bucket sort, per-read statistics, pair hits, unique (pair,count) appended to the
-// local accumulator. keysA/valsA are clobbered.
+// belong to buckets owned by this GPU: bucket sort, per-read statistics, and the pair hits — appended raw to the pair
+// buffer (sorted and counted once for many iterations) or, for HiFi-like hash fractions, counted per read in shared memory
+// and appended as (pair, count) to the local accumulator. keysA/valsA are clobbered.
 void lowhashProcessEntries(shb_context* c, uint64_t* keysA, uint32_t* valsA, uint64_t n64)
 {
     LowHashState& S = lowhashState(c);
