@@ -298,6 +298,20 @@ shb_status shb_compute_alignment_table(shb_context* ctx, const void* alignmentDa
 shb_status shb_compute_candidate_table(shb_context* ctx, const void* candidates, uint64_t candidateCount,
                                        uint64_t readCount, uint64_t** tableToc, uint64_t** tableData);
 
+/* Replaces Assembler::createReadGraph, ReadGraph.creationMethod 0 (src/AssemblerReadGraph.cpp:35-175): for each read the
+ * best maxAlignmentCount alignments by (markerCount, alignmentId), both descending, are kept; an alignment kept by either
+ * of its reads becomes two read graph edges (the edge and its reverse complement), in alignmentId order.
+ *   alignmentData    : n 64-byte AlignmentData records (host), IN/OUT: AlignmentInfo::isInReadGraph is set / cleared.
+ *   keep             : receives uint8[n] (1 = used in the read graph).
+ *   edges            : receives edgeCount 16-byte ReadGraphEdge records (src/ReadGraph.hpp:37-57) = Data/ReadGraphEdges payload.
+ *   connectivityToc  : receives uint32[2*readCount+1]; connectivityData: uint32[2*edgeCount] = Data/ReadGraphConnectivity
+ *                      (.toc/.data payload, VectorOfVectors<uint32_t,uint32_t>): per oriented read its edge indices, increasing.
+ * Free the four arrays with shb_free. (creationMethod 2, createReadGraph2, is not implemented.)
+ */
+shb_status shb_create_read_graph(shb_context* ctx, void* alignmentData, uint64_t alignmentCount, uint64_t readCount,
+                                 uint32_t maxAlignmentCount, uint8_t** keep, void** edges, uint64_t* edgeCount,
+                                 uint32_t** connectivityToc, uint32_t** connectivityData);
+
 /* ------------------------------------------------------------------------------------------
  * Read-sharded multi-GPU runs (BASELINE.json configs[2..4]): one process (and one context) per GPU,
  * NCCL over NVLink / NVSwitch for the two exchanges LowHash0 needs (bucket entries per iteration, pair counts once) and

@@ -446,6 +446,23 @@ def oracle_compute_candidate_table(candidates, read_count):
     return toc, table[:4 * len(cand)].copy()
 
 
+def oracle_create_read_graph(records, read_count, max_alignment_count):
+    """Assembler::createReadGraph, creationMethod 0 (src/AssemblerReadGraph.cpp:35-175). records uint32[n,16] is NOT modified.
+    Returns (records with isInReadGraph set, keep uint8[n], edges uint32[E,4], connectivityToc uint32[2R+1], connectivityData uint32[2E])."""
+    lib = _olib()
+    rec = np.ascontiguousarray(records, np.uint32).reshape(-1, 16).copy()
+    n = len(rec)
+    keep = np.zeros(n + 1, np.uint8)
+    edges = np.zeros((2 * n + 1, 4), np.uint32)
+    toc = np.zeros(2 * read_count + 1, np.uint32)
+    data = np.zeros(4 * n + 1, np.uint32)
+    lib.orc_create_read_graph.restype = C.c_uint64
+    lib.orc_create_read_graph.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    e = lib.orc_create_read_graph(rec.ctypes.data, n, read_count, int(max_alignment_count), keep.ctypes.data, edges.ctypes.data,
+                                  toc.ctypes.data, data.ctypes.data)
+    return rec, keep[:n].copy(), edges[:e].copy(), toc, data[:2 * e].copy()
+
+
 def set_dp_policy(bits):
     """Tie-break policy of the oracle's DP at run time (include/shb_dp_policy.h: bit 0 diagonal wins ties, bit 1 vertical
     before horizontal, bit 2 first maximum is the end cell). Returns the previous policy."""

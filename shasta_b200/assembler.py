@@ -245,6 +245,27 @@ class Assembler:
         mm_write_vector_of_vectors(self._name("CandidateTable"), toc, table, data_object_size=8, toc_dtype=np.uint64,
                                    page_size=self.page_size)
 
+    def createReadGraph(self, maxAlignmentCount, maxTrim=0):
+        """Assembler::createReadGraph (src/AssemblerReadGraph.cpp:35-175; ReadGraph.creationMethod 0; maxTrim is unused there
+        too). Sets AlignmentInfo::isInReadGraph in Data/AlignmentData and writes Data/ReadGraphEdges (16-byte ReadGraphEdge) and
+        Data/ReadGraphConnectivity.{toc,data} (VectorOfVectors<uint32_t,uint32_t>)."""
+        from . import capi
+        self.checkMarkersAreOpen()
+        if self._alignment_data is None:
+            raise RuntimeError("Alignment data are not accessible.")
+        rec = np.ascontiguousarray(np.array(self._alignment_data, np.uint32)).reshape(-1, 16)
+        try:
+            keep, edges, toc, data = capi.create_read_graph(self._context(), rec, len(self._markers[2]), maxAlignmentCount)
+        except capi.ShastaB200Error as e:
+            raise RuntimeError(str(e)) from None
+        self._alignment_data = rec
+        self._read_graph = (np.array(edges), np.array(toc), np.array(data))
+        mm_write_vector(self._name("AlignmentData"), rec, object_size=64, page_size=self.page_size)
+        mm_write_vector(self._name("ReadGraphEdges"), np.array(edges), object_size=16, page_size=self.page_size)
+        mm_write_vector_of_vectors(self._name("ReadGraphConnectivity"), np.array(toc), np.array(data), data_object_size=4,
+                                   toc_dtype=np.uint32, page_size=self.page_size)
+        return int(keep.sum())
+
     # ------------------------------------------------------------------ the two hot-path entry points
     def findAlignmentCandidatesLowHash0(self, m, hashFraction, minHashIterationCount, alignmentCandidatesPerRead,
                                         minBucketSize, maxBucketSize, minFrequency, log2MinHashBucketCount=0, threadCount=0):

@@ -129,6 +129,8 @@ def lib():
         L.shb_align_oriented_reads.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(AlignOptions), C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_uint64), C.c_void_p]
         L.shb_compute_candidate_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shb_create_read_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.shb_digest_records.restype = C.c_uint64
         L.shb_digest_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
         L.shb_digest_compressed.restype = C.c_uint64
@@ -433,6 +435,23 @@ def compute_alignment_table(ctx: Context, records, read_count):
     lib().shb_free(toc)
     lib().shb_free(data)
     return tocn, datan
+
+
+def create_read_graph(ctx: Context, records, read_count, max_alignment_count):
+    """Assembler::createReadGraph, ReadGraph.creationMethod 0 (shb_create_read_graph). records uint32[n,16] must be a writable,
+    C-contiguous array: AlignmentInfo::isInReadGraph is updated in place.
+    Returns (keep uint8[n], edges uint32[E,4] = 16-byte ReadGraphEdge records, connectivityToc uint32[2R+1], connectivityData uint32[2E])."""
+    assert records.dtype == np.uint32 and records.flags["C_CONTIGUOUS"] and records.flags["WRITEABLE"]
+    rec = records.reshape(-1, 16)
+    keep, edges, toc, data = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    e = C.c_uint64()
+    _check(lib().shb_create_read_graph(ctx._h, _ptr(rec), len(rec), int(read_count), int(max_alignment_count), C.byref(keep), C.byref(edges),
+                                       C.byref(e), C.byref(toc), C.byref(data)))
+    keepn = _owned_array(keep, len(rec), np.uint8)
+    edgesn = _owned_array(edges, 4 * e.value, np.uint32).reshape(-1, 4)
+    tocn = _owned_array(toc, 2 * int(read_count) + 1, np.uint32)
+    datan = _owned_array(data, 2 * e.value, np.uint32)
+    return keepn, edgesn, tocn, datan
 
 
 def align_oriented_reads(ctx: Context, oriented_read_id0, oriented_read_id1, options: AlignOptions):

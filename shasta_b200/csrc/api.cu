@@ -36,6 +36,8 @@ void findMarkers(shb_context* c, uint32_t k, uint64_t readCount, const uint64_t*
                  const uint64_t* baseCounts, const uint8_t* kmerTable24, const uint32_t* isMarkerBitmap,
                  const uint8_t* readFlags, uint64_t** tocOut, uint8_t** data7Out, shb_marker_result* result);
 void computeCandidateTable(shb_context* c, const void* candidates, uint64_t n, uint64_t readCount, uint64_t** tocOut, uint64_t** dataOut);
+void createReadGraph(shb_context* c, void* alignmentData, uint64_t n, uint64_t readCount, uint32_t maxAlignmentCount,
+                     uint8_t** keepOut, void** edgesOut, uint64_t* edgeCountOut, uint32_t** connectivityTocOut, uint32_t** connectivityDataOut);
 
 template<class F> shb_status guarded(F&& f)
 {
@@ -392,6 +394,17 @@ shb_status shb_compute_candidate_table(shb_context* c, const void* candidates, u
     return guarded([&] {
         SHB_REQUIRE(c && tableToc && tableData && (candidates || candidateCount == 0), SHB_ERR_INVALID, "Null argument.");
         computeCandidateTable(c, candidates, candidateCount, readCount, tableToc, tableData);
+    });
+}
+
+shb_status shb_create_read_graph(shb_context* c, void* alignmentData, uint64_t alignmentCount, uint64_t readCount,
+                                 uint32_t maxAlignmentCount, uint8_t** keep, void** edges, uint64_t* edgeCount,
+                                 uint32_t** connectivityToc, uint32_t** connectivityData)
+{
+    return guarded([&] {
+        SHB_REQUIRE(c && keep && edges && edgeCount && connectivityToc && connectivityData && (alignmentData || alignmentCount == 0),
+                    SHB_ERR_INVALID, "Null argument.");
+        createReadGraph(c, alignmentData, alignmentCount, readCount, maxAlignmentCount, keep, edges, edgeCount, connectivityToc, connectivityData);
     });
 }
 

@@ -151,6 +151,17 @@ def test_script_sequence_on_reference_data_dir(tmp_path, golden_dir):
     assert np.array_equal(rec, orec) and np.array_equal(toc, otoc) and np.array_equal(data, odata)
     table_toc = A.mm_read_vector(prefix + "AlignmentTable.toc", np.uint32, object_size=4)
     assert len(table_toc) == 2 * 20 + 1 and int(table_toc[-1]) == 4 * len(rec)
+    # srcMain/main.cpp:717-741 (ReadGraph.creationMethod 0): createReadGraph continues from the alignments
+    kept = b.createReadGraph(maxAlignmentCount=3, maxTrim=30)
+    wrec, wkeep, wedges, wtoc, wdata = B.oracle_create_read_graph(rec, 20, 3)
+    assert kept == int(wkeep.sum()) and 0 < kept < len(rec)
+    e = A.Assembler(largeDataFileNamePrefix=prefix)
+    e.accessAlignmentData()
+    assert np.array_equal(e._alignment_data, wrec)
+    edges = np.asarray(A.mm_read_vector(prefix + "ReadGraphEdges", np.uint32, object_size=16)).reshape(-1, 4)
+    ctoc = np.asarray(A.mm_read_vector(prefix + "ReadGraphConnectivity.toc", np.uint32, object_size=4))
+    cdata = np.asarray(A.mm_read_vector(prefix + "ReadGraphConnectivity.data", np.uint32, object_size=4))
+    assert np.array_equal(edges, wedges) and np.array_equal(ctoc, wtoc) and np.array_equal(cdata, wdata)
     # srcMain/main.cpp:706: computeCandidateTable after the candidates are known
     b.computeCandidateTable()
     ct_toc = np.asarray(A.mm_read_vector(prefix + "CandidateTable.toc", np.uint64, object_size=8))
