@@ -312,6 +312,21 @@ shb_status shb_create_read_graph(shb_context* ctx, void* alignmentData, uint64_t
                                  uint32_t maxAlignmentCount, uint8_t** keep, void** edges, uint64_t* edgeCount,
                                  uint32_t** connectivityToc, uint32_t** connectivityData);
 
+/* Replaces Assembler::createReadGraph2, ReadGraph.creationMethod 2 (src/AssemblerReadGraph2.cpp:69-248): the selection of
+ * shb_create_read_graph over the alignments that pass five thresholds read off histograms of the alignments' quality
+ * indicators (setReadGraph2Criteria); `criteria` receives the thresholds (Assembler::actualMinAlignedFraction ...,
+ * src/Assembler.hpp:154-158). Percentile arguments in the member's order; the other arguments as in shb_create_read_graph.
+ */
+typedef struct shb_read_graph2_criteria {
+    double minAlignedFraction;
+    uint64_t minAlignedMarkerCount, maxDrift, maxSkip, maxTrim;
+} shb_read_graph2_criteria;
+shb_status shb_create_read_graph2(shb_context* ctx, void* alignmentData, uint64_t alignmentCount, uint64_t readCount,
+                                  uint32_t maxAlignmentCount, double markerCountPercentile, double alignedFractionPercentile,
+                                  double maxSkipPercentile, double maxDriftPercentile, double maxTrimPercentile,
+                                  shb_read_graph2_criteria* criteria, uint8_t** keep, void** edges, uint64_t* edgeCount,
+                                  uint32_t** connectivityToc, uint32_t** connectivityData);
+
 /* ------------------------------------------------------------------------------------------
  * Read-sharded multi-GPU runs (BASELINE.json configs[2..4]): one process (and one context) per GPU,
  * NCCL over NVLink / NVSwitch for the two exchanges LowHash0 needs (bucket entries per iteration, pair counts once) and

@@ -463,6 +463,55 @@ def oracle_create_read_graph(records, read_count, max_alignment_count):
     return rec, keep[:n].copy(), edges[:e].copy(), toc, data[:2 * e].copy()
 
 
+def oracle_create_read_graph2(records, read_count, max_alignment_count, percentiles):
+    """Assembler::createReadGraph2, creationMethod 2 (src/AssemblerReadGraph2.cpp:69-248). percentiles = (markerCount,
+    alignedFraction, maxSkip, maxDrift, maxTrim). Returns (criteria dict, records, keep, edges, connectivityToc, connectivityData)."""
+    lib = _olib()
+    rec = np.ascontiguousarray(records, np.uint32).reshape(-1, 16).copy()
+    n = len(rec)
+    keep = np.zeros(n + 1, np.uint8)
+    edges = np.zeros((2 * n + 1, 4), np.uint32)
+    toc = np.zeros(2 * read_count + 1, np.uint32)
+    data = np.zeros(4 * n + 1, np.uint32)
+    pc = np.array(percentiles, np.float64)
+    crit = np.zeros(5, np.uint64)
+    lib.orc_create_read_graph2.restype = C.c_uint64
+    lib.orc_create_read_graph2.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+    e = lib.orc_create_read_graph2(rec.ctypes.data, n, read_count, int(max_alignment_count), pc.ctypes.data, crit.ctypes.data,
+                                   keep.ctypes.data, edges.ctypes.data, toc.ctypes.data, data.ctypes.data)
+    criteria = dict(minAlignedFraction=float(crit[:1].view(np.float64)[0]), minAlignedMarkerCount=int(crit[1]), maxDrift=int(crit[2]),
+                    maxSkip=int(crit[3]), maxTrim=int(crit[4]))
+    return criteria, rec, keep[:n].copy(), edges[:e].copy(), toc, data[:2 * e].copy()
+
+
+def oracle_histogram2_threshold(x, start, stop, bin_count, fraction):
+    lib = _olib()
+    x = np.ascontiguousarray(x, np.float64)
+    lib.orc_histogram2_threshold.restype = C.c_double
+    lib.orc_histogram2_threshold.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_uint64, C.c_double]
+    return lib.orc_histogram2_threshold(x.ctypes.data, len(x), start, stop, bin_count, fraction)
+
+
+def ref_histogram2_threshold(x, start, stop, bin_count, fraction):
+    """The reference's own Histogram2 (dynamic bounds), compiled unmodified (oracle/_ref)."""
+    lib = _rlib()
+    x = np.ascontiguousarray(x, np.float64)
+    lib.ref_histogram2_threshold.restype = C.c_double
+    lib.ref_histogram2_threshold.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_uint64, C.c_double]
+    return lib.ref_histogram2_threshold(x.ctypes.data, len(x), start, stop, bin_count, fraction)
+
+
+def ref_alignment_indicators(record16):
+    """(minAlignedFraction, markerCount, maxDrift, maxSkip, trim) by the reference's AlignmentInfo accessors."""
+    lib = _rlib()
+    rec = np.ascontiguousarray(record16, np.uint32).reshape(16)
+    out = np.zeros(5, np.float64)
+    lib.ref_alignment_indicators.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ref_alignment_indicators(rec.ctypes.data, out.ctypes.data)
+    return out
+
+
 def set_dp_policy(bits):
     """Tie-break policy of the oracle's DP at run time (include/shb_dp_policy.h: bit 0 diagonal wins ties, bit 1 vertical
     before horizontal, bit 2 first maximum is the end cell). Returns the previous policy."""

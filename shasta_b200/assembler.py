@@ -266,6 +266,35 @@ class Assembler:
                                    toc_dtype=np.uint32, page_size=self.page_size)
         return int(keep.sum())
 
+    def createReadGraph2(self, maxAlignmentCount, markerCountPercentile, alignedFractionPercentile, maxSkipPercentile,
+                         maxDriftPercentile, maxTrimPercentile):
+        """Assembler::createReadGraph2 (src/AssemblerReadGraph2.cpp:182-248, Python src/PythonModule.cpp:366-367;
+        ReadGraph.creationMethod 2). Same outputs as createReadGraph; the automatically selected criteria are kept in
+        self.readGraph2Criteria and printed like the reference does (:155-160)."""
+        from . import capi
+        self.checkMarkersAreOpen()
+        if self._alignment_data is None:
+            raise RuntimeError("Alignment data are not accessible.")
+        rec = np.ascontiguousarray(np.array(self._alignment_data, np.uint32)).reshape(-1, 16)
+        try:
+            crit, keep, edges, toc, data = capi.create_read_graph2(self._context(), rec, len(self._markers[2]), maxAlignmentCount,
+                                                                  markerCountPercentile, alignedFractionPercentile, maxSkipPercentile,
+                                                                  maxDriftPercentile, maxTrimPercentile)
+        except capi.ShastaB200Error as e:
+            raise RuntimeError(str(e)) from None
+        self.readGraph2Criteria = crit
+        print("Automatically selected alignment criteria:\n\tminAlignedFraction:\t%g\n\tminAlignedMarkerCount:\t\t%d\n\tmaxDrift:\t\t%d\n"
+              "\tmaxSkip:\t\t%d\n\tmaxTrim:\t\t%d" % (crit["minAlignedFraction"], crit["minAlignedMarkerCount"], crit["maxDrift"],
+                                                   crit["maxSkip"], crit["maxTrim"]))
+        print("Keeping %d alignments of %d" % (int(keep.sum()), len(rec)))
+        self._alignment_data = rec
+        self._read_graph = (np.array(edges), np.array(toc), np.array(data))
+        mm_write_vector(self._name("AlignmentData"), rec, object_size=64, page_size=self.page_size)
+        mm_write_vector(self._name("ReadGraphEdges"), np.array(edges), object_size=16, page_size=self.page_size)
+        mm_write_vector_of_vectors(self._name("ReadGraphConnectivity"), np.array(toc), np.array(data), data_object_size=4,
+                                   toc_dtype=np.uint32, page_size=self.page_size)
+        return int(keep.sum())
+
     # ------------------------------------------------------------------ the two hot-path entry points
     def findAlignmentCandidatesLowHash0(self, m, hashFraction, minHashIterationCount, alignmentCandidatesPerRead,
                                         minBucketSize, maxBucketSize, minFrequency, log2MinHashBucketCount=0, threadCount=0):

@@ -454,6 +454,37 @@ def create_read_graph(ctx: Context, records, read_count, max_alignment_count):
     return keepn, edgesn, tocn, datan
 
 
+class ReadGraph2Criteria(C.Structure):
+    _fields_ = [("minAlignedFraction", C.c_double), ("minAlignedMarkerCount", C.c_uint64), ("maxDrift", C.c_uint64),
+                ("maxSkip", C.c_uint64), ("maxTrim", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def create_read_graph2(ctx: Context, records, read_count, max_alignment_count, marker_count_percentile, aligned_fraction_percentile,
+                       max_skip_percentile, max_drift_percentile, max_trim_percentile):
+    """Assembler::createReadGraph2, ReadGraph.creationMethod 2 (shb_create_read_graph2). records as in create_read_graph.
+    Returns (criteria dict, keep, edges, connectivityToc, connectivityData)."""
+    assert records.dtype == np.uint32 and records.flags["C_CONTIGUOUS"] and records.flags["WRITEABLE"]
+    rec = records.reshape(-1, 16)
+    keep, edges, toc, data = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    e = C.c_uint64()
+    crit = ReadGraph2Criteria()
+    f = lib().shb_create_read_graph2
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                  C.POINTER(ReadGraph2Criteria), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    _check(f(ctx._h, _ptr(rec), len(rec), int(read_count), int(max_alignment_count), float(marker_count_percentile),
+             float(aligned_fraction_percentile), float(max_skip_percentile), float(max_drift_percentile), float(max_trim_percentile),
+             C.byref(crit), C.byref(keep), C.byref(edges), C.byref(e), C.byref(toc), C.byref(data)))
+    keepn = _owned_array(keep, len(rec), np.uint8)
+    edgesn = _owned_array(edges, 4 * e.value, np.uint32).reshape(-1, 4)
+    tocn = _owned_array(toc, 2 * int(read_count) + 1, np.uint32)
+    datan = _owned_array(data, 2 * e.value, np.uint32)
+    return crit.asdict(), keepn, edgesn, tocn, datan
+
+
 def align_oriented_reads(ctx: Context, oriented_read_id0, oriented_read_id1, options: AlignOptions):
     """Single pair in the orientation given (shb_align_oriented_reads). Returns (ordinals uint32[n,2], info uint32[13])."""
     ords = C.c_void_p()

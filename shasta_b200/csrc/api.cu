@@ -1,5 +1,6 @@
 // C ABI (include/shasta_b200.h): argument checking, exception -> status translation, marker upload.
 #include "context.cuh"
+#include <vector>
 #include "lowhash_kernels.cuh"
 #include "hostpool.cuh"
 #include "digest.cuh"
@@ -37,7 +38,9 @@ void findMarkers(shb_context* c, uint32_t k, uint64_t readCount, const uint64_t*
                  const uint8_t* readFlags, uint64_t** tocOut, uint8_t** data7Out, shb_marker_result* result);
 void computeCandidateTable(shb_context* c, const void* candidates, uint64_t n, uint64_t readCount, uint64_t** tocOut, uint64_t** dataOut);
 void createReadGraph(shb_context* c, void* alignmentData, uint64_t n, uint64_t readCount, uint32_t maxAlignmentCount,
+                     const uint8_t* eligibleHost,
                      uint8_t** keepOut, void** edgesOut, uint64_t* edgeCountOut, uint32_t** connectivityTocOut, uint32_t** connectivityDataOut);
+void readGraph2Criteria(const uint32_t* rec, uint64_t n, const double* percentiles, shb_read_graph2_criteria& out, std::vector<uint8_t>& eligible);
 
 template<class F> shb_status guarded(F&& f)
 {
@@ -404,7 +407,25 @@ shb_status shb_create_read_graph(shb_context* c, void* alignmentData, uint64_t a
     return guarded([&] {
         SHB_REQUIRE(c && keep && edges && edgeCount && connectivityToc && connectivityData && (alignmentData || alignmentCount == 0),
                     SHB_ERR_INVALID, "Null argument.");
-        createReadGraph(c, alignmentData, alignmentCount, readCount, maxAlignmentCount, keep, edges, edgeCount, connectivityToc, connectivityData);
+        createReadGraph(c, alignmentData, alignmentCount, readCount, maxAlignmentCount, nullptr, keep, edges, edgeCount, connectivityToc, connectivityData);
+    });
+}
+
+shb_status shb_create_read_graph2(shb_context* c, void* alignmentData, uint64_t alignmentCount, uint64_t readCount,
+                                  uint32_t maxAlignmentCount, double markerCountPercentile, double alignedFractionPercentile,
+                                  double maxSkipPercentile, double maxDriftPercentile, double maxTrimPercentile,
+                                  shb_read_graph2_criteria* criteria, uint8_t** keep, void** edges, uint64_t* edgeCount,
+                                  uint32_t** connectivityToc, uint32_t** connectivityData)
+{
+    return guarded([&] {
+        SHB_REQUIRE(c && criteria && keep && edges && edgeCount && connectivityToc && connectivityData && (alignmentData || alignmentCount == 0),
+                    SHB_ERR_INVALID, "Null argument.");
+        const double percentiles[5] = {markerCountPercentile, alignedFractionPercentile, maxSkipPercentile, maxDriftPercentile, maxTrimPercentile};
+        std::vector<uint8_t> eligible;
+        readGraph2Criteria(static_cast<const uint32_t*>(alignmentData), alignmentCount, percentiles, *criteria, eligible);
+        eligible.push_back(0);      // never an empty array
+        createReadGraph(c, alignmentData, alignmentCount, readCount, maxAlignmentCount, eligible.data(), keep, edges, edgeCount,
+                        connectivityToc, connectivityData);
     });
 }
 

@@ -8,11 +8,17 @@
 //   * an alignment is kept when it is among the best of EITHER of its reads (:77-85); kept alignments get
 //     AlignmentInfo::isInReadGraph (:103) and two edges each, in alignmentId order (:110-140);
 //   * ReadGraphConnectivity: for every oriented read the indices of its edges in increasing order (:147-159).
+// Assembler::createReadGraph2, ReadGraph.creationMethod 2 (src/AssemblerReadGraph2.cpp:182-248; what Nanopore-May2022.conf and
+// Nanopore-UL-May2022.conf select): the same selection over the alignments that pass five thresholds, which are read off
+// histograms of the alignments' quality indicators at given percentiles (setReadGraph2Criteria, :99-179). The histograms are
+// filled in alignment order on the host (Histogram2 with dynamic bounds is order dependent, see DynamicHistogram below).
 #include "context.cuh"
 #include "hostpool.cuh"
 
+#include <cmath>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace shb {
 namespace {
@@ -20,12 +26,15 @@ namespace {
 constexpr uint32_t kAlignmentWords = 16;            // 64-byte AlignmentData
 constexpr uint32_t kMarkerCountWord = 9;            // readIds[2], isSameStrand, AlignmentInfo: data[2] (6 words), markerCount
 
-__global__ void readGraphItemsKernel(const uint32_t* __restrict__ records, uint32_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+constexpr uint32_t kNoRead = 0x7fffffffu;           // items of alignments that fail the creation-method-2 criteria sort behind every read
+
+__global__ void readGraphItemsKernel(const uint32_t* __restrict__ records, const uint8_t* __restrict__ eligible, uint32_t n,
+                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if(j >= 2 * n) return;
     const uint32_t a = n - 1u - (j >> 1);               // alignment ids in descending order
-    const uint32_t readId = records[uint64_t(kAlignmentWords) * a + (j & 1u)];
+    const uint32_t readId = (eligible && !eligible[a]) ? kNoRead : records[uint64_t(kAlignmentWords) * a + (j & 1u)];
     const uint32_t markerCount = records[uint64_t(kAlignmentWords) * a + kMarkerCountWord];
     keys[j] = (uint64_t(readId) << 32) | (0xffffffffu - markerCount);
     vals[j] = a;
@@ -37,6 +46,7 @@ __global__ void readGraphKeepKernel(const uint64_t* __restrict__ sortedKeys, con
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= items) return;
     const uint64_t readKey = sortedKeys[i] & 0xffffffff00000000ull;
+    if(uint32_t(readKey >> 32) == kNoRead) return;
     uint32_t lo = 0, hi = i;                            // first item of this read
     while(lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if(sortedKeys[mid] < readKey) lo = mid + 1; else hi = mid; }
     if(i - lo < maxAlignmentCount) keep[sortedVals[i]] = 1u;
@@ -77,9 +87,83 @@ struct HostBlocks {         // frees what was not handed to the caller (error pa
     void disarm() { for(void*& q : p) q = nullptr; }
 };
 
+// shasta::Histogram2 (src/Histogram.cpp:14-140) as createReadGraph2 uses it: dynamicBounds = true. update() grows the
+// histogram to `index` bins when index > size and then increments bin `index` — which, for index >= the size before the call,
+// lies one past the end: the reference's write lands outside the deque and the sample is never seen by getSum() /
+// thresholdByCumulativeProportion(). So a sample is counted iff its index is below max(initial bins, every earlier index):
+// the content depends on the order of the updates, and this class reproduces it for the reference's (alignment id) order.
+class DynamicHistogram {
+public:
+    DynamicHistogram(double start, double stop, uint64_t binCount) : start(start), binSize((stop - start) / double(binCount)), bins(binCount, 0) {}
+    void update(double x)
+    {
+        const int64_t index = int64_t(std::floor((x - start) / binSize));
+        if(index < 0) return;                                   // not reachable for the five indicators (all >= 0)
+        if(uint64_t(index) > bins.size()) bins.resize(uint64_t(index), 0);
+        if(uint64_t(index) < bins.size()) bins[uint64_t(index)]++;
+    }
+    double thresholdByCumulativeProportion(double fraction) const
+    {
+        uint64_t total = 0;
+        for(uint64_t v : bins) total += v;
+        double cumulativeSum = 0;
+        uint64_t i;
+        for(i = 0; i < bins.size(); i++) {
+            cumulativeSum += double(bins[i]);
+            if(double(cumulativeSum) / double(total) >= fraction) break;
+        }
+        return start + binSize * double(i) + binSize / 2;
+    }
+private:
+    double start, binSize;
+    std::vector<uint64_t> bins;
+};
+
+struct AlignmentIndicators { double minAlignedFraction; uint32_t markerCount, maxDrift, maxSkip, trim; };
+
+// AlignmentInfo accessors (src/Alignment.hpp:103-121, 252-284) on the 13 info words of a 64-byte record.
+AlignmentIndicators indicators(const uint32_t* rec)
+{
+    const uint32_t* d0 = rec + 3; const uint32_t* d1 = rec + 6;         // Data: markerCount, firstOrdinal, lastOrdinal
+    AlignmentIndicators r;
+    r.markerCount = rec[9]; r.maxSkip = rec[13]; r.maxDrift = rec[14];
+    const double f0 = double(r.markerCount) / double(d0[2] + 1 - d0[1]), f1 = double(r.markerCount) / double(d1[2] + 1 - d1[1]);
+    r.minAlignedFraction = std::min(f0, f1);
+    const uint32_t leftTrim = std::min(d0[1], d1[1]), rightTrim = std::min(d0[0] - 1 - d0[2], d1[0] - 1 - d1[2]);
+    r.trim = std::max(leftTrim, rightTrim);
+    return r;
+}
+
 } // namespace
 
+// setReadGraph2Criteria (src/AssemblerReadGraph2.cpp:99-179) + passesReadGraph2Criteria (:69-96): thresholds, and which
+// alignments pass them. percentiles = markerCount, alignedFraction, maxSkip, maxDrift, maxTrim (the member's argument order).
+void readGraph2Criteria(const uint32_t* rec, uint64_t n, const double* percentiles, shb_read_graph2_criteria& out, std::vector<uint8_t>& eligible)
+{
+    DynamicHistogram alignedFraction(0, 1, 100), markerCount(0, 3000, 300), maxDrift(0, 100, 100), maxSkip(0, 100, 100), maxTrim(0, 100, 100);
+    for(uint64_t i = 0; i < n; i++) {
+        const AlignmentIndicators a = indicators(rec + kAlignmentWords * i);
+        alignedFraction.update(a.minAlignedFraction);
+        markerCount.update(a.markerCount);
+        maxDrift.update(a.maxDrift);
+        maxSkip.update(a.maxSkip);
+        maxTrim.update(a.trim);
+    }
+    out.minAlignedFraction = alignedFraction.thresholdByCumulativeProportion(percentiles[1]);
+    out.minAlignedMarkerCount = uint64_t(std::round(markerCount.thresholdByCumulativeProportion(percentiles[0])));
+    out.maxDrift = uint64_t(std::round(maxDrift.thresholdByCumulativeProportion(1 - percentiles[3])));
+    out.maxSkip = uint64_t(std::round(maxSkip.thresholdByCumulativeProportion(1 - percentiles[2])));
+    out.maxTrim = uint64_t(std::round(maxTrim.thresholdByCumulativeProportion(1 - percentiles[4])));
+    eligible.resize(n);
+    for(uint64_t i = 0; i < n; i++) {
+        const AlignmentIndicators a = indicators(rec + kAlignmentWords * i);
+        eligible[i] = !(a.minAlignedFraction < out.minAlignedFraction) && !(a.markerCount < out.minAlignedMarkerCount) &&
+                      !(a.maxDrift > out.maxDrift) && !(a.maxSkip > out.maxSkip) && !(a.trim > out.maxTrim);
+    }
+}
+
 void createReadGraph(shb_context* c, void* alignmentData, uint64_t n, uint64_t readCount, uint32_t maxAlignmentCount,
+                     const uint8_t* eligibleHost,
                      uint8_t** keepOut, void** edgesOut, uint64_t* edgeCountOut, uint32_t** connectivityTocOut, uint32_t** connectivityDataOut)
 {
     SHB_REQUIRE(4 * n < (1ull << 32), SHB_ERR_INVALID, "Too many alignments for one read graph (limit 2^30-1).");
@@ -97,6 +181,7 @@ void createReadGraph(shb_context* c, void* alignmentData, uint64_t n, uint64_t r
                     "One of the alignments refers to a read that does not exist.");
     }
     DeviceBuffer<uint32_t> dRec, valsA, valsB, keep, keepIndex, scanWs, dToc, dEdges;
+    DeviceBuffer<uint8_t> dEligible;
     DeviceBuffer<uint64_t> keysA, keysB;
     const uint32_t items = uint32_t(2 * n);
     uint32_t edgeCount = 0;
@@ -107,10 +192,13 @@ void createReadGraph(shb_context* c, void* alignmentData, uint64_t n, uint64_t r
         SHB_CUDA(cudaMemcpyAsync(dRec.get(), rec, 4ull * kAlignmentWords * n, cudaMemcpyHostToDevice, st));
         SHB_CUDA(cudaMemsetAsync(keep.get(), 0, 4ull * n, st));
         if(maxAlignmentCount) {
-            SHB_LAUNCH(readGraphItemsKernel, ceilDiv(items, 256), 256, 0, st, (const uint32_t*)dRec.get(), uint32_t(n), keysA.get(), valsA.get());
-            uint32_t readBits = 1;
-            while((1ull << readBits) < readCount) readBits++;
-            const int ranges[2][2] = {{0, 32}, {32, 32 + int(readBits)}};
+            if(eligibleHost) {
+                dEligible.reserve(n);
+                SHB_CUDA(cudaMemcpyAsync(dEligible.get(), eligibleHost, n, cudaMemcpyHostToDevice, st));
+            }
+            SHB_LAUNCH(readGraphItemsKernel, ceilDiv(items, 256), 256, 0, st, (const uint32_t*)dRec.get(),
+                       (const uint8_t*)(eligibleHost ? dEligible.get() : nullptr), uint32_t(n), keysA.get(), valsA.get());
+            const int ranges[2][2] = {{0, 32}, {32, 63}};          // read id (or the "no read" mark) in 31 bits
             const bool inB = radixSort<true>(keysA.get(), keysB.get(), valsA.get(), valsB.get(), items, ranges, 2, c->sortWs, st);
             SHB_LAUNCH(readGraphKeepKernel, ceilDiv(items, 256), 256, 0, st, (const uint64_t*)(inB ? keysB.get() : keysA.get()),
                        (const uint32_t*)(inB ? valsB.get() : valsA.get()), items, maxAlignmentCount, keep.get());

@@ -162,6 +162,15 @@ def test_script_sequence_on_reference_data_dir(tmp_path, golden_dir):
     ctoc = np.asarray(A.mm_read_vector(prefix + "ReadGraphConnectivity.toc", np.uint32, object_size=4))
     cdata = np.asarray(A.mm_read_vector(prefix + "ReadGraphConnectivity.data", np.uint32, object_size=4))
     assert np.array_equal(edges, wedges) and np.array_equal(ctoc, wtoc) and np.array_equal(cdata, wdata)
+    # ... and ReadGraph.creationMethod 2 (srcMain/main.cpp:731-739), the one the May2022 configurations select
+    f = A.Assembler(largeDataFileNamePrefix=prefix)
+    f.accessMarkers()
+    f.accessAlignmentData()
+    kept2 = f.createReadGraph2(3, 0.015, 0.12, 0.12, 0.12, 0.015)
+    crit2, wrec2, wkeep2, wedges2, wtoc2, wdata2 = B.oracle_create_read_graph2(rec, 20, 3, (0.015, 0.12, 0.12, 0.12, 0.015))
+    assert kept2 == int(wkeep2.sum()) and f.readGraph2Criteria == crit2
+    edges2 = np.asarray(A.mm_read_vector(prefix + "ReadGraphEdges", np.uint32, object_size=16)).reshape(-1, 4)
+    assert np.array_equal(edges2, wedges2)
     # srcMain/main.cpp:706: computeCandidateTable after the candidates are known
     b.computeCandidateTable()
     ct_toc = np.asarray(A.mm_read_vector(prefix + "CandidateTable.toc", np.uint64, object_size=8))

@@ -49,3 +49,19 @@ def test_on_computed_alignments(ctx):
     assert len(rec) > 500
     for k in (1, 6, 20):
         _check(ctx, np.array(rec, np.uint32), 400, k)
+
+
+def test_creation_method_2(ctx):
+    """createReadGraph2: thresholds from the histograms (host, alignment order) + the device selection over the alignments that pass."""
+    from shasta_b200 import capi
+    from test_oracle_readgraph import _quality_records
+    rng = np.random.default_rng(21)
+    pc = (0.015, 0.12, 0.12, 0.12, 0.015)
+    for n, reads, k in [(0, 4, 6), (400, 30, 6), (3000, 120, 6), (3000, 120, 2), (150000, 6000, 6)]:
+        rec = _quality_records(rng, n, reads)
+        ocrit, orec, okeep, oedges, otoc, odata = B.oracle_create_read_graph2(rec, reads, k, pc)
+        work = rec.copy()
+        crit, keep, edges, toc, data = capi.create_read_graph2(ctx, work, reads, k, *pc)
+        assert crit == ocrit
+        assert np.array_equal(keep, okeep) and np.array_equal(edges, oedges)
+        assert np.array_equal(toc, otoc) and np.array_equal(data, odata) and np.array_equal(work, orec)
