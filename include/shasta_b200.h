@@ -306,7 +306,7 @@ shb_status shb_compute_candidate_table(shb_context* ctx, const void* candidates,
  *   edges            : receives edgeCount 16-byte ReadGraphEdge records (src/ReadGraph.hpp:37-57) = Data/ReadGraphEdges payload.
  *   connectivityToc  : receives uint32[2*readCount+1]; connectivityData: uint32[2*edgeCount] = Data/ReadGraphConnectivity
  *                      (.toc/.data payload, VectorOfVectors<uint32_t,uint32_t>): per oriented read its edge indices, increasing.
- * Free the four arrays with shb_free. (creationMethod 2, createReadGraph2, is not implemented.)
+ * Free the four arrays with shb_free. (creationMethod 2: shb_create_read_graph2 below.)
  */
 shb_status shb_create_read_graph(shb_context* ctx, void* alignmentData, uint64_t alignmentCount, uint64_t readCount,
                                  uint32_t maxAlignmentCount, uint8_t** keep, void** edges, uint64_t* edgeCount,
