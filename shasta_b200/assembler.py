@@ -76,6 +76,33 @@ def mm_write_vector_of_vectors(name, toc, data, data_object_size=None, toc_dtype
     mm_write_vector(name + ".data", data, object_size=data_object_size, page_size=page_size)
 
 
+def _ostream_double(x):
+    """A double as C++'s `ostream << double` prints it with default flags (precision 6, %g)."""
+    return "%g" % x
+
+
+def write_read_low_hash_statistics_csv(path, stats, marker_toc, read_flags, m):
+    """ReadLowHashStatistics.csv as LowHash0 writes it (src/LowHash0.cpp:220-243). stats: uint64[R,3]; marker_toc: the Markers toc
+    (2R+1 entries); read_flags: uint8[R] (bit 0 = palindromic)."""
+    stats = np.asarray(stats, np.uint64).reshape(-1, 3)
+    toc = np.asarray(marker_toc, np.uint64)
+    with open(path, "w") as csv:
+        csv.write("ReadId,Palindromic,Features,Sparse,Good,Crowded,Total,FeatureSampling,SparseFraction,GoodFraction,CrowdedFraction\n")
+        for read_id in range(len(stats)):
+            c = [int(v) for v in stats[read_id]]
+            # std::accumulate(..., 0): the sum is carried in an int and converted to uint64_t (src/LowHash0.cpp:224)
+            total = (sum(c) + 2**31) % 2**32 - 2**31
+            total &= 2**64 - 1
+            feature_count = (int(toc[2 * read_id + 1]) - int(toc[2 * read_id]) - (m - 1)) & (2**64 - 1)
+            sampling = float(total) / float(feature_count) if feature_count else (float("nan") if total == 0 else float("inf"))
+            row = [str(read_id), "Yes" if (int(read_flags[read_id]) & 1) else "No", str(feature_count), str(c[0]), str(c[1]), str(c[2]),
+                   str(total), _ostream_double(sampling).replace("nan", "-nan" if total == 0 and feature_count == 0 else "nan")]
+            if total == 0:
+                csv.write(",".join(row) + ",,,\n")
+            else:
+                csv.write(",".join(row) + "," + ",".join(_ostream_double(float(v) / float(total)) for v in c) + "\n")
+
+
 class AlignOptions:
     """shasta.AlignOptions (src/PythonModule.cpp:85-107; defaults src/AssemblerOptions.cpp:380-489)."""
 
@@ -319,6 +346,8 @@ class Assembler:
         rec = cand.copy()          # 12-byte OrientedReadPair records: third word = isSameStrand byte + zero padding
         mm_write_vector(self._name("AlignmentCandidates"), rec, object_size=12, page_size=self.page_size)
         mm_write_vector(self._name("ReadLowHashStatistics"), stats, object_size=24, page_size=self.page_size)
+        # the reference also leaves ReadLowHashStatistics.csv in the working directory (src/LowHash0.cpp:220-243)
+        write_read_low_hash_statistics_csv("ReadLowHashStatistics.csv", stats, self._markers[0], self._markers[2], m)
 
     def computeAlignments(self, alignOptions, threadCount=0):
         """Assembler::computeAlignments (src/AssemblerAlign.cpp:208-304). Writes Data/AlignmentData,
