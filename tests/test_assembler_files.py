@@ -112,7 +112,8 @@ def test_companion_accessors_with_stubbed_device(tmp_path, golden_dir, monkeypat
 
 
 @pytest.mark.gpu
-def test_script_sequence_on_reference_data_dir(tmp_path, golden_dir):
+def test_script_sequence_on_reference_data_dir(tmp_path, golden_dir, monkeypatch):
+    monkeypatch.chdir(tmp_path)         # like the reference, the facade leaves ReadLowHashStatistics.csv in the working directory
     # scripts/FindAlignmentCandidatesLowHash0.py + scripts/ComputeAlignments.py call sequence. The Data/ inputs are written
     # with the facade's writer from the golden TinyTest markers (the reference tree is not on the GPU box).
     z = np.load(os.path.join(golden_dir, "tinytest_markers.npz"))
