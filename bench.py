@@ -260,6 +260,23 @@ def alignment_roofline(dp_cells, dp_ms, sm_mhz):
                            % (SM_COUNT, ALU_LANES_PER_SM, sm_mhz or 1965.0, ALU_OPS_PER_CELL)}
 
 
+def gpu_numa_cpus(torch, device_index):
+    """(numa node, CPUs) of the NUMA node the GPU hangs off — what `numactl --cpunodebind` would be given — or (None, None)."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return node, cpus
+    except Exception:
+        return None, None
+
+
 def _claim_stdout():
     """stdout carries exactly one JSON line. Libraries (NCCL prints its version banner) write to fd 1 directly, so fd 1
     is pointed at stderr for the whole run and the JSON line goes to a private copy of the original stdout."""
@@ -301,6 +318,19 @@ def main():
     from shasta_b200 import distributed as D
 
     torch.cuda.set_device(local_rank)
+    # Process placement: the rank's host threads (and the memory they first touch: pinned marker buffer, result blocks) on the
+    # CPUs of the GPU's own NUMA node, as `numactl --cpunodebind=<node of the GPU>` would do for a production process. The CPU
+    # baseline / parity legs below run with the original mask (all host cores). SHB_BENCH_NO_AFFINITY=1 turns it off.
+    affinity_all = os.sched_getaffinity(0)
+    affinity_gpu, numa_node = None, None
+    if not os.environ.get("SHB_BENCH_NO_AFFINITY"):
+        numa_node, cpus = gpu_numa_cpus(torch, local_rank)
+        if cpus and len(cpus & affinity_all) >= 8:
+            affinity_gpu = cpus & affinity_all
+            try:
+                os.sched_setaffinity(0, affinity_gpu)
+            except OSError:
+                affinity_gpu = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -533,6 +563,8 @@ def main():
         dms = capi.synth_generate_device(ctx, ps, want_data7=True)
         d = {"toc": dms.toc, "data": dms.data7_to_host(), "flags": dms.flags, "kmer": dms.kmer_ids_to_host()}
         cores = os.cpu_count()
+        if affinity_gpu:
+            os.sched_setaffinity(0, affinity_all)          # the CPU path gets every host core
         r = cpu_reference_once(d, cores, MINHASH, ALIGN, keep=True)
         n, sec_l, nalc, sec_a, kind = r["candidates"], r["lowhash_s"], r["alignments"], r["align_s"], r["kind"]
         Ms = int(d["toc"][-1])
@@ -603,6 +635,8 @@ def main():
         "per_rank_ms_per_step": {"lowhash_call": [round(r[0], 2) for r in per_rank], "alignment_call": [round(r[1], 2) for r in per_rank],
                                  "dp_kernels": [round(r[2], 2) for r in per_rank], "candidates": [int(r[3]) for r in per_rank],
                                  "sm_mhz": [r[4] for r in per_rank], "sw_power_cap_seen": [int(r[5]) for r in per_rank]},
+        "host_placement": {"numa_node_of_gpu": numa_node, "cpus_bound": (len(affinity_gpu) if affinity_gpu else None),
+                           "note": "timed legs run with the rank's threads bound to the CPUs of its GPU's NUMA node; the CPU legs use all host cores"},
         "gpu_launches": int(stats_acc["launches"]), "clocks": clocks.summary(),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }
