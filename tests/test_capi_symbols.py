@@ -45,3 +45,28 @@ def test_product_does_not_import_oracle():
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
             for line_no, line in enumerate(open(path), 1):
                 assert not forbidden.search(line), f"{path}:{line_no}: {line.strip()}"
+
+
+def declared_parameter_counts():
+    counts = {}
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        for name, params in re.findall(r"\b(shb_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+            params = params.strip()
+            counts[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return counts
+
+
+def test_ctypes_argument_lists_match_the_header():
+    """Every binding that declares argtypes passes as many arguments as the prototype in include/shasta_b200.h has."""
+    from shasta_b200 import capi
+    lib = capi.lib()
+    counts = declared_parameter_counts()
+    assert counts["shb_lowhash0"] == 8 and counts["shb_last_error"] == 0
+    checked = 0
+    for name, n in counts.items():
+        argtypes = getattr(lib, name).argtypes
+        if argtypes is not None:
+            assert len(argtypes) == n, f"{name}: {len(argtypes)} ctypes arguments, {n} in the header"
+            checked += 1
+    assert checked >= 15
