@@ -210,7 +210,7 @@ def run_reference(args, wl, rank):
     reads = int(CPU_SAMPLE_READS * min(1.0, budget_s / (max(1, args.steps + args.warmup) * full_sample_s)))
     p = synth_params(wl, reads=min(max(reads, 2000), wl["reads"]), seed=2)
     d = synth.generate(p)
-    cores = os.cpu_count()
+    cores = effective_cpus()          # threads = the CPUs the container may use (quota), not the logical CPU count
     for _ in range(args.warmup):
         cpu_reference_once(d, cores, wl["minhash"], wl["align"])
     tl = ta = 0.0
@@ -229,7 +229,7 @@ def run_reference(args, wl, rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64/i32", "data": "synthetic",
         "config": {"workload": args.workload, "minhash": wl["minhash"], "align": wl["align"], "sample": sample},
         "lowhash_pairs_per_s": n * args.steps / tl, "aligned_pairs_per_s": n * args.steps / ta,
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "host_logical_cpus": os.cpu_count(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -258,6 +258,25 @@ def alignment_roofline(dp_cells, dp_ms, sm_mhz):
             "achieved": achieved, "peak": peak, "unit": "G cell updates/s", "frac": achieved / peak,
             "peak_source": "%d SMs x %d integer-ALU lanes x %.0f MHz / %d ALU operations per DP cell"
                            % (SM_COUNT, ALU_LANES_PER_SM, sm_mhz or 1965.0, ALU_OPS_PER_CELL)}
+
+
+def effective_cpus():
+    """Host CPUs this process can actually use: the affinity mask, capped by the container's CFS quota (cgroup v2 cpu.max or
+    v1 cpu.cfs_quota_us / cpu.cfs_period_us). The pool's 1-GPU boxes show 128 logical CPUs under a quota of 16."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, -(-quota // period)))
+        except Exception:
+            pass
+    return n
 
 
 def gpu_numa_cpus(torch, device_index):
@@ -562,13 +581,13 @@ def main():
         # Same generator as the numpy one (bit-identical), run on the device to save minutes of host time.
         dms = capi.synth_generate_device(ctx, ps, want_data7=True)
         d = {"toc": dms.toc, "data": dms.data7_to_host(), "flags": dms.flags, "kmer": dms.kmer_ids_to_host()}
-        cores = os.cpu_count()
+        cores = effective_cpus()          # threads = the CPUs the container may use (quota), not the logical CPU count
         if affinity_gpu:
             os.sched_setaffinity(0, affinity_all)          # the CPU path gets every host core
         r = cpu_reference_once(d, cores, MINHASH, ALIGN, keep=True)
         n, sec_l, nalc, sec_a, kind = r["candidates"], r["lowhash_s"], r["alignments"], r["align_s"], r["kind"]
         Ms = int(d["toc"][-1])
-        cpu_baseline = {"value": n / (sec_l + sec_a), "unit": "pairs/s", "cores": cores, "kind": kind,
+        cpu_baseline = {"value": n / (sec_l + sec_a), "unit": "pairs/s", "cores": cores, "host_logical_cpus": os.cpu_count(), "kind": kind,
                         "sample": f"{ps.reads} synthetic reads ({Ms} markers both strands, same coverage/config), {n} candidates, "
                                   f"{nalc} stored alignments; LowHash0 {sec_l:.2f} s ({kind}: unmodified reference TUs), "
                                   f"alignment {sec_a:.2f} s (port: reference control flow + SeqAn stand-in DP)",
