@@ -22,3 +22,16 @@ def test_workloads_name_the_baseline_configuration():
     assert wl["reads"] == 1000000
     assert bench.MINHASH_MAY2022["m"] == 4 and bench.MINHASH_MAY2022["minHashIterationCount"] == 10
     assert bench.ALIGN_MAY2022["alignMethod"] == 3 and bench.ALIGN_MAY2022["downsamplingFactor"] == 0.05
+
+
+def test_effective_cpus_and_placement_helpers():
+    import os
+    n = bench.effective_cpus()
+    assert 1 <= n <= len(os.sched_getaffinity(0))
+
+    class NoCuda:           # a torch stand-in without a device: the helper must answer "unknown", never raise
+        class cuda:
+            @staticmethod
+            def get_device_properties(i):
+                raise RuntimeError("no device")
+    assert bench.gpu_numa_cpus(NoCuda, 0) == (None, None)
